@@ -1,0 +1,67 @@
+/* libspg -- C-ABI of the B200-native hot path behind StarkEx Perpetual.
+ *
+ * Every entry point names the reference interface it stands in for (paths relative to the
+ * reference repo starkware-libs/stark-perpetual).  Conventions:
+ *   - field elements ("felts") cross the boundary as 4 x uint64 little-endian limbs holding the
+ *     CANONICAL value in [0, p), p = 2^251 + 17*2^192 + 1; the *_be32 variants use the
+ *     reference's own byte ABI, 32-byte big-endian (fast_pedersen_hash.py:47-52,
+ *     starkware/python/utils.py:414-451);
+ *   - buffers are caller-owned and contiguous; they are host memory unless SPG_DEVICE_PTRS is set
+ *     in `flags`, in which case they are device pointers on the context's GPU;
+ *   - every function returns 0 or a negative SPG_E* code and never throws; spg_last_error()
+ *     gives the message.  There is NO CPU fallback: without a CUDA device spg_create fails.
+ *   - per-element outcomes of batched calls are reported in `status` arrays (one byte each) so
+ *     the Python layer can raise exactly the exception the reference raises.
+ */
+#ifndef SPG_H
+#define SPG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spg_ctx spg_ctx;
+
+#define SPG_OK 0
+#define SPG_E_CUDA (-1)      /* CUDA runtime error, see spg_last_error */
+#define SPG_E_ARG (-2)       /* bad argument */
+#define SPG_E_NOMEM (-3)
+#define SPG_E_NODEVICE (-4)
+#define SPG_E_PROOF (-5)     /* prover could not build a proof (e.g. trace does not satisfy the AIR) */
+
+#define SPG_DEVICE_PTRS 1    /* flags: buffers are device pointers */
+
+/* NTT orderings */
+#define SPG_NTT_NAT_TO_REV 0 /* natural order in, bit-reversed out (DIF) */
+#define SPG_NTT_REV_TO_NAT 1 /* bit-reversed in, natural out (DIT) */
+#define SPG_NTT_NAT_TO_NAT 2 /* natural in, natural out (DIF + permutation) */
+
+int spg_create(int device_ordinal, spg_ctx** out);
+void spg_destroy(spg_ctx* ctx);
+const char* spg_last_error(spg_ctx* ctx);
+int spg_device_count(void);
+/* device milliseconds (CUDA events on the context stream) spent in kernels by the last call */
+double spg_last_kernel_ms(spg_ctx* ctx);
+/* number of kernel launches issued by this context since creation */
+uint64_t spg_launch_count(spg_ctx* ctx);
+int spg_synchronize(spg_ctx* ctx);
+
+/* ---- field layer (a1/a2 of SURVEY section 8; signature.py:41-42, math_utils.py:50-56) ----------------- */
+/* out[i] = op(a[i], b[i]); op: 0 mul, 1 add, 2 sub, 3 inverse of a (b ignored), 4 a^b[0..3] */
+int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n,
+                 int flags);
+/* throughput probe: every thread runs `iters` dependent Montgomery multiplications on `chains`
+ * independent accumulators; returns field multiplications per second in *mul_per_s. */
+int spg_bench_field_mul(spg_ctx* ctx, int iters, int chains, double* mul_per_s, double* imad_wide_per_s);
+
+/* ---- NTT over the STARK prime (no reference symbol, field from signature.py:41-42) */
+/* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
+ * inverse != 0 uses omega^-1 and scales by 2^-log_n. */
+int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batch, int inverse, int order, int flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,47 @@
+"""ctypes loader of the plain-C oracle (oracle/c/spg_oracle.c).  TEST INFRASTRUCTURE."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libspg_oracle.so")
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.spgo_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads():
+    return lib().spgo_num_threads()
+
+
+def mul_batch(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    out = np.empty_like(a)
+    lib().spgo_mul_batch(_p(a), _p(b), _p(out), C.c_size_t(a.shape[0]))
+    return out
+
+
+def ntt(data, log_n, inverse=False, order=2):
+    arr = np.array(data, dtype=np.uint64, order="C", copy=True).reshape(-1, 4)
+    n = 1 << log_n
+    lib().spgo_ntt(_p(arr), C.c_uint(log_n), C.c_size_t(arr.shape[0] // n), C.c_int(int(inverse)), C.c_int(order))
+    return arr

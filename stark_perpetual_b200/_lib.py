@@ -1,0 +1,158 @@
+"""ctypes binding of libspg.so (include/spg.h).  Fails loudly when the library or a GPU is missing."""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_LOCK = threading.Lock()
+
+FIELD_PRIME = 2**251 + 17 * 2**192 + 1
+
+SPG_DEVICE_PTRS = 1
+NTT_NAT_TO_REV, NTT_REV_TO_NAT, NTT_NAT_TO_NAT = 0, 1, 2
+
+
+class SpgError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libspg.so")
+
+
+def _load():
+    global _LIB
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        path = lib_path()
+        if not os.path.exists(path):
+            raise SpgError(
+                "libspg.so not built (%s missing): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C stark_perpetual_b200/csrc`. There is no CPU fallback." % path)
+        lib = C.CDLL(path)
+        u64p, u8p, vp = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.c_void_p
+        sig = {
+            "spg_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+            "spg_destroy": (None, [vp]),
+            "spg_last_error": (C.c_char_p, [vp]),
+            "spg_device_count": (C.c_int, []),
+            "spg_last_kernel_ms": (C.c_double, [vp]),
+            "spg_launch_count": (C.c_uint64, [vp]),
+            "spg_synchronize": (C.c_int, [vp]),
+            "spg_field_op": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_bench_field_mul": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+            "spg_ntt": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_int, C.c_int, C.c_int]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(lib, name)     # AttributeError if the symbol is missing: loud by design
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+        return lib
+
+
+# ---- felt <-> numpy helpers -------------------------------------------------------------------
+def ints_to_limbs(values):
+    """list of Python ints in [0, 2^256) -> (n, 4) uint64 little-endian limbs."""
+    buf = b"".join(int(v).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype="<u8").reshape(-1, 4).copy()
+
+
+def limbs_to_ints(arr):
+    a = np.ascontiguousarray(arr, dtype="<u8").reshape(-1, 4)
+    raw = a.tobytes()
+    return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(a.shape[0])]
+
+
+def _ptr(arr):
+    return arr.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One spg_ctx (one GPU, one stream)."""
+
+    def __init__(self, device=0):
+        self._lib = _load()
+        h = C.c_void_p()
+        rc = self._lib.spg_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self._lib.spg_last_error(h).decode() if h else ""
+            if h:
+                self._lib.spg_destroy(h)
+            raise SpgError("spg_create(device=%d) failed with %d %s -- a CUDA device is required, "
+                           "there is no CPU fallback" % (device, rc, msg))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.spg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SpgError("libspg error %d: %s" % (rc, self._lib.spg_last_error(self._h).decode()))
+
+    @property
+    def last_kernel_ms(self):
+        return self._lib.spg_last_kernel_ms(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.spg_launch_count(self._h))
+
+    def synchronize(self):
+        self._check(self._lib.spg_synchronize(self._h))
+
+    # ---- field layer ----
+    def field_op(self, op, a, b=None):
+        """a, b: (n,4) uint64 canonical felts. op: 'mul','add','sub','inv','pow'."""
+        code = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "pow": 4}[op]
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        out = np.empty_like(a)
+        bp = None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.uint64)
+            assert b.shape == a.shape
+            bp = _ptr(b)
+        self._check(self._lib.spg_field_op(self._h, code, _ptr(a), bp, _ptr(out), a.shape[0], 0))
+        return out
+
+    def bench_field_mul(self, iters=2000, chains=4):
+        m, w = C.c_double(), C.c_double()
+        self._check(self._lib.spg_bench_field_mul(self._h, iters, chains, C.byref(m), C.byref(w)))
+        return m.value, w.value
+
+    # ---- NTT ----
+    def ntt(self, data, log_n, inverse=False, order=NTT_NAT_TO_NAT):
+        """data: (batch * 2^log_n, 4) uint64 canonical felts; returns a new array."""
+        arr = np.array(data, dtype=np.uint64, order="C", copy=True).reshape(-1, 4)
+        n = 1 << log_n
+        assert arr.shape[0] % n == 0
+        self._check(self._lib.spg_ntt(self._h, _ptr(arr), log_n, arr.shape[0] // n, int(bool(inverse)), order, 0))
+        return arr
+
+    def ntt_device(self, dev_ptr, log_n, batch, inverse=False, order=NTT_NAT_TO_REV):
+        """In-place transform of device-resident data (pointer from torch .data_ptr())."""
+        self._check(self._lib.spg_ntt(self._h, C.c_void_p(dev_ptr), log_n, batch, int(bool(inverse)), order,
+                                      SPG_DEVICE_PTRS))
+
+
+_CTX = {}
+
+
+def get_context(device=0):
+    """Process-wide cached Context per device."""
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]

@@ -1,0 +1,227 @@
+// Context lifetime, host-side constant tables, field-op entry points and throughput probes.
+#include <string.h>
+
+#include "common.h"
+
+// ------------------------------------------------------------------ host helpers
+static void exp_root(int log_n, uint32_t e[8]) {
+  // (p - 1) >> log_n = 2^(251 - k) + 2^(196 - k) + 2^(192 - k)
+  memset(e, 0, 32);
+  int bits[3] = {251 - log_n, 196 - log_n, 192 - log_n};
+  for (int b : bits) e[b >> 5] |= 1u << (b & 31);
+}
+
+Fp spg_host_from_u64(const uint64_t* canon) { return fp_to_mont(fp_from_u64(canon)); }
+void spg_host_to_u64(const Fp& mont, uint64_t* canon) {
+  Fp c = fp_from_mont(mont);
+  fp_to_u64(c, canon);
+}
+
+Fp spg_host_root_of_unity(int log_n) {
+  uint64_t three[4] = {3, 0, 0, 0};
+  Fp g = spg_host_from_u64(three);
+  uint32_t e[8];
+  exp_root(log_n, e);
+  return fp_pow(g, e, 8);
+}
+
+static int upload(spg_ctx* ctx, const std::vector<Fp>& h, Fp** d) {
+  SPG_CUDA(cudaMalloc((void**)d, h.size() * sizeof(Fp)));
+  SPG_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(Fp), cudaMemcpyHostToDevice));
+  return SPG_OK;
+}
+
+int spg_curve_tables_init(spg_ctx* ctx);   // ec.cu
+
+static int build_tables(spg_ctx* ctx) {
+  // intra-tile twiddles omega_1024^(+-e)
+  Fp w = spg_host_root_of_unity(10);
+  Fp wi = fp_inv(w);
+  std::vector<Fp> f(512), b(512);
+  f[0] = b[0] = fp_one();
+  for (int i = 1; i < 512; i++) { f[i] = fp_mul(f[i - 1], w); b[i] = fp_mul(b[i - 1], wi); }
+  int rc;
+  if ((rc = upload(ctx, f, &ctx->tw_fwd))) return rc;
+  if ((rc = upload(ctx, b, &ctx->tw_inv))) return rc;
+  // universal two-level table of omega_{2^26}
+  Fp u = spg_host_root_of_unity(26);
+  std::vector<Fp> A(8192), B(8192);
+  B[0] = fp_one();
+  for (int i = 1; i < 8192; i++) B[i] = fp_mul(B[i - 1], u);
+  Fp u13 = fp_mul(B[8191], u);
+  A[0] = fp_one();
+  for (int i = 1; i < 8192; i++) A[i] = fp_mul(A[i - 1], u13);
+  if ((rc = upload(ctx, A, &ctx->uniA))) return rc;
+  if ((rc = upload(ctx, B, &ctx->uniB))) return rc;
+  return spg_curve_tables_init(ctx);
+}
+
+// ------------------------------------------------------------------ C-ABI: lifetime
+extern "C" int spg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int spg_create(int device_ordinal, spg_ctx** out) {
+  if (!out) return SPG_E_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_ordinal < 0 || device_ordinal >= n)
+    return SPG_E_NODEVICE;   // no CPU fallback by design
+  spg_ctx* ctx = new spg_ctx();
+  ctx->device = device_ordinal;
+  auto fail = [&](int rc) { *out = ctx; return rc; };   // caller can still read spg_last_error
+  if (cudaSetDevice(device_ordinal) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return fail(SPG_E_CUDA); }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return fail(SPG_E_CUDA); }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream"; return fail(SPG_E_CUDA); }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  int rc = build_tables(ctx);
+  if (rc) return fail(rc);
+  *out = ctx;
+  return SPG_OK;
+}
+
+extern "C" void spg_destroy(spg_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->device >= 0) cudaSetDevice(ctx->device);
+  cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->uniA); cudaFree(ctx->uniB);
+  cudaFree(ctx->const_points);
+  for (void* p : ctx->owned) cudaFree(p);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* spg_last_error(spg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" double spg_last_kernel_ms(spg_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
+extern "C" uint64_t spg_launch_count(spg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int spg_synchronize(spg_ctx* ctx) {
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}
+
+// ------------------------------------------------------------------ field ops
+__global__ void k_field_op(int op, const Fp* a, const Fp* b, Fp* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp x = fp_to_mont(a[i]);
+  Fp r;
+  if (op == 3) {
+    r = fp_inv(x);
+  } else if (op == 4) {
+    Fp e = b[i];
+    r = fp_pow(x, e.v, 8);
+  } else {
+    Fp y = fp_to_mont(b[i]);
+    r = op == 0 ? fp_mul(x, y) : (op == 1 ? fp_add(x, y) : fp_sub(x, y));
+  }
+  out[i] = fp_from_mont(r);
+}
+
+extern "C" int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                            size_t n, int flags) {
+  SPG_ARG(ctx && a && out && op >= 0 && op <= 4, "spg_field_op");
+  SPG_ARG(op == 3 || b, "spg_field_op: b required");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  const Fp *da = (const Fp*)a, *db = (const Fp*)b;
+  Fp* dout = (Fp*)out;
+  DevBuf ba, bb, bo;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(ba.alloc(n * 32)); SPG_CUDA(bb.alloc(n * 32)); SPG_CUDA(bo.alloc(n * 32));
+    SPG_CUDA(cudaMemcpyAsync(ba.p, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) SPG_CUDA(cudaMemcpyAsync(bb.p, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    da = ba.as<Fp>(); db = bb.as<Fp>(); dout = bo.as<Fp>();
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_field_op<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(op, da, db, dout, n);
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS))
+    SPG_CUDA(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}
+
+// ------------------------------------------------------------------ throughput probes
+template <int CH>
+__global__ void __launch_bounds__(256) k_bench_mul(Fp* out, int iters) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  Fp x[CH], y;
+  y = fp_one();
+  y.v[0] ^= i; y.v[3] += 0x9e3779b9u * i;
+#pragma unroll
+  for (int c = 0; c < CH; c++) { x[c] = fp_r2(); x[c].v[1] ^= i * 2654435761u + c; }
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int c = 0; c < CH; c++) x[c] = fp_mul(x[c], y);
+  }
+  Fp acc = x[0];
+#pragma unroll
+  for (int c = 1; c < CH; c++) acc = fp_add_raw(acc, x[c]);
+  if (acc.v[7] == 0x12345678u) out[i] = acc;   // practically never; defeats dead-code elimination
+}
+
+__global__ void __launch_bounds__(256) k_bench_imad_wide(unsigned long long* out, int iters) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long a0 = i, a1 = i + 1, a2 = i + 2, a3 = i + 3, a4 = i + 4, a5 = i + 5, a6 = i + 6, a7 = i + 7;
+  unsigned m = i * 2654435761u + 12345u, q = i ^ 0x5bd1e995u;
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      asm volatile(
+          "mad.wide.u32 %0, %8, %9, %0;\n\t"
+          "mad.wide.u32 %1, %8, %9, %1;\n\t"
+          "mad.wide.u32 %2, %8, %9, %2;\n\t"
+          "mad.wide.u32 %3, %8, %9, %3;\n\t"
+          "mad.wide.u32 %4, %8, %9, %4;\n\t"
+          "mad.wide.u32 %5, %8, %9, %5;\n\t"
+          "mad.wide.u32 %6, %8, %9, %6;\n\t"
+          "mad.wide.u32 %7, %8, %9, %7;"
+          : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7)
+          : "r"(m), "r"(q));
+    }
+  }
+  unsigned long long s = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  if (s == 0x123456789abcdefull) out[i] = s;
+}
+
+extern "C" int spg_bench_field_mul(spg_ctx* ctx, int iters, int chains, double* mul_per_s,
+                                   double* imad_wide_per_s) {
+  SPG_ARG(ctx && iters > 0 && (chains == 1 || chains == 2 || chains == 4), "spg_bench_field_mul");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  const int threads = 256, blocks = ctx->sm_count * 8;
+  DevBuf o; SPG_CUDA(o.alloc((size_t)threads * blocks * 32));
+  float ms = 0;
+  for (int rep = 0; rep < 2; rep++) {   // first repetition warms up
+    SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (chains == 1) k_bench_mul<1><<<blocks, threads, 0, ctx->stream>>>(o.as<Fp>(), iters);
+    else if (chains == 2) k_bench_mul<2><<<blocks, threads, 0, ctx->stream>>>(o.as<Fp>(), iters);
+    else k_bench_mul<4><<<blocks, threads, 0, ctx->stream>>>(o.as<Fp>(), iters);
+    SPG_LAUNCH_CHECK();
+    SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  }
+  ctx->last_ms = ms;
+  if (mul_per_s) *mul_per_s = (double)threads * blocks * iters * chains / (ms * 1e-3);
+  if (imad_wide_per_s) {
+    for (int rep = 0; rep < 2; rep++) {
+      SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+      k_bench_imad_wide<<<blocks, threads, 0, ctx->stream>>>((unsigned long long*)o.p, iters);
+      SPG_LAUNCH_CHECK();
+      SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+      SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    }
+    *imad_wide_per_s = (double)threads * blocks * iters * 64.0 / (ms * 1e-3);
+  }
+  return SPG_OK;
+}

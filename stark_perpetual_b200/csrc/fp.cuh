@@ -1,0 +1,493 @@
+// 252-bit prime-field arithmetic for p = 2^251 + 17*2^192 + 1 (the STARK prime;
+// reference: src/starkware/crypto/signature/signature.py:41, nothing_up_my_sleeve_gen.py:35).
+//
+// Representation: 8 x u32 little-endian limbs (memory layout == 4 x u64 LE), Montgomery form with
+// R = 2^256.  Because p ~ 2^251 there are ~5 spare bits, so arithmetic is LAZY:
+//   * fp_mul never does a final conditional subtraction: for inputs a, b < 2^254 (~8p) the
+//     output is < p + a*b/R < 3p;  for inputs < 4p the output is < 1.5p.
+//   * fp_add / fp_sub keep values in [0, 2p) given inputs in [0, 2p).
+//   * fp_reduce brings a value < 4p to the canonical range [0, p).
+// The prime is sparse: p = 1 + p3 * 2^192 with p3 = 2^59 + 17, so -p^-1 mod 2^64 = -1 and the
+// Montgomery reduction needs no general multiplications, only shifts and adds (fp_redc).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SPG_HD __host__ __device__ __forceinline__
+#define SPG_D __device__ __forceinline__
+#else
+#define SPG_HD inline
+#define SPG_D inline
+#endif
+
+struct alignas(16) Fp {
+  uint32_t v[8];
+};
+
+// p, 2p in 32-bit limbs
+#define SPG_P0 0x00000001u
+#define SPG_P6 0x00000011u
+#define SPG_P7 0x08000000u
+#define SPG_2P0 0x00000002u
+#define SPG_2P6 0x00000022u
+#define SPG_2P7 0x10000000u
+
+SPG_HD Fp fp_zero() {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = 0;
+  return r;
+}
+// R mod p (Montgomery one) = 0x07fffffffffffdf0 ffffffffffffffff ffffffffffffffff ffffffffffffffe1
+SPG_HD Fp fp_one() {
+  Fp r;
+  r.v[0] = 0xffffffe1u; r.v[1] = 0xffffffffu; r.v[2] = 0xffffffffu; r.v[3] = 0xffffffffu;
+  r.v[4] = 0xffffffffu; r.v[5] = 0xffffffffu; r.v[6] = 0xfffffdf0u; r.v[7] = 0x07ffffffu;
+  return r;
+}
+// R^2 mod p = 0x07ffd4ab5e008810 ffffffffff6f8000 00000001330fffff fffffd737e000401
+SPG_HD Fp fp_r2() {
+  Fp r;
+  r.v[0] = 0x7e000401u; r.v[1] = 0xfffffd73u; r.v[2] = 0x330fffffu; r.v[3] = 0x00000001u;
+  r.v[4] = 0xff6f8000u; r.v[5] = 0xffffffffu; r.v[6] = 0x5e008810u; r.v[7] = 0x07ffd4abu;
+  return r;
+}
+
+SPG_HD bool fp_eq_raw(const Fp& a, const Fp& b) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d |= a.v[i] ^ b.v[i];
+  return d == 0;
+}
+SPG_HD bool fp_is_zero_raw(const Fp& a) {
+  uint32_t d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d |= a.v[i];
+  return d == 0;
+}
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------ device path (PTX carry chains)
+
+// r = a - k*p if that is >= 0 else a, with kp given by its three non-trivial limbs.
+SPG_D Fp fpd_csub(const Fp& a, uint32_t k0, uint32_t k6, uint32_t k7) {
+  Fp t;
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, 0;\n\t"
+      "subc.cc.u32 %2, %11, 0;\n\t"
+      "subc.cc.u32 %3, %12, 0;\n\t"
+      "subc.cc.u32 %4, %13, 0;\n\t"
+      "subc.cc.u32 %5, %14, 0;\n\t"
+      "subc.cc.u32 %6, %15, %18;\n\t"
+      "subc.cc.u32 %7, %16, %19;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]),
+        "=r"(t.v[6]), "=r"(t.v[7]), "=r"(borrow)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]), "r"(k0), "r"(k6), "r"(k7));
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = borrow ? a.v[i] : t.v[i];
+  return r;
+}
+
+// a + b, inputs < 2p  -> output < 2p
+SPG_D Fp fpd_add(const Fp& a, const Fp& b) {
+  Fp s;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]),
+        "=r"(s.v[6]), "=r"(s.v[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
+        "r"(b.v[6]), "r"(b.v[7]));
+  return fpd_csub(s, SPG_2P0, SPG_2P6, SPG_2P7);
+}
+// a + b with no reduction (caller guarantees the sum stays < 2^256 and within the lazy bounds)
+SPG_D Fp fpd_add_raw(const Fp& a, const Fp& b) {
+  Fp s;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32 %7, %15, %23;"
+      : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]),
+        "=r"(s.v[6]), "=r"(s.v[7])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
+        "r"(b.v[6]), "r"(b.v[7]));
+  return s;
+}
+
+// a - b (mod p), inputs < 2p -> output < 2p : computes a - b, adds 2p back on borrow.
+SPG_D Fp fpd_sub(const Fp& a, const Fp& b) {
+  Fp d;
+  uint32_t borrow;
+  asm("sub.cc.u32 %0, %9, %17;\n\t"
+      "subc.cc.u32 %1, %10, %18;\n\t"
+      "subc.cc.u32 %2, %11, %19;\n\t"
+      "subc.cc.u32 %3, %12, %20;\n\t"
+      "subc.cc.u32 %4, %13, %21;\n\t"
+      "subc.cc.u32 %5, %14, %22;\n\t"
+      "subc.cc.u32 %6, %15, %23;\n\t"
+      "subc.cc.u32 %7, %16, %24;\n\t"
+      "subc.u32 %8, 0, 0;"
+      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]),
+        "=r"(d.v[6]), "=r"(d.v[7]), "=r"(borrow)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
+        "r"(b.v[6]), "r"(b.v[7]));
+  // borrow is 0 or 0xffffffff: add (2p & borrow)
+  uint32_t k0 = borrow & SPG_2P0, k6 = borrow & SPG_2P6, k7 = borrow & SPG_2P7;
+  Fp r;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, 0;\n\t"
+      "addc.cc.u32 %2, %10, 0;\n\t"
+      "addc.cc.u32 %3, %11, 0;\n\t"
+      "addc.cc.u32 %4, %12, 0;\n\t"
+      "addc.cc.u32 %5, %13, 0;\n\t"
+      "addc.cc.u32 %6, %14, %17;\n\t"
+      "addc.u32 %7, %15, %18;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+        "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]), "r"(d.v[6]),
+        "r"(d.v[7]), "r"(k0), "r"(k6), "r"(k7));
+  return r;
+}
+
+// value < 4p -> canonical [0, p)
+SPG_D Fp fpd_reduce(const Fp& a) {
+  Fp r = fpd_csub(a, SPG_2P0, SPG_2P6, SPG_2P7);
+  return fpd_csub(r, SPG_P0, SPG_P6, SPG_P7);
+}
+
+// ---- 8x8 limb schoolbook product, even/odd column accumulators so that every mad.lo/mad.hi pair
+// lands on an aligned 64-bit accumulator (ptxas fuses each pair into one IMAD.WIDE.U32[.X]).
+#define SPG_ROW_MUL(acc, k, A0, A1, A2, A3, B)                                         \
+  asm("mul.lo.u32 %0, %8, %12;\n\t"                                                     \
+      "mul.hi.u32 %1, %8, %12;\n\t"                                                     \
+      "mul.lo.u32 %2, %9, %12;\n\t"                                                     \
+      "mul.hi.u32 %3, %9, %12;\n\t"                                                     \
+      "mul.lo.u32 %4, %10, %12;\n\t"                                                    \
+      "mul.hi.u32 %5, %10, %12;\n\t"                                                    \
+      "mul.lo.u32 %6, %11, %12;\n\t"                                                    \
+      "mul.hi.u32 %7, %11, %12;"                                                        \
+      : "=r"(acc[k]), "=r"(acc[k + 1]), "=r"(acc[k + 2]), "=r"(acc[k + 3]), "=r"(acc[k + 4]), \
+        "=r"(acc[k + 5]), "=r"(acc[k + 6]), "=r"(acc[k + 7])                             \
+      : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B))
+
+#define SPG_ROW_MAD(acc, k, A0, A1, A2, A3, B)                                         \
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"                                              \
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"                                             \
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"                                            \
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"                                            \
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"                                            \
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"                                            \
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"                                            \
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"                                            \
+      "addc.u32 %8, %8, 0;"                                                             \
+      : "+r"(acc[k]), "+r"(acc[k + 1]), "+r"(acc[k + 2]), "+r"(acc[k + 3]), "+r"(acc[k + 4]), \
+        "+r"(acc[k + 5]), "+r"(acc[k + 6]), "+r"(acc[k + 7]), "+r"(acc[k + 8])           \
+      : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B))
+
+// t[0..15] = a * b
+SPG_D void fpd_mul_wide(uint32_t (&t)[16], const Fp& a, const Fp& b) {
+  uint32_t E[17], O[16];
+#pragma unroll
+  for (int i = 8; i < 17; i++) E[i] = 0;
+#pragma unroll
+  for (int i = 8; i < 16; i++) O[i] = 0;
+  // E[k] has weight 2^(32k); O[k] has weight 2^(32(k+1)).
+  SPG_ROW_MUL(E, 0, a.v[0], a.v[2], a.v[4], a.v[6], b.v[0]);
+  SPG_ROW_MUL(O, 0, a.v[1], a.v[3], a.v[5], a.v[7], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) {
+    if (i & 1) {
+      SPG_ROW_MAD(E, i + 1, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+      SPG_ROW_MAD(O, i - 1, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+    } else {
+      SPG_ROW_MAD(E, i, a.v[0], a.v[2], a.v[4], a.v[6], b.v[i]);
+      SPG_ROW_MAD(O, i, a.v[1], a.v[3], a.v[5], a.v[7], b.v[i]);
+    }
+  }
+  t[0] = E[0];
+  asm("add.cc.u32 %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32 %14, %29, %44;"
+      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
+        "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]),
+        "=r"(t[15])
+      : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]),
+        "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+        "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]),
+        "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+}
+
+// Montgomery reduction of a 512-bit value T (< 2^508): returns T * 2^-256 mod p, lazily
+// (< p + T/2^256).  Uses p = 1 + p3*2^192, p3 = 2^59 + 17:
+//   Ml = -T[0..191] mod 2^192, c0 = (T[0..191] != 0)
+//   Q  = p3 * Ml                      (256 bits)
+//   x  = T[192..255] + c0 + Q[0..63]  (64 bits, carry c1)
+//   m3 = -x mod 2^64, c3 = (x != 0),  Q' = p3 * m3   (128 bits)
+//   result = T[256..511] + (Q >> 64) + c1 + c3 + Q' * 2^128
+SPG_D Fp fpd_redc(const uint32_t (&t)[16]) {
+  uint32_t m[6], c0;
+  asm("sub.cc.u32 %0, 0, %7;\n\t"
+      "subc.cc.u32 %1, 0, %8;\n\t"
+      "subc.cc.u32 %2, 0, %9;\n\t"
+      "subc.cc.u32 %3, 0, %10;\n\t"
+      "subc.cc.u32 %4, 0, %11;\n\t"
+      "subc.cc.u32 %5, 0, %12;\n\t"
+      "subc.u32 %6, 0, 0;"
+      : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]), "=r"(m[4]), "=r"(m[5]), "=r"(c0)
+      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]));
+  c0 &= 1u;  // borrow mask -> 0/1
+  // A = 17 * Ml  (7 limbs) = (Ml << 4) + Ml
+  uint32_t s4[7];
+  s4[0] = m[0] << 4;
+#pragma unroll
+  for (int i = 1; i < 6; i++) s4[i] = __funnelshift_l(m[i - 1], m[i], 4);
+  s4[6] = m[5] >> 28;
+  uint32_t A[7];
+  asm("add.cc.u32 %0, %7, %14;\n\t"
+      "addc.cc.u32 %1, %8, %15;\n\t"
+      "addc.cc.u32 %2, %9, %16;\n\t"
+      "addc.cc.u32 %3, %10, %17;\n\t"
+      "addc.cc.u32 %4, %11, %18;\n\t"
+      "addc.cc.u32 %5, %12, %19;\n\t"
+      "addc.u32 %6, %13, 0;"
+      : "=r"(A[0]), "=r"(A[1]), "=r"(A[2]), "=r"(A[3]), "=r"(A[4]), "=r"(A[5]), "=r"(A[6])
+      : "r"(s4[0]), "r"(s4[1]), "r"(s4[2]), "r"(s4[3]), "r"(s4[4]), "r"(s4[5]), "r"(s4[6]),
+        "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]));
+  // B = Ml << 59 = (Ml << 27) << 32 : limbs B[1..7]
+  uint32_t B[8];
+  B[1] = m[0] << 27;
+#pragma unroll
+  for (int i = 1; i < 6; i++) B[i + 1] = __funnelshift_l(m[i - 1], m[i], 27);
+  B[7] = m[5] >> 5;
+  // Q = A + B  (8 limbs, Q[0] = A[0])
+  uint32_t Q[8];
+  Q[0] = A[0];
+  asm("add.cc.u32 %0, %7, %13;\n\t"
+      "addc.cc.u32 %1, %8, %14;\n\t"
+      "addc.cc.u32 %2, %9, %15;\n\t"
+      "addc.cc.u32 %3, %10, %16;\n\t"
+      "addc.cc.u32 %4, %11, %17;\n\t"
+      "addc.cc.u32 %5, %12, %18;\n\t"
+      "addc.u32 %6, 0, %19;"
+      : "=r"(Q[1]), "=r"(Q[2]), "=r"(Q[3]), "=r"(Q[4]), "=r"(Q[5]), "=r"(Q[6]), "=r"(Q[7])
+      : "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(B[1]), "r"(B[2]),
+        "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
+  // x = T[6..7] + Q[0..1] + c0 ; c1 = carries (0..1, see header comment)
+  uint32_t x0, x1, c1;
+  asm("add.cc.u32 %0, %3, %5;\n\t"
+      "addc.cc.u32 %1, %4, %6;\n\t"
+      "addc.u32 %2, 0, 0;\n\t"
+      "add.cc.u32 %0, %0, %7;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "=&r"(x0), "=&r"(x1), "=&r"(c1)
+      : "r"(t[6]), "r"(t[7]), "r"(Q[0]), "r"(Q[1]), "r"(c0));
+  // m3 = -x, c3 = (x != 0)
+  uint32_t n0, n1, c3;
+  asm("sub.cc.u32 %0, 0, %3;\n\t"
+      "subc.cc.u32 %1, 0, %4;\n\t"
+      "subc.u32 %2, 0, 0;"
+      : "=r"(n0), "=r"(n1), "=r"(c3)
+      : "r"(x0), "r"(x1));
+  c3 &= 1u;
+  // Q' = p3 * m3 = 17*m3 + (m3 << 59): 4 limbs
+  uint32_t a0 = n0 << 4, a1 = __funnelshift_l(n0, n1, 4), a2 = n1 >> 28;
+  uint32_t b1 = n0 << 27, b2 = __funnelshift_l(n0, n1, 27), b3 = n1 >> 5;
+  uint32_t q0, q1, q2, q3;
+  asm("add.cc.u32 %0, %4, %7;\n\t"
+      "addc.cc.u32 %1, %5, %8;\n\t"
+      "addc.u32 %2, %6, 0;\n\t"
+      "add.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.u32 %3, 0, %11;"
+      : "=&r"(q0), "=&r"(q1), "=&r"(q2), "=&r"(q3)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(n0), "r"(n1), "r"(b1), "r"(b2), "r"(b3));
+  // result = T[8..15] + Q[2..7] + (c1 + c3) + Q' << 128
+  uint32_t cc = c1 + c3;
+  Fp r;
+  asm("add.cc.u32 %0, %8, %16;\n\t"
+      "addc.cc.u32 %1, %9, %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, 0;\n\t"
+      "addc.u32 %7, %15, 0;\n\t"
+      "add.cc.u32 %0, %0, %22;\n\t"
+      "addc.cc.u32 %1, %1, 0;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.cc.u32 %3, %3, 0;\n\t"
+      "addc.cc.u32 %4, %4, %23;\n\t"
+      "addc.cc.u32 %5, %5, %24;\n\t"
+      "addc.cc.u32 %6, %6, %25;\n\t"
+      "addc.u32 %7, %7, %26;"
+      : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]),
+        "=&r"(r.v[6]), "=&r"(r.v[7])
+      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]),
+        "r"(t[15]), "r"(Q[2]), "r"(Q[3]), "r"(Q[4]), "r"(Q[5]), "r"(Q[6]), "r"(Q[7]), "r"(cc),
+        "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+  return r;
+}
+
+SPG_D Fp fpd_mul(const Fp& a, const Fp& b) {
+  uint32_t t[16];
+  fpd_mul_wide(t, a, b);
+  return fpd_redc(t);
+}
+SPG_D Fp fpd_sqr(const Fp& a) { return fpd_mul(a, a); }
+
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------ host path (unsigned __int128)
+typedef unsigned __int128 spg_u128;
+
+static inline void fp_to_u64(const Fp& a, uint64_t* w) {
+  for (int i = 0; i < 4; i++) w[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+}
+static inline Fp fp_from_u64(const uint64_t* w) {
+  Fp r;
+  for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)w[i]; r.v[2 * i + 1] = (uint32_t)(w[i] >> 32); }
+  return r;
+}
+static const uint64_t SPG_P64[4] = {1ull, 0ull, 0ull, 0x0800000000000011ull};
+
+static inline bool u256_geq(const uint64_t* a, const uint64_t* b) {
+  for (int i = 3; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; }
+  return true;
+}
+static inline void u256_sub(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t br = 0;
+  for (int i = 0; i < 4; i++) {
+    spg_u128 d = (spg_u128)a[i] - b[i] - br;
+    r[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1;
+  }
+}
+static inline void u256_add(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t c = 0;
+  for (int i = 0; i < 4; i++) {
+    spg_u128 s = (spg_u128)a[i] + b[i] + c;
+    r[i] = (uint64_t)s; c = (uint64_t)(s >> 64);
+  }
+}
+// host functions always return canonical values
+inline Fp fph_reduce(const Fp& a) {
+  uint64_t w[4]; fp_to_u64(a, w);
+  while (u256_geq(w, SPG_P64)) u256_sub(w, w, SPG_P64);
+  return fp_from_u64(w);
+}
+inline Fp fph_add(const Fp& a, const Fp& b) {
+  uint64_t x[4], y[4]; fp_to_u64(a, x); fp_to_u64(b, y);
+  u256_add(x, x, y);
+  return fph_reduce(fp_from_u64(x));
+}
+inline Fp fph_sub(const Fp& a, const Fp& b) {
+  uint64_t x[4], y[4]; fp_to_u64(fph_reduce(a), x); fp_to_u64(fph_reduce(b), y);
+  if (!u256_geq(x, y)) u256_add(x, x, SPG_P64);
+  u256_sub(x, x, y);
+  return fp_from_u64(x);
+}
+inline Fp fph_mul(const Fp& a, const Fp& b) {
+  uint64_t x[4], y[4], t[9] = {0};
+  fp_to_u64(a, x); fp_to_u64(b, y);
+  for (int i = 0; i < 4; i++) {
+    uint64_t c = 0;
+    for (int j = 0; j < 4; j++) {
+      spg_u128 s = (spg_u128)x[j] * y[i] + t[i + j] + c;
+      t[i + j] = (uint64_t)s; c = (uint64_t)(s >> 64);
+    }
+    t[i + 4] = c;
+  }
+  // word-serial Montgomery, m = -t[k] (since -p^-1 = -1 mod 2^64)
+  for (int k = 0; k < 4; k++) {
+    uint64_t m = (uint64_t)0 - t[k];
+    uint64_t c = 0;
+    for (int j = 0; j < 4; j++) {
+      spg_u128 s = (spg_u128)m * SPG_P64[j] + t[k + j] + c;
+      t[k + j] = (uint64_t)s; c = (uint64_t)(s >> 64);
+    }
+    for (int j = k + 4; c && j < 9; j++) {
+      spg_u128 s = (spg_u128)t[j] + c;
+      t[j] = (uint64_t)s; c = (uint64_t)(s >> 64);
+    }
+  }
+  return fph_reduce(fp_from_u64(t + 4));
+}
+inline Fp fph_sqr(const Fp& a) { return fph_mul(a, a); }
+
+// ------------------------------------------------------------------ dispatch wrappers
+#if defined(__CUDA_ARCH__)
+#define SPG_DISPATCH(dev, hst) return dev
+#else
+#define SPG_DISPATCH(dev, hst) return hst
+#endif
+SPG_HD Fp fp_mul(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_mul(a, b), fph_mul(a, b)); }
+SPG_HD Fp fp_sqr(const Fp& a) { SPG_DISPATCH(fpd_mul(a, a), fph_mul(a, a)); }
+SPG_HD Fp fp_add(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_add(a, b), fph_add(a, b)); }
+SPG_HD Fp fp_sub(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_sub(a, b), fph_sub(a, b)); }
+SPG_HD Fp fp_reduce(const Fp& a) { SPG_DISPATCH(fpd_reduce(a), fph_reduce(a)); }
+// sum with no reduction (device: caller keeps the lazy bounds; host: canonical)
+SPG_HD Fp fp_add_raw(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_add_raw(a, b), fph_add(a, b)); }
+
+// ------------------------------------------------------------------ shared helpers
+SPG_HD Fp fp_to_mont(const Fp& a) { return fp_mul(a, fp_r2()); }
+SPG_HD Fp fp_from_mont(const Fp& a) {
+  Fp one = fp_zero();
+  one.v[0] = 1;
+  return fp_reduce(fp_mul(a, one));
+}
+SPG_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
+// canonical equality of two lazy values
+SPG_HD bool fp_eq(const Fp& a, const Fp& b) { return fp_eq_raw(fp_reduce(a), fp_reduce(b)); }
+SPG_HD bool fp_is_zero(const Fp& a) { return fp_is_zero_raw(fp_reduce(a)); }
+
+// a^e for a 256-bit exponent given as 8 x u32 LE (Montgomery in / out)
+SPG_HD Fp fp_pow(const Fp& a, const uint32_t* e, int nlimbs) {
+  Fp r = fp_one();
+  bool started = false;
+  for (int i = nlimbs * 32 - 1; i >= 0; i--) {
+    if (started) r = fp_sqr(r);
+    if ((e[i >> 5] >> (i & 31)) & 1) {
+      r = started ? fp_mul(r, a) : a;
+      started = true;
+    }
+  }
+  return r;
+}
+SPG_HD Fp fp_pow_u64(const Fp& a, uint64_t e) {
+  uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
+  return fp_pow(a, w, 2);
+}
+// a^-1 = a^(p-2); p-2 = 0x0800000000000010 ffffffffffffffff ffffffffffffffff ffffffffffffffff
+SPG_HD Fp fp_inv(const Fp& a) {
+  const uint32_t e[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu,
+                         0xffffffffu, 0xffffffffu, 0x00000010u, 0x08000000u};
+  return fp_pow(a, e, 8);
+}

@@ -1,0 +1,123 @@
+// NTT passes as CUDA kernels + the pass planner + the spg_ntt entry point.
+// (SURVEY.md section 8 row p1 / BASELINE.json configs[1]; conventions in DESIGN.md.)
+#include "common.h"
+#include "ntt.cuh"
+
+#define NTT_LOG_WS 11
+typedef NttTile<NTT_LOG_WS> Tile;
+
+template <bool DIT>
+__global__ void __launch_bounds__(Tile::NT, 2) k_ntt_pass(NttPass P) {
+  extern __shared__ uint4 smem_raw[];
+  Fp* ws = reinterpret_cast<Fp*>(smem_raw);
+  const int tid = threadIdx.x;
+  const unsigned cta = blockIdx.x, col = blockIdx.y;
+#pragma unroll
+  for (int j = 0; j < 8; j++) Tile::load_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
+  __syncthreads();
+  const int ns = Tile::n_steps(P);
+  for (int k = 0; k < ns; k++) {
+    int w, sh;
+    Tile::step_geom<DIT>(P, k, &w, &sh);
+    Tile::step_w<DIT>(P, ws, tid, w, sh);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) Tile::store_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
+}
+
+__global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n = (size_t)1 << log_n;
+  if (i >= n * ncols) return;
+  size_t col = i >> log_n, r = i & (n - 1);
+  out[col * n + spg_bitrev((unsigned)r, (int)log_n)] = in[i];
+}
+
+int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
+                   size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
+                   const Fp* scale_lo, const Fp* scale_hi) {
+  SPG_ARG(log_n <= 26, "NTT size above 2^26 not supported by the universal twiddle table");
+  SPG_ARG(ncols < 65536, "too many columns in one NTT batch");
+  if (ncols == 0) return SPG_OK;
+  static bool attr_set = false;
+  const int smem = Tile::WS * (int)sizeof(Fp);
+  if (!attr_set) {
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  NttPass passes[8];
+  if (!dit && coset_exp != 0) { ctx->err = "coset shift only supported for DIT"; return SPG_E_ARG; }
+  const int np = spg_ntt_make_passes(passes, NTT_LOG_WS, in, out, log_n, in_stride, out_stride, inverse, dit,
+                                     coset_exp, scale_lo, scale_hi, ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
+  for (int pi = 0; pi < np; pi++) {
+    const NttPass& P = passes[pi];
+    const size_t ctas = ((size_t)1 << log_n) >> (P.log_r + P.log_g);
+    dim3 grid((unsigned)ctas, (unsigned)ncols);
+    if (dit) k_ntt_pass<true><<<grid, Tile::NT, smem, ctx->stream>>>(P);
+    else k_ntt_pass<false><<<grid, Tile::NT, smem, ctx->stream>>>(P);
+    SPG_LAUNCH_CHECK();
+  }
+  return SPG_OK;
+}
+
+int spg_bitrev_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
+  size_t total = ((size_t)1 << log_n) * ncols;
+  k_bitrev<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in, out, log_n, ncols);
+  SPG_LAUNCH_CHECK();
+  return SPG_OK;
+}
+
+__global__ void k_fill(Fp* p, Fp v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batch, int inverse, int order,
+                       int flags) {
+  SPG_ARG(ctx && data, "spg_ntt: null");
+  SPG_ARG(order >= 0 && order <= 2, "spg_ntt: order");
+  SPG_ARG(log_n <= 26, "spg_ntt: log_n");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (batch == 0) return SPG_OK;
+  const size_t n = (size_t)1 << log_n, total = n * batch;
+  Fp* d = (Fp*)data;
+  DevBuf buf, tmp, sc;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(buf.alloc(total * 32));
+    SPG_CUDA(cudaMemcpyAsync(buf.p, data, total * 32, cudaMemcpyHostToDevice, ctx->stream));
+    d = buf.as<Fp>();
+  }
+  // inverse: scale by 1/N through the scale_hi hook of the contiguous pass
+  const Fp* scale_hi = nullptr;
+  if (inverse) {
+    int lr, lb;
+    spg_ntt_last_pass_geometry(log_n, &lr, &lb);
+    uint64_t nn[4] = {(uint64_t)n, 0, 0, 0};
+    Fp ninv = fp_inv(spg_host_from_u64(nn));
+    SPG_CUDA(sc.alloc(((size_t)1 << lb) * 32));
+    k_fill<<<(unsigned)((((size_t)1 << lb) + 255) / 256), 256, 0, ctx->stream>>>(sc.as<Fp>(), ninv, (size_t)1 << lb);
+    SPG_LAUNCH_CHECK();
+    scale_hi = sc.as<Fp>();
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (size_t c0 = 0; c0 < batch; c0 += 32768) {
+    size_t nc = batch - c0 < 32768 ? batch - c0 : 32768;
+    int rc = spg_ntt_device(ctx, d + c0 * n, d + c0 * n, log_n, nc, n, n, inverse, order == SPG_NTT_REV_TO_NAT, 0,
+                            nullptr, scale_hi);
+    if (rc) return rc;
+  }
+  if (order == SPG_NTT_NAT_TO_NAT && log_n > 0) {
+    SPG_CUDA(tmp.alloc(total * 32));
+    int rc = spg_bitrev_device(ctx, d, tmp.as<Fp>(), log_n, batch);
+    if (rc) return rc;
+    SPG_CUDA(cudaMemcpyAsync(d, tmp.p, total * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS))
+    SPG_CUDA(cudaMemcpyAsync(data, d, total * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}

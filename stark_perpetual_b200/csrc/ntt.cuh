@@ -1,0 +1,262 @@
+// Tiled number-theoretic transform over the STARK prime.
+//
+// No reference symbol exists for this stage: the field and generator come from
+// signature.py:41-42; the transform conventions are this repo's own (DESIGN.md "NTT").
+//
+// A size-2^n transform is a sequence of PASSES.  A pass views the column as [B][R][S]
+// (element = b*R*S + r*S + c) and runs, for every (b, c), a size-R transform over r entirely in
+// shared memory; consecutive passes are glued by the classic "four-step" diagonal twiddle
+// w_{RS}^(bitrev(r) * c).  Two butterfly networks are provided:
+//   DIF (Gentleman-Sande)  natural order in  -> bit-reversed order out
+//   DIT (Cooley-Tukey)     bit-reversed in   -> natural order out
+// so LDE (inverse DIF, then per-coset forward DIT) never needs a permutation pass.
+//
+// One CTA owns a WORKSPACE of 2^LOG_WS field elements in shared memory: R rows x G columns when
+// S > 1 (G*32-byte global segments), or G whole contiguous tiles when S == 1.  Each thread holds 8
+// elements in registers per STEP and does up to 3 butterfly stages (radix-8) between exchanges.
+//
+// Everything is written as per-thread functions of (tid, step) so the same code runs under the
+// CPU emulation harness in tests/host_emul (g++, no GPU).
+#pragma once
+#include "fp.cuh"
+
+#define SPG_TW_LOG 10          // intra-tile twiddle table: omega_1024^e, e < 512
+#define SPG_UNI_LOG 26         // universal two-level table: omega_{2^26}^e = uniA[e >> 13] * uniB[e & 8191]
+#define SPG_UNI_HALF 13
+
+struct NttPass {
+  const Fp* in;                // column 0
+  Fp* out;
+  unsigned long long in_col_stride, out_col_stride;   // elements between columns
+  int log_n;                   // whole transform size
+  int log_r, log_s;            // this pass: rows R, row stride S   (B = N / (R S))
+  int log_g;                   // S > 1: columns per CTA;  S == 1: tiles per CTA
+  int inverse;                 // use omega^-1
+  const Fp* tw;                // omega_1024^e  (forward) or omega_1024^-e (inverse), 512 entries
+  const Fp* uniA;              // universal table, high part (8192 entries)
+  const Fp* uniB;              // universal table, low part (8192 entries)
+  // diagonal twiddle  omega_{2^26}^( +- bitrev_R(r) * (c * ec + e0) )  applied AFTER a DIF pass /
+  // BEFORE a DIT pass.  use_diag = 0 disables it (last DIF pass / first DIT pass without coset).
+  int use_diag;
+  unsigned long long ec, e0;
+  // optional element-wise scaling tables (Montgomery form), DIF: applied at the end of the pass,
+  // DIT: applied at the start:  x *= lo[r] * hi[b]   (either may be null)
+  const Fp* scale_lo;          // R entries
+  const Fp* scale_hi;          // B entries
+};
+
+SPG_HD unsigned spg_bitrev(unsigned x, int bits) {
+#if defined(__CUDA_ARCH__)
+  return bits ? (__brev(x) >> (32 - bits)) : 0u;
+#else
+  unsigned r = 0;
+  for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+  return r;
+#endif
+}
+
+template <int LOG_WS>
+struct NttTile {
+  static constexpr int WS = 1 << LOG_WS;
+  static constexpr int NT = WS / 8;
+
+  // workspace slot of (row r, column/tile g)
+  static SPG_HD int slot(const NttPass& P, int r, int g) {
+    return P.log_s ? ((r << P.log_g) | g) : ((g << P.log_r) | r);
+  }
+  // global element offset (within a column) of workspace-linear index idx for CTA `cta`
+  static SPG_HD unsigned long long gaddr(const NttPass& P, unsigned cta, int idx, int* r_out, int* g_out,
+                                         unsigned* b_out, unsigned* c_out) {
+    if (P.log_s) {
+      int g = idx & ((1 << P.log_g) - 1), r = idx >> P.log_g;
+      unsigned ctas_per_block = 1u << (P.log_s - P.log_g);
+      unsigned b = cta / ctas_per_block, c = ((cta % ctas_per_block) << P.log_g) + g;
+      *r_out = r; *g_out = g; *b_out = b; *c_out = c;
+      return ((unsigned long long)b << (P.log_r + P.log_s)) + ((unsigned long long)r << P.log_s) + c;
+    } else {
+      int r = idx & ((1 << P.log_r) - 1), g = idx >> P.log_r;
+      unsigned b = (cta << P.log_g) + g;
+      *r_out = r; *g_out = g; *b_out = b; *c_out = 0;
+      return ((unsigned long long)b << P.log_r) + r;
+    }
+  }
+
+  // omega_{2^26}^E through the two-level table
+  static SPG_HD Fp uni_pow(const NttPass& P, unsigned long long E) {
+    E &= (1ull << SPG_UNI_LOG) - 1;
+    unsigned hi = (unsigned)(E >> SPG_UNI_HALF), lo = (unsigned)(E & ((1u << SPG_UNI_HALF) - 1));
+    if (lo == 0) return P.uniA[hi];
+    if (hi == 0) return P.uniB[lo];
+    return fp_mul(P.uniA[hi], P.uniB[lo]);
+  }
+
+  // factor applied to element (b, r, c): diagonal twiddle and optional scale tables
+  static SPG_HD Fp apply_factors(const NttPass& P, Fp x, unsigned b, int r, unsigned c) {
+    if (P.use_diag) {
+      unsigned long long k = spg_bitrev((unsigned)r, P.log_r);
+      unsigned long long E = k * ((unsigned long long)c * P.ec + P.e0);
+      if (P.inverse) E = (0ull - E);
+      if (E & ((1ull << SPG_UNI_LOG) - 1)) x = fp_mul(x, uni_pow(P, E));
+    }
+    if (P.scale_lo) x = fp_mul(x, P.scale_lo[r]);
+    if (P.scale_hi) x = fp_mul(x, P.scale_hi[b]);
+    return x;
+  }
+
+  // one butterfly step of width W bits at bit position sh of r, for thread tid.
+  template <int W, bool DIT>
+  static SPG_HD void step(const NttPass& P, Fp* ws, int tid, int sh) {
+    constexpr int GROUPS = 8 >> W;      // groups of 2^W elements per thread
+    constexpr int GS = 1 << W;
+    const int t = P.log_r;
+#pragma unroll
+    for (int gi = 0; gi < GROUPS; gi++) {
+      int u = gi * NT + tid;
+      if (u >= (1 << (t + P.log_g - W))) continue;   // workspace larger than the whole problem
+      int g, x;
+      if (P.log_s) { g = u & ((1 << P.log_g) - 1); x = u >> P.log_g; }
+      else { x = u & ((1 << (t - W)) - 1); g = u >> (t - W); }
+      int lo = x & ((1 << sh) - 1), hi = x >> sh;
+      int rbase = (hi << (sh + W)) | lo;
+      Fp v[GS];
+#pragma unroll
+      for (int f = 0; f < GS; f++) v[f] = ws[slot(P, rbase | (f << sh), g)];
+      if (DIT) {
+#pragma unroll
+        for (int s = 0; s < W; s++) {
+#pragma unroll
+          for (int f = 0; f < GS; f++) {
+            if (f & (1 << s)) continue;
+            int e = (((f & ((1 << s) - 1)) << sh) | lo) << (t - 1 - (sh + s));
+            Fp a = v[f], bb = v[f | (1 << s)];
+            Fp tq = e ? fp_mul(bb, P.tw[e << (SPG_TW_LOG - t)]) : bb;
+            if (!e) tq = bb;
+            v[f] = fp_add(a, tq);
+            v[f | (1 << s)] = fp_sub(a, tq);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = W - 1; s >= 0; s--) {
+#pragma unroll
+          for (int f = 0; f < GS; f++) {
+            if (f & (1 << s)) continue;
+            int e = (((f & ((1 << s) - 1)) << sh) | lo) << (t - 1 - (sh + s));
+            Fp a = v[f], bb = v[f | (1 << s)];
+            v[f] = fp_add(a, bb);
+            Fp d = fp_sub(a, bb);
+            v[f | (1 << s)] = e ? fp_mul(d, P.tw[e << (SPG_TW_LOG - t)]) : d;
+          }
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < GS; f++) ws[slot(P, rbase | (f << sh), g)] = v[f];
+    }
+  }
+
+  // dispatch on runtime width
+  template <bool DIT>
+  static SPG_HD void step_w(const NttPass& P, Fp* ws, int tid, int w, int sh) {
+    if (w == 3) step<3, DIT>(P, ws, tid, sh);
+    else if (w == 2) step<2, DIT>(P, ws, tid, sh);
+    else step<1, DIT>(P, ws, tid, sh);
+  }
+
+  // load phase for linear index idx of this CTA
+  template <bool DIT>
+  static SPG_HD void load_one(const NttPass& P, Fp* ws, unsigned cta, unsigned col, int idx) {
+    int r, g; unsigned b, c;
+    if (idx >= (1 << (P.log_r + P.log_g))) return;
+    unsigned long long off = gaddr(P, cta, idx, &r, &g, &b, &c);
+    Fp x = P.in[col * P.in_col_stride + off];
+    if (DIT) x = apply_factors(P, x, b, r, c);
+    ws[slot(P, r, g)] = x;
+  }
+  template <bool DIT>
+  static SPG_HD void store_one(const NttPass& P, const Fp* ws, unsigned cta, unsigned col, int idx) {
+    int r, g; unsigned b, c;
+    if (idx >= (1 << (P.log_r + P.log_g))) return;
+    unsigned long long off = gaddr(P, cta, idx, &r, &g, &b, &c);
+    Fp x = ws[slot(P, r, g)];
+    if (!DIT) x = apply_factors(P, x, b, r, c);
+    P.out[col * P.out_col_stride + off] = fp_reduce(x);
+  }
+  // number of butterfly steps and the (width, shift) of step k.  DIF walks the bits of r from the
+  // top, DIT from the bottom; the short step (log_r mod 3) comes last for DIF and first for DIT... both
+  // choices keep strides monotone.
+  static SPG_HD int n_steps(const NttPass& P) { return (P.log_r + 2) / 3; }
+  template <bool DIT>
+  static SPG_HD void step_geom(const NttPass& P, int k, int* w, int* sh) {
+    int t = P.log_r, rem = t % 3, ns = (t + 2) / 3;
+    if (DIT) {
+      // ascending strides: first step has width rem (if any)
+      if (rem) { *w = (k == 0) ? rem : 3; *sh = (k == 0) ? 0 : rem + 3 * (k - 1); }
+      else { *w = 3; *sh = 3 * k; }
+    } else {
+      // descending strides: last step has width rem (if any)
+      if (rem && k == ns - 1) { *w = rem; *sh = 0; }
+      else { *w = 3; *sh = t - 3 * (k + 1); }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ pass planner (host)
+// Split log_n into per-pass tile sizes (each <= 10 bits, as even as possible, larger first).
+static inline int spg_ntt_plan_bits(unsigned log_n, int bits[8]) {
+  if (log_n == 0) { bits[0] = 0; return 1; }
+  int np = (log_n + 9) / 10;
+  int base = log_n / np, extra = log_n % np;
+  for (int i = 0; i < np; i++) bits[i] = base + (i < extra ? 1 : 0);
+  return np;
+}
+
+// geometry of the pass that touches contiguous tiles (last for DIF, first for DIT):
+// it sees the column as [2^log_b_hi blocks][2^log_r_lo rows]
+static inline void spg_ntt_last_pass_geometry(unsigned log_n, int* log_r_lo, int* log_b_hi) {
+  int bits[8];
+  int np = spg_ntt_plan_bits(log_n, bits);
+  *log_r_lo = bits[np - 1];
+  *log_b_hi = (int)log_n - bits[np - 1];
+}
+
+// Build the pass list of one transform.  bits[0] covers the most significant index bits (largest
+// stride); DIF runs passes 0..np-1, DIT runs them in the opposite order (contiguous pass first).
+// coset_exp (DIT only): the input at coefficient index k is multiplied by omega_{2^26}^(coset_exp*k).
+// scale_lo / scale_hi are attached to the contiguous pass.
+static inline int spg_ntt_make_passes(NttPass* passes, int log_ws, const Fp* in, Fp* out, unsigned log_n,
+                                      unsigned long long in_stride, unsigned long long out_stride,
+                                      int inverse, int dit, unsigned long long coset_exp, const Fp* scale_lo,
+                                      const Fp* scale_hi, const Fp* tw_fwd, const Fp* tw_inv, const Fp* uniA,
+                                      const Fp* uniB) {
+  int bits[8];
+  const int np = spg_ntt_plan_bits(log_n, bits);
+  for (int pi = 0; pi < np; pi++) {
+    const int i = dit ? np - 1 - pi : pi;
+    int log_s = 0;
+    for (int k = i + 1; k < np; k++) log_s += bits[k];
+    NttPass& P = passes[pi];
+    P.in = (pi == 0) ? in : out;
+    P.out = out;
+    P.in_col_stride = (pi == 0) ? in_stride : out_stride;
+    P.out_col_stride = out_stride;
+    P.log_n = (int)log_n;
+    P.log_r = bits[i];
+    P.log_s = log_s;
+    P.inverse = inverse;
+    P.tw = inverse ? tw_inv : tw_fwd;
+    P.uniA = uniA;
+    P.uniB = uniB;
+    const int log_b = (int)log_n - P.log_r - log_s;
+    int log_g = log_ws - P.log_r;
+    if (log_s) { if (log_g > log_s) log_g = log_s; }
+    else { if (log_g > log_b) log_g = log_b; }
+    P.log_g = log_g;
+    P.ec = log_s ? (1ull << (SPG_UNI_LOG - (P.log_r + log_s))) : 0ull;
+    // coefficient index k = bitrev_n(pos); the r field of pos contributes bitrev_R(r) << log_b
+    P.e0 = coset_exp << log_b;
+    P.use_diag = (log_s != 0) || (dit && coset_exp != 0);
+    P.scale_lo = nullptr; P.scale_hi = nullptr;
+    if (log_s == 0) { P.scale_lo = scale_lo; P.scale_hi = scale_hi; }
+  }
+  return np;
+}

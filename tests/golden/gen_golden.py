@@ -151,6 +151,16 @@ def main():
         add_verify(z, r, s, ref.private_key_to_ec_point_on_stark_curve(d), "structural:zG==rQ")
     add_verify(z, r, s, tuple(ref.SHIFT_POINT), "structural:Q==shift")
     add_verify(z, r, s, tuple(ref.EC_GEN), "structural:Q==G")
+    # crafted public keys Q = (+-2^k - (r mod 2^k))^-1 * shift: the step-k partial sum of r*Q + shift
+    # collides in x with 2^k * Q (signature.py:183), so the reference answers False at step k
+    for kk, sign_ in ((0, 1), (1, 1), (7, -1), (100, 1), (250, -1)):
+        rr = rng.randrange(2**250, 2**251)
+        c = pow((sign_ * 2**kk - (rr % 2**kk)) % ref.EC_ORDER, -1, ref.EC_ORDER)
+        Q = ref.ec_mult(c, tuple(ref.SHIFT_POINT), ref.ALPHA, P)
+        ss = rng.randrange(1, ref.EC_ORDER)
+        while not (1 <= pow(ss, -1, ref.EC_ORDER) < 2**251):
+            ss = rng.randrange(1, ref.EC_ORDER)
+        add_verify(z, rr, ss, Q, "structural:collision@%d" % kk)
     out["verify"] = ver
     out["sign"] = sigs
 

@@ -1,0 +1,97 @@
+"""GPU parity: field ops and NTT through the C-ABI against the oracles (bit-exact)."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import rand_felts
+from oracle import clib, ntt as ontt
+from oracle.params import FIELD_PRIME as P
+from stark_perpetual_b200._lib import (NTT_NAT_TO_NAT, NTT_NAT_TO_REV, NTT_REV_TO_NAT, ints_to_limbs,
+                                       limbs_to_ints)
+
+pytestmark = pytest.mark.gpu
+
+EDGE = [0, 1, 2, P - 1, P - 2, 2**251, 2**192, 2**192 - 1, 2**64, 2**64 - 1, (P - 1) // 2, 17 * 2**192]
+
+
+def test_field_ops_vs_python(ctx):
+    rng = random.Random(11)
+    a = EDGE + [rng.randrange(P) for _ in range(4096 - len(EDGE))]
+    b = [rng.randrange(P) for _ in range(4096 - len(EDGE))] + EDGE[::-1]
+    A, B = ints_to_limbs(a), ints_to_limbs(b)
+    assert limbs_to_ints(ctx.field_op("mul", A, B)) == [x * y % P for x, y in zip(a, b)]
+    assert limbs_to_ints(ctx.field_op("add", A, B)) == [(x + y) % P for x, y in zip(a, b)]
+    assert limbs_to_ints(ctx.field_op("sub", A, B)) == [(x - y) % P for x, y in zip(a, b)]
+    nz = [x if x else 5 for x in a[:256]]
+    assert limbs_to_ints(ctx.field_op("inv", ints_to_limbs(nz))) == [pow(x, -1, P) for x in nz]
+    e = [rng.randrange(2**256) for _ in range(64)]
+    assert limbs_to_ints(ctx.field_op("pow", A[:64], ints_to_limbs(e))) == [pow(x, k, P) for x, k in zip(a[:64], e)]
+
+
+def test_field_mul_vs_c_oracle_large(ctx):
+    A, B = rand_felts(1 << 18, 21), rand_felts(1 << 18, 22)
+    assert np.array_equal(ctx.field_op("mul", A, B), clib.mul_batch(A, B))
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 4, 7, 10, 11, 12])
+def test_ntt_small_vs_python(ctx, log_n):
+    rng = random.Random(100 + log_n)
+    n = 1 << log_n
+    v = [rng.randrange(P) for _ in range(3 * n)]
+    if log_n >= 2:
+        v[0], v[1], v[2] = 0, 1, P - 1
+    arr = ints_to_limbs(v)
+    for inverse in (False, True):
+        want = sum((ontt.ntt(v[k * n:(k + 1) * n], inverse) for k in range(3)), [])
+        assert limbs_to_ints(ctx.ntt(arr, log_n, inverse, NTT_NAT_TO_NAT)) == want
+        rev = sum((ontt.bitrev_permute(want[k * n:(k + 1) * n]) for k in range(3)), [])
+        assert limbs_to_ints(ctx.ntt(arr, log_n, inverse, NTT_NAT_TO_REV)) == rev
+        vin = sum((ontt.bitrev_permute(v[k * n:(k + 1) * n]) for k in range(3)), [])
+        assert limbs_to_ints(ctx.ntt(ints_to_limbs(vin), log_n, inverse, NTT_REV_TO_NAT)) == want
+
+
+def test_ntt_2_18_config2(ctx):
+    """BASELINE.json configs[1]: 2^18-point NTT, seed 1002, bit-exact vs the CPU oracle,
+    natural->bit-reversed and natural->natural, and inverse(forward) == identity."""
+    log_n = 18
+    x = rand_felts(1 << log_n, 1002)
+    want = clib.ntt(x, log_n, False, 2)
+    # pin the C oracle to the Python oracle on a sample of outputs through linearity is costly; check
+    # a handful of output points by direct evaluation instead
+    xi = limbs_to_ints(x)
+    from oracle.params import root_of_unity
+    w = root_of_unity(log_n)
+    wi = limbs_to_ints(want)
+    for k in (0, 1, 77, (1 << log_n) - 1):
+        wk = pow(w, k, P)
+        acc, t = 0, 1
+        for i in range(1 << log_n):
+            acc += xi[i] * t
+            t = t * wk % P
+        assert acc % P == wi[k]
+    got = ctx.ntt(x, log_n, False, NTT_NAT_TO_NAT)
+    assert np.array_equal(got, want)
+    got_rev = ctx.ntt(x, log_n, False, NTT_NAT_TO_REV)
+    assert np.array_equal(got_rev, clib.ntt(x, log_n, False, 0))
+    back = ctx.ntt(got_rev, log_n, True, NTT_REV_TO_NAT)
+    assert np.array_equal(back, x)
+
+
+@pytest.mark.parametrize("log_n,batch", [(13, 5), (16, 3), (20, 2), (21, 1), (22, 1)])
+def test_ntt_large_vs_c_oracle(ctx, log_n, batch):
+    x = rand_felts(batch << log_n, 500 + log_n)
+    for inverse in (False, True):
+        assert np.array_equal(ctx.ntt(x, log_n, inverse, NTT_NAT_TO_REV), clib.ntt(x, log_n, inverse, 0))
+    fwd = ctx.ntt(x, log_n, False, NTT_NAT_TO_REV)
+    assert np.array_equal(ctx.ntt(fwd, log_n, True, NTT_REV_TO_NAT), x)
+
+
+def test_ntt_linearity_full_size(ctx):
+    """Size-independent property at 2^22: NTT(a + b) == NTT(a) + NTT(b)."""
+    log_n = 22
+    a, b = rand_felts(1 << log_n, 31), rand_felts(1 << log_n, 32)
+    s = ctx.field_op("add", a, b)
+    lhs = ctx.ntt(s, log_n, False, NTT_NAT_TO_REV)
+    rhs = ctx.field_op("add", ctx.ntt(a, log_n, False, NTT_NAT_TO_REV), ctx.ntt(b, log_n, False, NTT_NAT_TO_REV))
+    assert np.array_equal(lhs, rhs)
