@@ -117,7 +117,7 @@ class Context:
     # ---- field layer ----
     def field_op(self, op, a, b=None):
         """a, b: (n,4) uint64 canonical felts. op: 'mul','add','sub','inv','pow'."""
-        code = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "pow": 4}[op]
+        code = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "pow": 4, "rawmul": 5, "widelo": 6, "widehi": 7, "reduce": 8, "redcdbg": 9}[op]
         a = np.ascontiguousarray(a, dtype=np.uint64)
         out = np.empty_like(a)
         bp = None

@@ -110,6 +110,19 @@ extern "C" int spg_synchronize(spg_ctx* ctx) {
 __global__ void k_field_op(int op, const Fp* a, const Fp* b, Fp* out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (op >= 5) {   // debug probes: raw Montgomery product / wide product halves / reduce
+    Fp r;
+    if (op == 5) r = fp_mul(a[i], b[i]);
+    else if (op == 8) r = fp_reduce(a[i]);
+    else if (op == 9) { uint32_t t[16]; fpd_mul_wide(t, a[i], b[i]); fpd_redc(t, r.v); }
+    else {
+      uint32_t t[16];
+      fpd_mul_wide(t, a[i], b[i]);
+      for (int k = 0; k < 8; k++) r.v[k] = t[(op == 6 ? 0 : 8) + k];
+    }
+    out[i] = r;
+    return;
+  }
   Fp x = fp_to_mont(a[i]);
   Fp r;
   if (op == 3) {
@@ -126,7 +139,7 @@ __global__ void k_field_op(int op, const Fp* a, const Fp* b, Fp* out, size_t n) 
 
 extern "C" int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
                             size_t n, int flags) {
-  SPG_ARG(ctx && a && out && op >= 0 && op <= 4, "spg_field_op");
+  SPG_ARG(ctx && a && out && op >= 0 && op <= 9, "spg_field_op");
   SPG_ARG(op == 3 || b, "spg_field_op: b required");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;

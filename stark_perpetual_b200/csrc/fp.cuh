@@ -82,8 +82,8 @@ SPG_D Fp fpd_csub(const Fp& a, uint32_t k0, uint32_t k6, uint32_t k7) {
       "subc.cc.u32 %6, %15, %18;\n\t"
       "subc.cc.u32 %7, %16, %19;\n\t"
       "subc.u32 %8, 0, 0;"
-      : "=r"(t.v[0]), "=r"(t.v[1]), "=r"(t.v[2]), "=r"(t.v[3]), "=r"(t.v[4]), "=r"(t.v[5]),
-        "=r"(t.v[6]), "=r"(t.v[7]), "=r"(borrow)
+      : "=&r"(t.v[0]), "=&r"(t.v[1]), "=&r"(t.v[2]), "=&r"(t.v[3]), "=&r"(t.v[4]), "=&r"(t.v[5]),
+        "=&r"(t.v[6]), "=&r"(t.v[7]), "=&r"(borrow)
       : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
         "r"(a.v[7]), "r"(k0), "r"(k6), "r"(k7));
   Fp r;
@@ -103,8 +103,8 @@ SPG_D Fp fpd_add(const Fp& a, const Fp& b) {
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, %23;"
-      : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]),
-        "=r"(s.v[6]), "=r"(s.v[7])
+      : "=&r"(s.v[0]), "=&r"(s.v[1]), "=&r"(s.v[2]), "=&r"(s.v[3]), "=&r"(s.v[4]), "=&r"(s.v[5]),
+        "=&r"(s.v[6]), "=&r"(s.v[7])
       : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
         "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
         "r"(b.v[6]), "r"(b.v[7]));
@@ -121,8 +121,8 @@ SPG_D Fp fpd_add_raw(const Fp& a, const Fp& b) {
       "addc.cc.u32 %5, %13, %21;\n\t"
       "addc.cc.u32 %6, %14, %22;\n\t"
       "addc.u32 %7, %15, %23;"
-      : "=r"(s.v[0]), "=r"(s.v[1]), "=r"(s.v[2]), "=r"(s.v[3]), "=r"(s.v[4]), "=r"(s.v[5]),
-        "=r"(s.v[6]), "=r"(s.v[7])
+      : "=&r"(s.v[0]), "=&r"(s.v[1]), "=&r"(s.v[2]), "=&r"(s.v[3]), "=&r"(s.v[4]), "=&r"(s.v[5]),
+        "=&r"(s.v[6]), "=&r"(s.v[7])
       : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
         "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
         "r"(b.v[6]), "r"(b.v[7]));
@@ -142,8 +142,8 @@ SPG_D Fp fpd_sub(const Fp& a, const Fp& b) {
       "subc.cc.u32 %6, %15, %23;\n\t"
       "subc.cc.u32 %7, %16, %24;\n\t"
       "subc.u32 %8, 0, 0;"
-      : "=r"(d.v[0]), "=r"(d.v[1]), "=r"(d.v[2]), "=r"(d.v[3]), "=r"(d.v[4]), "=r"(d.v[5]),
-        "=r"(d.v[6]), "=r"(d.v[7]), "=r"(borrow)
+      : "=&r"(d.v[0]), "=&r"(d.v[1]), "=&r"(d.v[2]), "=&r"(d.v[3]), "=&r"(d.v[4]), "=&r"(d.v[5]),
+        "=&r"(d.v[6]), "=&r"(d.v[7]), "=&r"(borrow)
       : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
         "r"(a.v[7]), "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]),
         "r"(b.v[6]), "r"(b.v[7]));
@@ -158,8 +158,8 @@ SPG_D Fp fpd_sub(const Fp& a, const Fp& b) {
       "addc.cc.u32 %5, %13, 0;\n\t"
       "addc.cc.u32 %6, %14, %17;\n\t"
       "addc.u32 %7, %15, %18;"
-      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
-        "=r"(r.v[6]), "=r"(r.v[7])
+      : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]),
+        "=&r"(r.v[6]), "=&r"(r.v[7])
       : "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]), "r"(d.v[6]),
         "r"(d.v[7]), "r"(k0), "r"(k6), "r"(k7));
   return r;
@@ -182,8 +182,8 @@ SPG_D Fp fpd_reduce(const Fp& a) {
       "mul.hi.u32 %5, %10, %12;\n\t"                                                    \
       "mul.lo.u32 %6, %11, %12;\n\t"                                                    \
       "mul.hi.u32 %7, %11, %12;"                                                        \
-      : "=r"(acc[k]), "=r"(acc[k + 1]), "=r"(acc[k + 2]), "=r"(acc[k + 3]), "=r"(acc[k + 4]), \
-        "=r"(acc[k + 5]), "=r"(acc[k + 6]), "=r"(acc[k + 7])                             \
+      : "=&r"(acc[k]), "=&r"(acc[k + 1]), "=&r"(acc[k + 2]), "=&r"(acc[k + 3]), "=&r"(acc[k + 4]), \
+        "=&r"(acc[k + 5]), "=&r"(acc[k + 6]), "=&r"(acc[k + 7])                             \
       : "r"(A0), "r"(A1), "r"(A2), "r"(A3), "r"(B))
 
 #define SPG_ROW_MAD(acc, k, A0, A1, A2, A3, B)                                         \
@@ -236,9 +236,9 @@ SPG_D void fpd_mul_wide(uint32_t (&t)[16], const Fp& a, const Fp& b) {
       "addc.cc.u32 %12, %27, %42;\n\t"
       "addc.cc.u32 %13, %28, %43;\n\t"
       "addc.u32 %14, %29, %44;"
-      : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
-        "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]),
-        "=r"(t[15])
+      : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]),
+        "=&r"(t[8]), "=&r"(t[9]), "=&r"(t[10]), "=&r"(t[11]), "=&r"(t[12]), "=&r"(t[13]), "=&r"(t[14]),
+        "=&r"(t[15])
       : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]),
         "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
         "r"(O[0]), "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]),
@@ -246,114 +246,102 @@ SPG_D void fpd_mul_wide(uint32_t (&t)[16], const Fp& a, const Fp& b) {
 }
 
 // Montgomery reduction of a 512-bit value T (< 2^508): returns T * 2^-256 mod p, lazily
-// (< p + T/2^256).  Uses p = 1 + p3*2^192, p3 = 2^59 + 17:
-//   Ml = -T[0..191] mod 2^192, c0 = (T[0..191] != 0)
-//   Q  = p3 * Ml                      (256 bits)
-//   x  = T[192..255] + c0 + Q[0..63]  (64 bits, carry c1)
-//   m3 = -x mod 2^64, c3 = (x != 0),  Q' = p3 * m3   (128 bits)
-//   result = T[256..511] + (Q >> 64) + c1 + c3 + Q' * 2^128
-SPG_D Fp fpd_redc(const uint32_t (&t)[16]) {
-  uint32_t m[6], c0;
-  asm("sub.cc.u32 %0, 0, %7;\n\t"
-      "subc.cc.u32 %1, 0, %8;\n\t"
-      "subc.cc.u32 %2, 0, %9;\n\t"
-      "subc.cc.u32 %3, 0, %10;\n\t"
-      "subc.cc.u32 %4, 0, %11;\n\t"
-      "subc.cc.u32 %5, 0, %12;\n\t"
-      "subc.u32 %6, 0, 0;"
-      : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(m[3]), "=r"(m[4]), "=r"(m[5]), "=r"(c0)
-      : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]));
-  c0 &= 1u;  // borrow mask -> 0/1
-  // A = 17 * Ml  (7 limbs) = (Ml << 4) + Ml
-  uint32_t s4[7];
-  s4[0] = m[0] << 4;
+// (0 < result <= p + T/2^256).  Subtractive form, free of multi-limb negations (ptxas 12.9 folds a
+// negation into LEA-with-carry and gets the carry wrong when the shifted operand wraps to zero, which
+// broke an earlier additive version).  With p = 1 + p3*2^192, p3 = 2^59 + 17, p^-1 = 1 - p3*2^192 (mod 2^256):
+//   V  = p3 * T[0..63] mod 2^64
+//   M  = T[0..255] * p^-1 mod 2^256 = T[0..191] | ((T[192..255] - V) mod 2^64) << 192 ,  c = borrow of that
+//   U  = p3 * M = 17*M + (M << 59)                     (320 bits; its low 64 bits equal V)
+//   result = T[256..511] + (p - c) - (U >> 64)         (M*p == T mod 2^256, so the low halves cancel exactly)
+SPG_D Fp fpd_redc(const uint32_t (&t)[16], uint32_t* dbg = nullptr) {
+  // V = (v0, v1)
+  uint32_t v0, v1;
+  {
+    uint32_t a0 = t[0] << 4, a1 = __funnelshift_l(t[0], t[1], 4), b1 = t[0] << 27;
+    asm("add.cc.u32 %0, %2, %4;\n\t"
+        "addc.u32 %1, %3, %5;\n\t"
+        "add.u32 %1, %1, %6;"
+        : "=&r"(v0), "=&r"(v1)
+        : "r"(a0), "r"(a1), "r"(t[0]), "r"(t[1]), "r"(b1));
+  }
+  uint32_t w[8], c;
 #pragma unroll
-  for (int i = 1; i < 6; i++) s4[i] = __funnelshift_l(m[i - 1], m[i], 4);
-  s4[6] = m[5] >> 28;
-  uint32_t A[7];
-  asm("add.cc.u32 %0, %7, %14;\n\t"
-      "addc.cc.u32 %1, %8, %15;\n\t"
-      "addc.cc.u32 %2, %9, %16;\n\t"
-      "addc.cc.u32 %3, %10, %17;\n\t"
-      "addc.cc.u32 %4, %11, %18;\n\t"
-      "addc.cc.u32 %5, %12, %19;\n\t"
-      "addc.u32 %6, %13, 0;"
-      : "=r"(A[0]), "=r"(A[1]), "=r"(A[2]), "=r"(A[3]), "=r"(A[4]), "=r"(A[5]), "=r"(A[6])
-      : "r"(s4[0]), "r"(s4[1]), "r"(s4[2]), "r"(s4[3]), "r"(s4[4]), "r"(s4[5]), "r"(s4[6]),
-        "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(m[4]), "r"(m[5]));
-  // B = Ml << 59 = (Ml << 27) << 32 : limbs B[1..7]
-  uint32_t B[8];
-  B[1] = m[0] << 27;
-#pragma unroll
-  for (int i = 1; i < 6; i++) B[i + 1] = __funnelshift_l(m[i - 1], m[i], 27);
-  B[7] = m[5] >> 5;
-  // Q = A + B  (8 limbs, Q[0] = A[0])
-  uint32_t Q[8];
-  Q[0] = A[0];
-  asm("add.cc.u32 %0, %7, %13;\n\t"
-      "addc.cc.u32 %1, %8, %14;\n\t"
-      "addc.cc.u32 %2, %9, %15;\n\t"
-      "addc.cc.u32 %3, %10, %16;\n\t"
-      "addc.cc.u32 %4, %11, %17;\n\t"
-      "addc.cc.u32 %5, %12, %18;\n\t"
-      "addc.u32 %6, 0, %19;"
-      : "=r"(Q[1]), "=r"(Q[2]), "=r"(Q[3]), "=r"(Q[4]), "=r"(Q[5]), "=r"(Q[6]), "=r"(Q[7])
-      : "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(B[1]), "r"(B[2]),
-        "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
-  // x = T[6..7] + Q[0..1] + c0 ; c1 = carries (0..1, see header comment)
-  uint32_t x0, x1, c1;
-  asm("add.cc.u32 %0, %3, %5;\n\t"
-      "addc.cc.u32 %1, %4, %6;\n\t"
-      "addc.u32 %2, 0, 0;\n\t"
-      "add.cc.u32 %0, %0, %7;\n\t"
-      "addc.cc.u32 %1, %1, 0;\n\t"
-      "addc.u32 %2, %2, 0;"
-      : "=&r"(x0), "=&r"(x1), "=&r"(c1)
-      : "r"(t[6]), "r"(t[7]), "r"(Q[0]), "r"(Q[1]), "r"(c0));
-  // m3 = -x, c3 = (x != 0)
-  uint32_t n0, n1, c3;
-  asm("sub.cc.u32 %0, 0, %3;\n\t"
-      "subc.cc.u32 %1, 0, %4;\n\t"
+  for (int i = 0; i < 6; i++) w[i] = t[i];
+  asm("sub.cc.u32 %0, %3, %5;\n\t"
+      "subc.cc.u32 %1, %4, %6;\n\t"
       "subc.u32 %2, 0, 0;"
-      : "=r"(n0), "=r"(n1), "=r"(c3)
-      : "r"(x0), "r"(x1));
-  c3 &= 1u;
-  // Q' = p3 * m3 = 17*m3 + (m3 << 59): 4 limbs
-  uint32_t a0 = n0 << 4, a1 = __funnelshift_l(n0, n1, 4), a2 = n1 >> 28;
-  uint32_t b1 = n0 << 27, b2 = __funnelshift_l(n0, n1, 27), b3 = n1 >> 5;
-  uint32_t q0, q1, q2, q3;
-  asm("add.cc.u32 %0, %4, %7;\n\t"
-      "addc.cc.u32 %1, %5, %8;\n\t"
-      "addc.u32 %2, %6, 0;\n\t"
-      "add.cc.u32 %1, %1, %9;\n\t"
-      "addc.cc.u32 %2, %2, %10;\n\t"
-      "addc.u32 %3, 0, %11;"
-      : "=&r"(q0), "=&r"(q1), "=&r"(q2), "=&r"(q3)
-      : "r"(a0), "r"(a1), "r"(a2), "r"(n0), "r"(n1), "r"(b1), "r"(b2), "r"(b3));
-  // result = T[8..15] + Q[2..7] + (c1 + c3) + Q' << 128
-  uint32_t cc = c1 + c3;
-  Fp r;
+      : "=&r"(w[6]), "=&r"(w[7]), "=&r"(c)
+      : "r"(t[6]), "r"(t[7]), "r"(v0), "r"(v1));
+  const uint32_t k0 = (c & 1u) ^ 1u;   // limb 0 of (p - c)
+  // A = 17 * M = (M << 4) + M   (9 limbs)
+  uint32_t s4[9];
+  s4[0] = w[0] << 4;
+#pragma unroll
+  for (int i = 1; i < 8; i++) s4[i] = __funnelshift_l(w[i - 1], w[i], 4);
+  s4[8] = w[7] >> 28;
+  uint32_t A[9];
+  asm("add.cc.u32 %0, %9, %18;\n\t"
+      "addc.cc.u32 %1, %10, %19;\n\t"
+      "addc.cc.u32 %2, %11, %20;\n\t"
+      "addc.cc.u32 %3, %12, %21;\n\t"
+      "addc.cc.u32 %4, %13, %22;\n\t"
+      "addc.cc.u32 %5, %14, %23;\n\t"
+      "addc.cc.u32 %6, %15, %24;\n\t"
+      "addc.cc.u32 %7, %16, %25;\n\t"
+      "addc.u32 %8, %17, 0;"
+      : "=&r"(A[0]), "=&r"(A[1]), "=&r"(A[2]), "=&r"(A[3]), "=&r"(A[4]), "=&r"(A[5]), "=&r"(A[6]),
+        "=&r"(A[7]), "=&r"(A[8])
+      : "r"(s4[0]), "r"(s4[1]), "r"(s4[2]), "r"(s4[3]), "r"(s4[4]), "r"(s4[5]), "r"(s4[6]), "r"(s4[7]),
+        "r"(s4[8]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]));
+  // B = M << 59 : limbs B[1..9]
+  uint32_t B[10];
+  B[1] = w[0] << 27;
+#pragma unroll
+  for (int i = 1; i < 8; i++) B[i + 1] = __funnelshift_l(w[i - 1], w[i], 27);
+  B[9] = w[7] >> 5;
+  // X = (A + B) >> 64 : limbs U[2..9]; limb 1 only feeds its carry
+  uint32_t U1, X[8];
+  asm("add.cc.u32 %0, %9, %17;\n\t"
+      "addc.cc.u32 %1, %10, %18;\n\t"
+      "addc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, %20;\n\t"
+      "addc.cc.u32 %4, %13, %21;\n\t"
+      "addc.cc.u32 %5, %14, %22;\n\t"
+      "addc.cc.u32 %6, %15, %23;\n\t"
+      "addc.cc.u32 %7, %16, %24;\n\t"
+      "addc.u32 %8, 0, %25;"
+      : "=&r"(U1), "=&r"(X[0]), "=&r"(X[1]), "=&r"(X[2]), "=&r"(X[3]), "=&r"(X[4]), "=&r"(X[5]), "=&r"(X[6]),
+        "=&r"(X[7])
+      : "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]), "r"(B[1]),
+        "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]), "r"(B[8]), "r"(B[9]));
+  if (dbg) { dbg[0] = c; dbg[1] = v0; dbg[2] = v1; dbg[3] = w[6]; dbg[4] = w[7]; dbg[5] = U1; dbg[6] = X[0]; dbg[7] = X[7]; }
+  // result = (T_hi + (p - c)) - X
+  Fp h, r;
   asm("add.cc.u32 %0, %8, %16;\n\t"
-      "addc.cc.u32 %1, %9, %17;\n\t"
-      "addc.cc.u32 %2, %10, %18;\n\t"
-      "addc.cc.u32 %3, %11, %19;\n\t"
-      "addc.cc.u32 %4, %12, %20;\n\t"
-      "addc.cc.u32 %5, %13, %21;\n\t"
-      "addc.cc.u32 %6, %14, 0;\n\t"
-      "addc.u32 %7, %15, 0;\n\t"
-      "add.cc.u32 %0, %0, %22;\n\t"
-      "addc.cc.u32 %1, %1, 0;\n\t"
-      "addc.cc.u32 %2, %2, 0;\n\t"
-      "addc.cc.u32 %3, %3, 0;\n\t"
-      "addc.cc.u32 %4, %4, %23;\n\t"
-      "addc.cc.u32 %5, %5, %24;\n\t"
-      "addc.cc.u32 %6, %6, %25;\n\t"
-      "addc.u32 %7, %7, %26;"
+      "addc.cc.u32 %1, %9, 0;\n\t"
+      "addc.cc.u32 %2, %10, 0;\n\t"
+      "addc.cc.u32 %3, %11, 0;\n\t"
+      "addc.cc.u32 %4, %12, 0;\n\t"
+      "addc.cc.u32 %5, %13, 0;\n\t"
+      "addc.cc.u32 %6, %14, %17;\n\t"
+      "addc.u32 %7, %15, %18;"
+      : "=&r"(h.v[0]), "=&r"(h.v[1]), "=&r"(h.v[2]), "=&r"(h.v[3]), "=&r"(h.v[4]), "=&r"(h.v[5]),
+        "=&r"(h.v[6]), "=&r"(h.v[7])
+      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]),
+        "r"(k0), "r"(SPG_P6), "r"(SPG_P7));
+  asm("sub.cc.u32 %0, %8, %16;\n\t"
+      "subc.cc.u32 %1, %9, %17;\n\t"
+      "subc.cc.u32 %2, %10, %18;\n\t"
+      "subc.cc.u32 %3, %11, %19;\n\t"
+      "subc.cc.u32 %4, %12, %20;\n\t"
+      "subc.cc.u32 %5, %13, %21;\n\t"
+      "subc.cc.u32 %6, %14, %22;\n\t"
+      "subc.u32 %7, %15, %23;"
       : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]),
         "=&r"(r.v[6]), "=&r"(r.v[7])
-      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]),
-        "r"(t[15]), "r"(Q[2]), "r"(Q[3]), "r"(Q[4]), "r"(Q[5]), "r"(Q[6]), "r"(Q[7]), "r"(cc),
-        "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+      : "r"(h.v[0]), "r"(h.v[1]), "r"(h.v[2]), "r"(h.v[3]), "r"(h.v[4]), "r"(h.v[5]), "r"(h.v[6]),
+        "r"(h.v[7]), "r"(X[0]), "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]));
+  (void)U1;
   return r;
 }
 
