@@ -32,6 +32,8 @@ typedef struct spg_ctx spg_ctx;
 #define SPG_E_PROOF (-5)     /* prover could not build a proof (e.g. trace does not satisfy the AIR) */
 
 #define SPG_DEVICE_PTRS 1    /* flags: buffers are device pointers */
+#define SPG_NO_SYNC 2        /* flags (with SPG_DEVICE_PTRS): enqueue on the context stream and return; the
+                                caller synchronises (spg_synchronize / its own events) */
 
 /* NTT orderings */
 #define SPG_NTT_NAT_TO_REV 0 /* natural order in, bit-reversed out (DIF) */
@@ -47,6 +49,11 @@ double spg_last_kernel_ms(spg_ctx* ctx);
 /* number of kernel launches issued by this context since creation */
 uint64_t spg_launch_count(spg_ctx* ctx);
 int spg_synchronize(spg_ctx* ctx);
+/* run all subsequent work of this context on an existing CUDA stream (a cudaStream_t, e.g. the host
+ * framework's current stream) instead of the context's own one */
+int spg_set_stream(spg_ctx* ctx, void* cuda_stream);
+/* device milliseconds of stage `stage` of the last pipeline call (stage ids are listed per entry point) */
+double spg_stage_ms(spg_ctx* ctx, int stage);
 
 /* ---- field layer (a1/a2 of SURVEY section 8; signature.py:41-42, math_utils.py:50-56) ----------------- */
 /* out[i] = op(a[i], b[i]); op: 0 mul, 1 add, 2 sub, 3 inverse of a (b ignored), 4 a^b[0..3] */
@@ -60,6 +67,22 @@ int spg_bench_field_mul(spg_ctx* ctx, int iters, int chains, double* mul_per_s, 
 /* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
  * inverse != 0 uses omega^-1 and scales by 2^-log_n. */
 int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batch, int inverse, int order, int flags);
+
+/* ---- LDE (BASELINE.json configs[2]; no reference symbol) ------------------------------
+ * trace: n_cols columns of 2^log_n felts, column-major [n_cols][N], values on <w_N> in natural order.
+ * out:   [B][n_cols][N], B = 2^log_blowup:  out[j][c][i] = f_c(g * w_{BN}^j * w_N^i), f_c the degree < N
+ *        interpolant of column c, g = *coset_offset (canonical felt, HOST pointer; NULL = 3 = FIELD_GEN,
+ *        signature.py:42).  Stages for spg_stage_ms: 0 interpolation (inverse NTT), 1 coset evaluations. */
+int spg_lde(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size_t n_cols, unsigned log_blowup,
+            const uint64_t* coset_offset, uint64_t* out, int flags);
+/* The two phases of spg_lde separately, for the multi-GPU split (device pointers only):
+ *   spg_lde_coeffs: columns -> coefficient columns scaled by g^k, bit-reversed order (column-sharded phase);
+ *   spg_lde_cosets: (all-gathered) coefficient columns -> cosets [coset_begin, coset_begin + coset_count),
+ *                   out[j - coset_begin][c][i]  (coset-sharded phase). */
+int spg_lde_coeffs(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size_t n_cols,
+                   const uint64_t* coset_offset, uint64_t* coeffs, int flags);
+int spg_lde_cosets(spg_ctx* ctx, const uint64_t* coeffs, unsigned log_n, size_t n_cols, unsigned log_blowup,
+                   size_t coset_begin, size_t coset_count, uint64_t* out, int flags);
 
 #ifdef __cplusplus
 }

@@ -148,6 +148,40 @@ void spgo_ntt(uint64_t* data, unsigned log_n, size_t batch, int inverse, int ord
   free(tw);
 }
 
+/* LDE: trace [C][N] canonical, natural order on <w_N>  ->  out [B][C][N],
+ * out[j][c][i] = f_c(g * w_{BN}^j * w_N^i)  (same convention as oracle/ntt.py lde()).  g canonical. */
+void spgo_lde(const uint64_t* trace, unsigned log_n, size_t C, unsigned log_blowup, const uint64_t* g_canon,
+              uint64_t* out) {
+  size_t n = (size_t)1 << log_n, B = (size_t)1 << log_blowup;
+  fe* twi = make_twiddles((int)log_n, 1);
+  fe* twf = make_twiddles((int)log_n, 0);
+  fe ninv, nn = {{(uint64_t)n, 0, 0, 0}}, g, wb;
+  to_mont(&nn, &nn); fe_inv(&ninv, &nn);
+  memcpy(&g, g_canon, 32); to_mont(&g, &g);
+  root_of_unity(&wb, (int)(log_n + log_blowup));
+#pragma omp parallel for schedule(dynamic)
+  for (size_t c = 0; c < C; c++) {
+    fe* coef = (fe*)malloc(n * sizeof(fe));
+    fe* tmp = (fe*)malloc(n * sizeof(fe));
+    fe* work = (fe*)malloc(n * sizeof(fe));
+    memcpy(tmp, trace + 4 * n * c, n * sizeof(fe));
+    dif_core(tmp, n, twi);
+    for (size_t i = 0; i < n; i++) fe_mul(&coef[bitrev((unsigned)i, (int)log_n)], &tmp[i], &ninv);
+    /* coef now canonical * (Montgomery ninv) = canonical c_k */
+    fe s = g;   /* Montgomery */
+    for (size_t j = 0; j < B; j++) {
+      fe acc = R1;
+      for (size_t k = 0; k < n; k++) { fe_mul(&work[k], &coef[k], &acc); fe_mul(&acc, &acc, &s); }
+      dif_core(work, n, twf);
+      fe* o = (fe*)(out + 4 * n * (j * C + c));
+      for (size_t i = 0; i < n; i++) o[bitrev((unsigned)i, (int)log_n)] = work[i];
+      fe_mul(&s, &s, &wb);
+    }
+    free(coef); free(tmp); free(work);
+  }
+  free(twi); free(twf);
+}
+
 int spgo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

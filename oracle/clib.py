@@ -45,3 +45,14 @@ def ntt(data, log_n, inverse=False, order=2):
     n = 1 << log_n
     lib().spgo_ntt(_p(arr), C.c_uint(log_n), C.c_size_t(arr.shape[0] // n), C.c_int(int(inverse)), C.c_int(order))
     return arr
+
+
+def lde(trace, log_n, n_cols, log_blowup, offset=3):
+    """trace (n_cols * 2^log_n, 4) -> (2^log_blowup * n_cols * 2^log_n, 4), layout [B][C][N]."""
+    tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
+    n = 1 << log_n
+    assert tr.shape[0] == n_cols * n
+    out = np.empty(((n_cols * n) << log_blowup, 4), dtype=np.uint64)
+    g = np.frombuffer(int(offset).to_bytes(32, "little"), dtype="<u8").copy()
+    lib().spgo_lde(_p(tr), C.c_uint(log_n), C.c_size_t(n_cols), C.c_uint(log_blowup), _p(g), _p(out))
+    return out

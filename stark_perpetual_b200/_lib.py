@@ -12,6 +12,7 @@ _LOCK = threading.Lock()
 FIELD_PRIME = 2**251 + 17 * 2**192 + 1
 
 SPG_DEVICE_PTRS = 1
+SPG_NO_SYNC = 2
 NTT_NAT_TO_REV, NTT_REV_TO_NAT, NTT_NAT_TO_NAT = 0, 1, 2
 
 
@@ -46,6 +47,11 @@ def _load():
             "spg_field_op": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_bench_field_mul": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
             "spg_ntt": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_int, C.c_int, C.c_int]),
+            "spg_set_stream": (C.c_int, [vp, vp]),
+            "spg_stage_ms": (C.c_double, [vp, C.c_int]),
+            "spg_lde": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, vp, vp, C.c_int]),
+            "spg_lde_coeffs": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, vp, vp, C.c_int]),
+            "spg_lde_cosets": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, C.c_size_t, C.c_size_t, vp, C.c_int]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)     # AttributeError if the symbol is missing: loud by design
@@ -114,6 +120,13 @@ class Context:
     def synchronize(self):
         self._check(self._lib.spg_synchronize(self._h))
 
+    def set_stream(self, cuda_stream_handle):
+        """Run this context's work on an existing CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._lib.spg_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def stage_ms(self, stage):
+        return self._lib.spg_stage_ms(self._h, int(stage))
+
     # ---- field layer ----
     def field_op(self, op, a, b=None):
         """a, b: (n,4) uint64 canonical felts. op: 'mul','add','sub','inv','pow'."""
@@ -146,6 +159,41 @@ class Context:
         """In-place transform of device-resident data (pointer from torch .data_ptr())."""
         self._check(self._lib.spg_ntt(self._h, C.c_void_p(dev_ptr), log_n, batch, int(bool(inverse)), order,
                                       SPG_DEVICE_PTRS))
+
+
+    # ---- LDE ----
+    def _offset(self, offset):
+        if offset is None:
+            return None, None
+        arr = ints_to_limbs([offset])
+        return arr, _ptr(arr)
+
+    def lde(self, trace, log_n, n_cols, log_blowup, offset=None):
+        """trace: (n_cols * 2^log_n, 4) canonical felts, column-major; returns ([B * n_cols * N], 4),
+        layout [B][n_cols][N] (include/spg.h spg_lde)."""
+        tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
+        assert tr.shape[0] == n_cols << log_n
+        out = np.empty((tr.shape[0] << log_blowup, 4), dtype=np.uint64)
+        keep, op = self._offset(offset)
+        self._check(self._lib.spg_lde(self._h, _ptr(tr), log_n, n_cols, log_blowup, op, _ptr(out), 0))
+        return out
+
+    def lde_device(self, trace_ptr, log_n, n_cols, log_blowup, out_ptr, offset=None, sync=True):
+        keep, op = self._offset(offset)
+        flags = SPG_DEVICE_PTRS | (0 if sync else SPG_NO_SYNC)
+        self._check(self._lib.spg_lde(self._h, C.c_void_p(trace_ptr), log_n, n_cols, log_blowup, op,
+                                      C.c_void_p(out_ptr), flags))
+
+    def lde_coeffs_device(self, trace_ptr, log_n, n_cols, coeffs_ptr, offset=None, sync=True):
+        keep, op = self._offset(offset)
+        flags = SPG_DEVICE_PTRS | (0 if sync else SPG_NO_SYNC)
+        self._check(self._lib.spg_lde_coeffs(self._h, C.c_void_p(trace_ptr), log_n, n_cols, op,
+                                             C.c_void_p(coeffs_ptr), flags))
+
+    def lde_cosets_device(self, coeffs_ptr, log_n, n_cols, log_blowup, coset_begin, coset_count, out_ptr, sync=True):
+        flags = SPG_DEVICE_PTRS | (0 if sync else SPG_NO_SYNC)
+        self._check(self._lib.spg_lde_cosets(self._h, C.c_void_p(coeffs_ptr), log_n, n_cols, log_blowup,
+                                             coset_begin, coset_count, C.c_void_p(out_ptr), flags))
 
 
 _CTX = {}

@@ -26,7 +26,52 @@ struct spg_ctx {
   Fp* const_points = nullptr;   // 506 x (x, y) Montgomery
   // scratch cache
   std::vector<void*> owned;
+  bool own_stream = true;
+  bool ntt_attr_set = false;
+  // growable scratch slots (device), kept until spg_destroy
+  void* scratch_p[8] = {nullptr};
+  size_t scratch_sz[8] = {0};
+  // LDE scale tables cached per (log_n, offset): lo[R] , hi[B]
+  int lde_log_n = -1;
+  uint64_t lde_offset[4] = {0, 0, 0, 0};
+  Fp* lde_lo = nullptr;
+  Fp* lde_hi = nullptr;
+  // per-stage device milliseconds of the last pipeline call (spg_stage_ms)
+  double stage_ms[16] = {0};
+  cudaEvent_t stage_ev[16][2] = {{nullptr}};
+  bool stage_used[16] = {false};
 };
+
+// stage timers: events on the context stream; spg_stage_collect() after a stream sync fills stage_ms
+static inline void spg_stage_begin(spg_ctx* ctx, int s) {
+  if (!ctx->stage_ev[s][0]) { cudaEventCreate(&ctx->stage_ev[s][0]); cudaEventCreate(&ctx->stage_ev[s][1]); }
+  cudaEventRecord(ctx->stage_ev[s][0], ctx->stream);
+  ctx->stage_used[s] = true;
+}
+static inline void spg_stage_end(spg_ctx* ctx, int s) { cudaEventRecord(ctx->stage_ev[s][1], ctx->stream); }
+static inline void spg_stage_reset(spg_ctx* ctx) {
+  for (int s = 0; s < 16; s++) { ctx->stage_used[s] = false; ctx->stage_ms[s] = 0.0; }
+}
+static inline void spg_stage_collect(spg_ctx* ctx) {
+  for (int s = 0; s < 16; s++) {
+    if (!ctx->stage_used[s]) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->stage_ev[s][0], ctx->stage_ev[s][1]) == cudaSuccess) ctx->stage_ms[s] = ms;
+  }
+}
+
+// device scratch slot `slot` of at least `bytes` (grown by reallocation; contents not preserved)
+static inline cudaError_t spg_scratch(spg_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (ctx->scratch_sz[slot] < bytes) {
+    if (ctx->scratch_p[slot]) cudaFree(ctx->scratch_p[slot]);
+    ctx->scratch_p[slot] = nullptr; ctx->scratch_sz[slot] = 0;
+    cudaError_t e = cudaMalloc(&ctx->scratch_p[slot], bytes);
+    if (e != cudaSuccess) return e;
+    ctx->scratch_sz[slot] = bytes;
+  }
+  *out = ctx->scratch_p[slot];
+  return cudaSuccess;
+}
 
 #define SPG_CUDA(call)                                                                  \
   do {                                                                                  \
@@ -70,3 +115,7 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
                    const Fp* scale_lo, const Fp* scale_hi);
 int spg_bitrev_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols);
+// lde.cu: device-resident LDE, trace [C][N] -> out [B][C][N]; coeffs (optional) receives the scaled
+// coefficient columns g^k c_k (bit-reversed order)
+int spg_lde_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, unsigned log_blowup,
+                   const uint64_t* offset_canon, Fp* out, Fp* coeffs);

@@ -90,16 +90,31 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
   if (ctx->device >= 0) cudaSetDevice(ctx->device);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->uniA); cudaFree(ctx->uniB);
   cudaFree(ctx->const_points);
+  cudaFree(ctx->lde_lo); cudaFree(ctx->lde_hi);
   for (void* p : ctx->owned) cudaFree(p);
+  for (void* p : ctx->scratch_p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (auto& e : ctx->stage_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }
+  if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
 
 extern "C" const char* spg_last_error(spg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" double spg_last_kernel_ms(spg_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
 extern "C" uint64_t spg_launch_count(spg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int spg_set_stream(spg_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return SPG_E_ARG;
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return SPG_OK;
+}
+extern "C" double spg_stage_ms(spg_ctx* ctx, int stage) {
+  return (ctx && stage >= 0 && stage < 16) ? ctx->stage_ms[stage] : 0.0;
+}
 extern "C" int spg_synchronize(spg_ctx* ctx) {
   SPG_CUDA(cudaSetDevice(ctx->device));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));

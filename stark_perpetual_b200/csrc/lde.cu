@@ -1,0 +1,151 @@
+// Low-degree extension of trace columns (SURVEY.md section 8 row p2 / BASELINE.json configs[2]).
+// No reference symbol exists for this stage; conventions are this repo's own (DESIGN.md "LDE"):
+//   column values are evaluations on <w_N> in natural order; the extension is evaluated on the B
+//   cosets  g * w_{BN}^j * <w_N>,  j = 0..B-1 (g = 3 by default = FIELD_GEN, signature.py:42), each
+//   in natural order, stored coset-major:  out[j][c][i] = f_c(g * w_{BN}^j * w_N^i).
+//
+// Data flow per column:  inverse DIF (natural -> bit-reversed) with the factors g^k / N folded into
+// the store phase of its last pass, then per coset one forward DIT (bit-reversed -> natural) whose
+// load phase applies w_{BN}^(j k).  No permutation or scaling pass touches HBM on its own.
+#include <string.h>
+
+#include "common.h"
+#include "ntt.cuh"
+
+static int ensure_scale_tables(spg_ctx* ctx, unsigned log_n, const uint64_t* offset) {
+  if (ctx->lde_log_n == (int)log_n && memcmp(ctx->lde_offset, offset, 32) == 0) return SPG_OK;
+  std::vector<Fp> lo, hi;
+  spg_lde_scale_tables(log_n, spg_host_from_u64(offset), lo, hi);
+  const size_t R = lo.size(), B = hi.size();
+  cudaFree(ctx->lde_lo); cudaFree(ctx->lde_hi);
+  ctx->lde_lo = ctx->lde_hi = nullptr; ctx->lde_log_n = -1;
+  SPG_CUDA(cudaMalloc((void**)&ctx->lde_lo, R * sizeof(Fp)));
+  SPG_CUDA(cudaMalloc((void**)&ctx->lde_hi, B * sizeof(Fp)));
+  SPG_CUDA(cudaMemcpy(ctx->lde_lo, lo.data(), R * sizeof(Fp), cudaMemcpyHostToDevice));
+  SPG_CUDA(cudaMemcpy(ctx->lde_hi, hi.data(), B * sizeof(Fp), cudaMemcpyHostToDevice));
+  ctx->lde_log_n = (int)log_n;
+  memcpy(ctx->lde_offset, offset, 32);
+  return SPG_OK;
+}
+
+// phase A: columns -> scaled coefficient columns  g^k c_k  (bit-reversed order)
+int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, const uint64_t* offset_canon,
+                          Fp* coeffs) {
+  static const uint64_t three[4] = {3, 0, 0, 0};
+  const uint64_t* off = offset_canon ? offset_canon : three;
+  int rc = ensure_scale_tables(ctx, log_n, off);
+  if (rc) return rc;
+  const size_t n = (size_t)1 << log_n;
+  for (size_t c0 = 0; c0 < C; c0 += 32768) {
+    const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
+    rc = spg_ntt_device(ctx, trace + c0 * n, coeffs + c0 * n, log_n, nc, n, n, /*inverse=*/1, /*dit=*/0, 0,
+                        ctx->lde_lo, ctx->lde_hi);
+    if (rc) return rc;
+  }
+  return SPG_OK;
+}
+
+// phase B: scaled coefficients -> evaluations on cosets [j0, j0 + nj) of the 2^log_blowup cosets;
+// out[(j - j0)][c][i]
+int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t C, unsigned log_blowup, size_t j0,
+                          size_t nj, Fp* out) {
+  SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG, "spg_lde: log_n + log_blowup above 26");
+  SPG_ARG(j0 + nj <= ((size_t)1 << log_blowup), "spg_lde: coset range");
+  const size_t n = (size_t)1 << log_n;
+  for (size_t j = j0; j < j0 + nj; j++) {
+    const unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
+    for (size_t c0 = 0; c0 < C; c0 += 32768) {
+      const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
+      int rc = spg_ntt_device(ctx, coeffs + c0 * n, out + ((j - j0) * C + c0) * n, log_n, nc, n, n, /*inverse=*/0,
+                              /*dit=*/1, coset_exp, nullptr, nullptr);
+      if (rc) return rc;
+    }
+  }
+  return SPG_OK;
+}
+
+int spg_lde_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, unsigned log_blowup,
+                   const uint64_t* offset_canon, Fp* out, Fp* coeffs) {
+  SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG, "spg_lde: log_n + log_blowup above 26");
+  const size_t n = (size_t)1 << log_n;
+  if (!coeffs) {
+    void* p;
+    SPG_CUDA(spg_scratch(ctx, 0, C * n * sizeof(Fp), &p));
+    coeffs = (Fp*)p;
+  }
+  spg_stage_begin(ctx, 0);
+  int rc = spg_lde_coeffs_device(ctx, trace, log_n, C, offset_canon, coeffs);
+  if (rc) return rc;
+  spg_stage_end(ctx, 0);
+  spg_stage_begin(ctx, 1);
+  rc = spg_lde_cosets_device(ctx, coeffs, log_n, C, log_blowup, 0, (size_t)1 << log_blowup, out);
+  if (rc) return rc;
+  spg_stage_end(ctx, 1);
+  return SPG_OK;
+}
+
+// common tail of the device-pointer entry points
+static int finish(spg_ctx* ctx, int flags) {
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_NO_SYNC)) {
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+    spg_stage_collect(ctx);
+  }
+  return SPG_OK;
+}
+
+extern "C" int spg_lde_coeffs(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size_t n_cols,
+                              const uint64_t* coset_offset, uint64_t* coeffs, int flags) {
+  SPG_ARG(ctx && trace && coeffs, "spg_lde_coeffs: null");
+  SPG_ARG(flags & SPG_DEVICE_PTRS, "spg_lde_coeffs: device pointers only");
+  SPG_ARG(log_n <= SPG_UNI_LOG, "spg_lde_coeffs: log_n");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n_cols == 0) return SPG_OK;
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = spg_lde_coeffs_device(ctx, (const Fp*)trace, log_n, n_cols, coset_offset, (Fp*)coeffs);
+  if (rc) return rc;
+  return finish(ctx, flags);
+}
+
+extern "C" int spg_lde_cosets(spg_ctx* ctx, const uint64_t* coeffs, unsigned log_n, size_t n_cols,
+                              unsigned log_blowup, size_t coset_begin, size_t coset_count, uint64_t* out, int flags) {
+  SPG_ARG(ctx && coeffs && out, "spg_lde_cosets: null");
+  SPG_ARG(flags & SPG_DEVICE_PTRS, "spg_lde_cosets: device pointers only");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n_cols == 0 || coset_count == 0) return SPG_OK;
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = spg_lde_cosets_device(ctx, (const Fp*)coeffs, log_n, n_cols, log_blowup, coset_begin, coset_count, (Fp*)out);
+  if (rc) return rc;
+  return finish(ctx, flags);
+}
+
+extern "C" int spg_lde(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size_t n_cols, unsigned log_blowup,
+                       const uint64_t* coset_offset, uint64_t* out, int flags) {
+  SPG_ARG(ctx && trace && out, "spg_lde: null");
+  SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG && log_blowup <= 6, "spg_lde: size");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n_cols == 0) return SPG_OK;
+  const size_t n = (size_t)1 << log_n, in_bytes = n_cols * n * 32, out_bytes = in_bytes << log_blowup;
+  const Fp* din = (const Fp*)trace;
+  Fp* dout = (Fp*)out;
+  DevBuf bi, bo;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(bi.alloc(in_bytes)); SPG_CUDA(bo.alloc(out_bytes));
+    SPG_CUDA(cudaMemcpyAsync(bi.p, trace, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    din = bi.as<Fp>(); dout = bo.as<Fp>();
+  }
+  spg_stage_reset(ctx);
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = spg_lde_device(ctx, din, log_n, n_cols, log_blowup, coset_offset, dout, nullptr);
+  if (rc) return rc;
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS))
+    SPG_CUDA(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!((flags & SPG_NO_SYNC) && (flags & SPG_DEVICE_PTRS))) {
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+    spg_stage_collect(ctx);
+  }
+  return SPG_OK;
+}

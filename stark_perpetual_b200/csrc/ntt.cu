@@ -40,8 +40,8 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
   SPG_ARG(log_n <= 26, "NTT size above 2^26 not supported by the universal twiddle table");
   SPG_ARG(ncols < 65536, "too many columns in one NTT batch");
   if (ncols == 0) return SPG_OK;
-  static bool attr_set = false;
   const int smem = Tile::WS * (int)sizeof(Fp);
+  bool& attr_set = ctx->ntt_attr_set;
   if (!attr_set) {
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -117,6 +117,7 @@ extern "C" int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batc
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!(flags & SPG_DEVICE_PTRS))
     SPG_CUDA(cudaMemcpyAsync(data, d, total * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((flags & SPG_NO_SYNC) && (flags & SPG_DEVICE_PTRS) && !inverse && order != SPG_NTT_NAT_TO_NAT) return SPG_OK;
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
   return SPG_OK;

@@ -260,3 +260,23 @@ static inline int spg_ntt_make_passes(NttPass* passes, int log_ws, const Fp* in,
   }
   return np;
 }
+
+#include <vector>
+// LDE scale tables for the store phase of the inverse DIF: output position b*R + r holds coefficient
+// k = bitrev_R(r) * B + bitrev_B(b), which gets  g^k / N = lo[r] * hi[b].
+static inline void spg_lde_scale_tables(unsigned log_n, const Fp& g_mont, std::vector<Fp>& lo, std::vector<Fp>& hi) {
+  int lr, lb;
+  spg_ntt_last_pass_geometry(log_n, &lr, &lb);
+  const size_t R = (size_t)1 << lr, B = (size_t)1 << lb;
+  lo.resize(R); hi.resize(B);
+  uint64_t nn[4] = {(uint64_t)1 << log_n, 0, 0, 0};
+  const Fp ninv = fp_inv(fp_to_mont(fp_from_u64(nn)));
+  std::vector<Fp> pw(B), pr(R);
+  pw[0] = fp_one();
+  for (size_t i = 1; i < B; i++) pw[i] = fp_mul(pw[i - 1], g_mont);
+  for (size_t b = 0; b < B; b++) hi[b] = pw[spg_bitrev((unsigned)b, lb)];
+  const Fp gB = fp_mul(pw[B - 1], g_mont);
+  pr[0] = ninv;
+  for (size_t i = 1; i < R; i++) pr[i] = fp_mul(pr[i - 1], gB);
+  for (size_t r = 0; r < R; r++) lo[r] = pr[spg_bitrev((unsigned)r, lr)];
+}
