@@ -63,6 +63,21 @@ int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uin
  * independent accumulators; returns field multiplications per second in *mul_per_s. */
 int spg_bench_field_mul(spg_ctx* ctx, int iters, int chains, double* mul_per_s, double* imad_wide_per_s);
 
+/* ---- Pedersen hash (BASELINE.json configs[0]) ------------------------------------
+ * Replaces signature.py:296-318 pedersen_hash(*elements) and fast_pedersen_hash.py:34-52.
+ * status[i]: 0 ok; 1 an input is >= p (the reference raises AssertionError, signature.py:307);
+ *            2 "Unhashable input." (signature.py:313).  out[i] = 0 when status[i] != 0. */
+int spg_pedersen_hash2_batch(spg_ctx* ctx, const uint64_t* x, const uint64_t* y, uint64_t* out, uint8_t* status,
+                             size_t n, int flags);
+/* the reference's byte ABI: 32-byte big-endian in and out (fast_pedersen_hash.py:47-52); host pointers */
+int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, const uint8_t* y, uint8_t* out, uint8_t* status,
+                                  size_t n);
+/* n hash chains of chain_len elements each, elems[n][chain_len]:  h = H(e0, e1); h = H(h, e2); ...
+ * (chain_len = 1 hashes a single element, like pedersen_hash(x)).  This is the shape of the message hashes
+ * of perpetual_messages.py:253-286 and of the program-hash chain (program_hash_test_utils.py:7-21). */
+int spg_pedersen_chain_batch(spg_ctx* ctx, const uint64_t* elems, size_t chain_len, uint64_t* out, uint8_t* status,
+                             size_t n, int flags);
+
 /* ---- NTT over the STARK prime (no reference symbol, field from signature.py:41-42) */
 /* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
  * inverse != 0 uses omega^-1 and scales by 2^-log_n. */

@@ -47,6 +47,9 @@ def _load():
             "spg_field_op": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_bench_field_mul": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
             "spg_ntt": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_int, C.c_int, C.c_int]),
+            "spg_pedersen_hash2_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_pedersen_hash2_batch_be32": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t]),
+            "spg_pedersen_chain_batch": (C.c_int, [vp, vp, C.c_size_t, vp, vp, C.c_size_t, C.c_int]),
             "spg_set_stream": (C.c_int, [vp, vp]),
             "spg_stage_ms": (C.c_double, [vp, C.c_int]),
             "spg_lde": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, vp, vp, C.c_int]),
@@ -145,6 +148,36 @@ class Context:
         m, w = C.c_double(), C.c_double()
         self._check(self._lib.spg_bench_field_mul(self._h, iters, chains, C.byref(m), C.byref(w)))
         return m.value, w.value
+
+    # ---- Pedersen ----
+    def pedersen_hash2(self, x, y):
+        """x, y: (n, 4) uint64 canonical felts -> (out (n, 4), status (n,) uint8)."""
+        x = np.ascontiguousarray(x, dtype=np.uint64).reshape(-1, 4)
+        y = np.ascontiguousarray(y, dtype=np.uint64).reshape(-1, 4)
+        assert x.shape == y.shape
+        out = np.empty_like(x)
+        st = np.empty(x.shape[0], dtype=np.uint8)
+        self._check(self._lib.spg_pedersen_hash2_batch(self._h, _ptr(x), _ptr(y), _ptr(out), _ptr(st), x.shape[0], 0))
+        return out, st
+
+    def pedersen_hash2_be32(self, x, y):
+        """x, y: (n, 32) uint8 big-endian -> (out (n, 32) uint8, status)."""
+        x = np.ascontiguousarray(x, dtype=np.uint8).reshape(-1, 32)
+        y = np.ascontiguousarray(y, dtype=np.uint8).reshape(-1, 32)
+        out = np.empty_like(x)
+        st = np.empty(x.shape[0], dtype=np.uint8)
+        self._check(self._lib.spg_pedersen_hash2_batch_be32(self._h, _ptr(x), _ptr(y), _ptr(out), _ptr(st), x.shape[0]))
+        return out, st
+
+    def pedersen_chain(self, elems, chain_len):
+        """elems: (n * chain_len, 4) canonical felts, row-major [n][chain_len] -> (out (n, 4), status)."""
+        e = np.ascontiguousarray(elems, dtype=np.uint64).reshape(-1, 4)
+        assert e.shape[0] % chain_len == 0
+        n = e.shape[0] // chain_len
+        out = np.empty((n, 4), dtype=np.uint64)
+        st = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.spg_pedersen_chain_batch(self._h, _ptr(e), chain_len, _ptr(out), _ptr(st), n, 0))
+        return out, st
 
     # ---- NTT ----
     def ntt(self, data, log_n, inverse=False, order=NTT_NAT_TO_NAT):

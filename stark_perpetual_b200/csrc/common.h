@@ -24,6 +24,8 @@ struct spg_ctx {
   Fp* uniB = nullptr;     // omega_{2^26}^i, 8192
   // curve tables
   Fp* const_points = nullptr;   // 506 x (x, y) Montgomery
+  Fp* gen_doubles = nullptr;    // G * 2^t, t < 251, (x, y) Montgomery
+  std::vector<Fp> h_const_points;   // host copy of const_points
   // scratch cache
   std::vector<void*> owned;
   bool own_stream = true;

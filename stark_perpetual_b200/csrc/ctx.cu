@@ -89,7 +89,7 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
   if (!ctx) return;
   if (ctx->device >= 0) cudaSetDevice(ctx->device);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->uniA); cudaFree(ctx->uniB);
-  cudaFree(ctx->const_points);
+  cudaFree(ctx->const_points); cudaFree(ctx->gen_doubles);
   cudaFree(ctx->lde_lo); cudaFree(ctx->lde_hi);
   for (void* p : ctx->owned) cudaFree(p);
   for (void* p : ctx->scratch_p) cudaFree(p);

@@ -1,0 +1,163 @@
+// STARK-curve arithmetic  y^2 = x^3 + x + beta  over the STARK prime (alpha = 1).
+// Reference semantics restated: src/starkware/crypto/signature/math_utils.py:59-100 (affine
+// ec_add / ec_double / ec_mult with their assertions), signature.py:176-190, 296-318.
+//
+// Device code works in Jacobian coordinates (X : Y : Z), x = X / Z^2, y = Y / Z^3, Montgomery residues
+// with the lazy bounds of fp.cuh (all values < 2p).  The reference's assertions are about AFFINE x / y
+// being equal or zero; in Jacobian form  x1 == x2  <=>  X1 * Z2^2 == X2 * Z1^2  and  y == 0 <=> Y == 0,
+// so every exceptional case of the reference is detected exactly, without inversions.
+#pragma once
+#include "fp.cuh"
+
+struct APoint { Fp x, y; };          // affine, Montgomery form
+struct JPoint { Fp X, Y, Z; };       // Jacobian, Z != 0
+
+// a^-1 = a^(p-2), p - 2 = 2^251 + 2^196 + 2^192 - 1: 251 squarings + 13 multiplications
+SPG_HD Fp fp_inv_chain(const Fp& a) {
+  Fp x2 = fp_mul(fp_sqr(a), a);                       // 2^2 - 1
+  Fp t = x2;
+  for (int i = 0; i < 2; i++) t = fp_sqr(t);
+  Fp x4 = fp_mul(t, x2);
+  t = x4;
+  for (int i = 0; i < 4; i++) t = fp_sqr(t);
+  Fp x8 = fp_mul(t, x4);
+  t = x8;
+  for (int i = 0; i < 8; i++) t = fp_sqr(t);
+  Fp x16 = fp_mul(t, x8);
+  t = x16;
+  for (int i = 0; i < 16; i++) t = fp_sqr(t);
+  Fp x32 = fp_mul(t, x16);
+  t = x32;
+  for (int i = 0; i < 32; i++) t = fp_sqr(t);
+  Fp x64 = fp_mul(t, x32);
+  t = x64;
+  for (int i = 0; i < 64; i++) t = fp_sqr(t);
+  Fp x128 = fp_mul(t, x64);
+  t = x128;
+  for (int i = 0; i < 64; i++) t = fp_sqr(t);
+  Fp x192 = fp_mul(t, x64);                           // a^(2^192 - 1)
+  Fp e192 = fp_mul(x192, a);                          // a^(2^192)
+  t = e192;
+  for (int i = 0; i < 4; i++) t = fp_sqr(t);          // a^(2^196)
+  Fp e196 = t;
+  for (int i = 0; i < 55; i++) t = fp_sqr(t);         // a^(2^251)
+  return fp_mul(fp_mul(t, e196), x192);
+}
+
+// Jacobian + affine, NO special cases (caller has checked x1 != x2).  8M + 3S.
+// zz = Z1^2 and zzz = Z1^3 are passed in (callers cache them) together with u2 = x2 * zz.
+SPG_HD JPoint ec_madd_nocheck(const JPoint& p, const APoint& q, const Fp& zzz, const Fp& u2) {
+  Fp s2 = fp_mul(q.y, zzz);
+  Fp h = fp_sub(u2, p.X);
+  Fp r = fp_sub(s2, p.Y);
+  Fp hh = fp_sqr(h);
+  Fp hhh = fp_mul(h, hh);
+  Fp v = fp_mul(p.X, hh);
+  JPoint o;
+  o.X = fp_sub(fp_sub(fp_sqr(r), hhh), fp_add(v, v));
+  o.Y = fp_sub(fp_mul(r, fp_sub(v, o.X)), fp_mul(p.Y, hhh));
+  o.Z = fp_mul(p.Z, h);
+  return o;
+}
+
+// Jacobian + Jacobian, NO special cases (caller has checked x1 != x2, given u1, u2, and both Z^2).
+SPG_HD JPoint ec_jadd_nocheck(const JPoint& p, const JPoint& q, const Fp& z1z1, const Fp& z2z2, const Fp& u1,
+                              const Fp& u2) {
+  Fp s1 = fp_mul(p.Y, fp_mul(q.Z, z2z2));
+  Fp s2 = fp_mul(q.Y, fp_mul(p.Z, z1z1));
+  Fp h = fp_sub(u2, u1);
+  Fp r = fp_sub(s2, s1);
+  Fp hh = fp_sqr(h);
+  Fp hhh = fp_mul(h, hh);
+  Fp v = fp_mul(u1, hh);
+  JPoint o;
+  o.X = fp_sub(fp_sub(fp_sqr(r), hhh), fp_add(v, v));
+  o.Y = fp_sub(fp_mul(r, fp_sub(v, o.X)), fp_mul(s1, hhh));
+  o.Z = fp_mul(fp_mul(p.Z, q.Z), h);
+  return o;
+}
+
+// Jacobian doubling for alpha = 1 (caller has checked Y != 0).  4M + 6S... M = 3 X^2 + Z^4.
+SPG_HD JPoint ec_jdouble_nocheck(const JPoint& p) {
+  Fp xx = fp_sqr(p.X);
+  Fp yy = fp_sqr(p.Y);
+  Fp yyyy = fp_sqr(yy);
+  Fp zz = fp_sqr(p.Z);
+  Fp s = fp_mul(p.X, yy);
+  s = fp_add(s, s); s = fp_add(s, s);                              // 4 X Y^2
+  Fp m = fp_add(fp_add(fp_add(xx, xx), xx), fp_sqr(zz));           // 3 X^2 + alpha Z^4
+  JPoint o;
+  o.X = fp_sub(fp_sqr(m), fp_add(s, s));
+  Fp y8 = fp_add(yyyy, yyyy); y8 = fp_add(y8, y8); y8 = fp_add(y8, y8);
+  o.Y = fp_sub(fp_mul(m, fp_sub(s, o.X)), y8);
+  Fp yz = fp_mul(p.Y, p.Z);
+  o.Z = fp_add(yz, yz);
+  return o;
+}
+
+// ---- affine arithmetic with one inversion per operation (host table building, witness generation)
+SPG_HD APoint ec_affine_add(const APoint& a, const APoint& b) {     // math_utils.py:59-68, x1 != x2 assumed
+  Fp m = fp_mul(fp_sub(a.y, b.y), fp_inv_chain(fp_sub(a.x, b.x)));
+  APoint o;
+  o.x = fp_sub(fp_sub(fp_sqr(m), a.x), b.x);
+  o.y = fp_sub(fp_mul(m, fp_sub(a.x, o.x)), a.y);
+  return o;
+}
+SPG_HD APoint ec_affine_double(const APoint& a) {                   // math_utils.py:79-88, y != 0 assumed
+  Fp xx = fp_sqr(a.x);
+  Fp num = fp_add(fp_add(fp_add(xx, xx), xx), fp_one());
+  Fp m = fp_mul(num, fp_inv_chain(fp_add(a.y, a.y)));
+  APoint o;
+  o.x = fp_sub(fp_sub(fp_sqr(m), a.x), a.x);
+  o.y = fp_sub(fp_mul(m, fp_sub(a.x, o.x)), a.y);
+  return o;
+}
+
+// canonical 4 x u64 value >= p ?
+SPG_HD bool spg_canon_geq_p(const uint32_t* v) {
+  // p = 0x08000000 00000011 00000000 ... 00000001
+  if (v[7] != SPG_P7) return v[7] > SPG_P7;
+  if (v[6] != SPG_P6) return v[6] > SPG_P6;
+  if (v[5] | v[4] | v[3] | v[2] | v[1]) return true;
+  return v[0] >= SPG_P0;
+}
+
+#define SPG_N_CONST_POINTS 506
+#define SPG_HASH_BITS 252      // N_ELEMENT_BITS_HASH, signature.py:50
+#define SPG_ECDSA_BITS 251     // N_ELEMENT_BITS_ECDSA, signature.py:47
+
+// ---- Pedersen accumulator (shared by the hash kernel and the host emulation test)
+struct PedersenAcc {
+  JPoint p;
+  Fp zz, zzz;
+  SPG_HD void init(const APoint& s) {
+    p.X = s.x; p.Y = s.y; p.Z = fp_one(); zz = fp_one(); zzz = fp_one();
+  }
+};
+
+// Absorb one canonical element (8 x u32 limbs, already checked < p) with table slice `tab` (252 points).
+// Returns false on "Unhashable input." (signature.py:313).
+SPG_HD bool pedersen_absorb(PedersenAcc& a, const uint32_t (&x)[8], const APoint* tab) {
+  bool ok = true;
+#pragma unroll 1
+  for (int w = 0; w < 8; w++) {
+    uint32_t word = x[0];
+    // select limb w without dynamic register indexing
+#pragma unroll
+    for (int k = 1; k < 8; k++) word = (w == k) ? x[k] : word;
+    const int nb = (w == 7) ? (SPG_HASH_BITS - 224) : 32;
+#pragma unroll 1
+    for (int b = 0; b < nb; b++) {
+      const APoint q = tab[w * 32 + b];
+      const Fp u2 = fp_mul(q.x, a.zz);
+      if (fp_is_zero(fp_sub(u2, a.p.X))) ok = false;
+      if ((word >> b) & 1u) {
+        a.p = ec_madd_nocheck(a.p, q, a.zzz, u2);
+        a.zz = fp_sqr(a.p.Z);
+        a.zzz = fp_mul(a.zz, a.p.Z);
+      }
+    }
+  }
+  return ok;
+}
+

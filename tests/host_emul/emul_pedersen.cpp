@@ -1,0 +1,51 @@
+// CPU emulation of the Pedersen hash kernel's per-thread code (csrc/ec.cuh), compiled with g++.
+// stdin: lines "x_hex y_hex" (canonical, no 0x); stdout: "hash_hex status".
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../stark_perpetual_b200/csrc/ec.cuh"
+#include "../../stark_perpetual_b200/csrc/curve_params.inc"
+
+static Fp from_canon(const uint64_t* w) { return fp_to_mont(fp_from_u64(w)); }
+static void parse_hex(const char* s, uint64_t w[4]) {
+  memset(w, 0, 32);
+  size_t n = strlen(s);
+  for (size_t i = 0; i < n; i++) {
+    char c = s[n - 1 - i];
+    uint64_t d = (c >= '0' && c <= '9') ? c - '0' : (c >= 'a' && c <= 'f') ? c - 'a' + 10 : c - 'A' + 10;
+    if (i < 64) w[i / 16] |= d << (4 * (i % 16));
+  }
+}
+int main() {
+  std::vector<APoint> pts;
+  auto base = [&](int i) { APoint a; a.x = from_canon(SPG_BASE_POINTS[i][0]); a.y = from_canon(SPG_BASE_POINTS[i][1]); return a; };
+  pts.push_back(base(0)); pts.push_back(base(1));
+  const int chain[4] = {248, 4, 248, 4};
+  for (int k = 0; k < 4; k++) { APoint q = base(2 + k); for (int i = 0; i < chain[k]; i++) { pts.push_back(q); q = ec_affine_double(q); } }
+  char a[128], b[128];
+  while (scanf("%100s %100s", a, b) == 2) {
+    uint64_t xw[4], yw[4];
+    parse_hex(a, xw); parse_hex(b, yw);
+    uint32_t x[8], y[8];
+    for (int i = 0; i < 4; i++) { x[2 * i] = (uint32_t)xw[i]; x[2 * i + 1] = (uint32_t)(xw[i] >> 32); y[2 * i] = (uint32_t)yw[i]; y[2 * i + 1] = (uint32_t)(yw[i] >> 32); }
+    int st = 0;
+    if (spg_canon_geq_p(x) || spg_canon_geq_p(y)) st = 1;
+    uint64_t out[4] = {0, 0, 0, 0};
+    if (!st) {
+      PedersenAcc acc; acc.init(pts[0]);
+      bool ok = pedersen_absorb(acc, x, pts.data() + 2);
+      ok = pedersen_absorb(acc, y, pts.data() + 2 + SPG_HASH_BITS) && ok;
+      if (!ok) st = 2;
+      else {
+        Fp zi = fp_inv_chain(acc.p.Z);
+        Fp r = fp_from_mont(fp_mul(acc.p.X, fp_sqr(zi)));
+        fp_to_u64(r, out);
+      }
+    }
+    printf("%016llx%016llx%016llx%016llx %d\n", (unsigned long long)out[3], (unsigned long long)out[2],
+           (unsigned long long)out[1], (unsigned long long)out[0], st);
+  }
+  return 0;
+}
