@@ -99,6 +99,34 @@ int spg_lde_coeffs(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size_t n
 int spg_lde_cosets(spg_ctx* ctx, const uint64_t* coeffs, unsigned log_n, size_t n_cols, unsigned log_blowup,
                    size_t coset_begin, size_t coset_count, uint64_t* out, int flags);
 
+/* ---- Merkle commitment, BLAKE2s (no reference symbol) -----------------------------------
+ * table: [8][n_cols][rows] 256-bit values (hashed as given, 32 bytes big-endian each).  Leaf j*rows/8 + i'
+ * = BLAKE2s of the rows i' + k*rows/8 (k = 0..7) of coset j, all columns of a row in order; node =
+ * BLAKE2s(left || right).  root32 receives the root; tree_out (optional) the whole tree: `rows` leaf
+ * digests, then rows/2, ..., 1 node digests (2*rows - 1 digests of 32 bytes). */
+int spg_merkle_commit(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, uint8_t* root32,
+                      uint8_t* tree_out, int flags);
+
+/* ---- Pedersen hash-chain AIR: witness, constraint evaluation, proof -----------
+ * The statement (DESIGN.md "AIR"): 5 lanes of Pedersen hashes (signature.py:296-318), 512 trace rows per
+ * hash, chained in segments of 2^chain_log hashes starting from the public seed x0[lane]; public output =
+ * result of the last hash of every lane.  Trace = [25][2^log_n] canonical felts, columns (X, Y, S, M, I)
+ * per lane.  spg_pedersen_chain_trace is the witness generator (the role cairo-run plays for the real
+ * program, cairo_cmake_rules.cmake:94-110): x0 [5] and ys [5][2^log_n / 512] canonical felts. */
+int spg_pedersen_chain_trace(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+                             const uint64_t* ys, uint64_t* trace_out, int flags);
+/* composition polynomial sum_k alpha^k C_k(x) / Z_k(x) of the trace on the LDE cosets j = 0, 2, 4, 6:
+ * cp_out [4][2^log_n] canonical; x0, outs [5], alpha canonical (host pointers).  Stage 2 of spg_stage_ms. */
+int spg_air_eval(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+                 const uint64_t* outs, const uint64_t* alpha, uint64_t* cp_out, int flags);
+/* Full proof.  trace: [25][2^log_n] canonical felts (host, or device with SPG_DEVICE_PTRS); x0 [5] canonical
+ * (host).  Writes the proof bytes (format: DESIGN.md "Proof") to proof_out (capacity proof_cap) and their
+ * number to *proof_len; with proof_out = NULL only the length is returned.  SPG_E_PROOF if the trace does
+ * not satisfy the AIR.  Stages for spg_stage_ms: 0 trace LDE, 1 trace Merkle, 2 AIR/composition, 3 chunk
+ * split + LDE, 4 chunk Merkle, 5 out-of-domain evaluation, 6 DEEP quotient, 7 FRI, 8 query openings. */
+int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+              unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,10 @@ def _load():
             "spg_pedersen_hash2_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_pedersen_hash2_batch_be32": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t]),
             "spg_pedersen_chain_batch": (C.c_int, [vp, vp, C.c_size_t, vp, vp, C.c_size_t, C.c_int]),
+            "spg_merkle_commit": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, vp, vp, C.c_int]),
+            "spg_pedersen_chain_trace": (C.c_int, [vp, C.c_uint, C.c_uint, vp, vp, vp, C.c_int]),
+            "spg_air_eval": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, vp, vp, vp, C.c_int]),
+            "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_set_stream": (C.c_int, [vp, vp]),
             "spg_stage_ms": (C.c_double, [vp, C.c_int]),
             "spg_lde": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, vp, vp, C.c_int]),
@@ -227,6 +231,51 @@ class Context:
         flags = SPG_DEVICE_PTRS | (0 if sync else SPG_NO_SYNC)
         self._check(self._lib.spg_lde_cosets(self._h, C.c_void_p(coeffs_ptr), log_n, n_cols, log_blowup,
                                              coset_begin, coset_count, C.c_void_p(out_ptr), flags))
+
+    # ---- Merkle / AIR / proof ----
+    def merkle_commit(self, table, n_cols, rows, want_tree=False):
+        """table: (8 * n_cols * rows, 4) uint64, layout [8][n_cols][rows] -> root bytes (and the tree)."""
+        t = np.ascontiguousarray(table, dtype=np.uint64).reshape(-1, 4)
+        assert t.shape[0] == 8 * n_cols * rows
+        root = np.empty(32, dtype=np.uint8)
+        tree = np.empty((2 * rows - 1, 32), dtype=np.uint8) if want_tree else None
+        self._check(self._lib.spg_merkle_commit(self._h, _ptr(t), n_cols, rows, _ptr(root),
+                                                _ptr(tree) if want_tree else None, 0))
+        return (root.tobytes(), tree) if want_tree else root.tobytes()
+
+    def pedersen_chain_trace(self, log_n, chain_log, x0, ys):
+        """x0: 5 ints; ys: (5 * 2^log_n / 512, 4) uint64 canonical, lane-major -> trace (25 * 2^log_n, 4)."""
+        x0a = ints_to_limbs(x0)
+        ysa = np.ascontiguousarray(ys, dtype=np.uint64).reshape(-1, 4)
+        assert x0a.shape[0] == 5 and ysa.shape[0] == 5 * ((1 << log_n) >> 9)
+        out = np.empty((25 << log_n, 4), dtype=np.uint64)
+        self._check(self._lib.spg_pedersen_chain_trace(self._h, log_n, chain_log, _ptr(x0a), _ptr(ysa), _ptr(out), 0))
+        return out
+
+    def air_eval(self, trace, log_n, chain_log, x0, outs, alpha):
+        tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
+        assert tr.shape[0] == 25 << log_n
+        x0a, oa, aa = ints_to_limbs(x0), ints_to_limbs(outs), ints_to_limbs([alpha])
+        cp = np.empty((4 << log_n, 4), dtype=np.uint64)
+        self._check(self._lib.spg_air_eval(self._h, _ptr(tr), log_n, chain_log, _ptr(x0a), _ptr(oa), _ptr(aa), _ptr(cp), 0))
+        return cp
+
+    def prove(self, trace, log_n, chain_log, x0, n_queries=30, device_ptr=None):
+        """trace: (25 * 2^log_n, 4) uint64 canonical (host), or device_ptr = address of the same on the GPU.
+        Returns the proof bytes."""
+        x0a = ints_to_limbs(x0)
+        if device_ptr is None:
+            tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
+            assert tr.shape[0] == 25 << log_n
+            tp, flags = _ptr(tr), 0
+        else:
+            tp, flags = C.c_void_p(device_ptr), SPG_DEVICE_PTRS
+        cap = 64 + 64 * 32 + 64 * 32 + 128 * 32 + n_queries * (8 * 29 + 8 * 8 + 10 * 24) * 32 + 65536
+        buf = np.empty(cap, dtype=np.uint8)
+        ln = C.c_size_t(0)
+        self._check(self._lib.spg_prove(self._h, tp, log_n, chain_log, _ptr(x0a), n_queries, _ptr(buf), cap,
+                                        C.byref(ln), flags))
+        return buf[:ln.value].tobytes()
 
 
 _CTX = {}

@@ -33,11 +33,14 @@ struct spg_ctx {
   // growable scratch slots (device), kept until spg_destroy
   void* scratch_p[8] = {nullptr};
   size_t scratch_sz[8] = {0};
-  // LDE scale tables cached per (log_n, offset): lo[R] , hi[B]
-  int lde_log_n = -1;
-  uint64_t lde_offset[4] = {0, 0, 0, 0};
-  Fp* lde_lo = nullptr;
-  Fp* lde_hi = nullptr;
+  // LDE scale tables cached per (log_n, offset, mont): lo[R] , hi[B]
+  struct LdeTables { int log_n; uint64_t offset[4]; int mont; Fp* lo; Fp* hi; };
+  std::vector<LdeTables> lde_tables;
+  // AIR tables cached per (log_n, chain_log)
+  int air_log_n = -1, air_chain_log = -1;
+  Fp* air_izt = nullptr;      // [7][4][seg] inverse zerofiers on cosets 0,2,4,6
+  Fp* air_plde = nullptr;     // [8][2][512] periodic point columns on the LDE cosets
+  Fp* air_ilast = nullptr;    // [4][N] 1 / (x - w^(N-1)) on cosets 0,2,4,6
   // per-stage device milliseconds of the last pipeline call (spg_stage_ms)
   double stage_ms[16] = {0};
   cudaEvent_t stage_ev[16][2] = {{nullptr}};
@@ -112,6 +115,8 @@ Fp spg_host_root_of_unity(int log_n);   // omega_{2^log_n}, Montgomery
 Fp spg_host_from_u64(const uint64_t* canon);   // canonical -> Montgomery
 void spg_host_to_u64(const Fp& mont, uint64_t* canon);
 
+// ctx.cu: in-place Montgomery -> canonical
+int spg_from_mont_device(spg_ctx* ctx, Fp* data, size_t n);
 // ntt.cu
 int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
@@ -120,4 +125,9 @@ int spg_bitrev_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_
 // lde.cu: device-resident LDE, trace [C][N] -> out [B][C][N]; coeffs (optional) receives the scaled
 // coefficient columns g^k c_k (bit-reversed order)
 int spg_lde_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, unsigned log_blowup,
-                   const uint64_t* offset_canon, Fp* out, Fp* coeffs);
+                   const uint64_t* offset_canon, Fp* out, Fp* coeffs, int mont = 0);
+// the two phases; mont != 0 additionally multiplies by R = 2^256 (canonical input -> Montgomery output)
+int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, const uint64_t* offset_canon,
+                          Fp* coeffs, int mont = 0);
+int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t C, unsigned log_blowup, size_t j0,
+                          size_t nj, Fp* out);

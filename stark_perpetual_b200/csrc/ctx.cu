@@ -90,7 +90,8 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
   if (ctx->device >= 0) cudaSetDevice(ctx->device);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->uniA); cudaFree(ctx->uniB);
   cudaFree(ctx->const_points); cudaFree(ctx->gen_doubles);
-  cudaFree(ctx->lde_lo); cudaFree(ctx->lde_hi);
+  for (auto& t : ctx->lde_tables) { cudaFree(t.lo); cudaFree(t.hi); }
+  cudaFree(ctx->air_izt); cudaFree(ctx->air_plde); cudaFree(ctx->air_ilast);
   for (void* p : ctx->owned) cudaFree(p);
   for (void* p : ctx->scratch_p) cudaFree(p);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -175,6 +176,17 @@ extern "C" int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint6
     SPG_CUDA(cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}
+
+__global__ void k_from_mont(Fp* p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = fp_from_mont(p[i]);
+}
+int spg_from_mont_device(spg_ctx* ctx, Fp* data, size_t n) {
+  if (!n) return SPG_OK;
+  k_from_mont<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(data, n);
+  SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
 

@@ -1,0 +1,225 @@
+// DEEP quotient, batched inversion over the evaluation domain, FRI fold-by-8 and out-of-domain
+// polynomial evaluation (protocol in DESIGN.md, CPU restatement in
+// oracle/stark.py -- no reference symbol exists for these stages).
+#include "stark_kernels.cuh"
+
+// ------------------------------------------------------------------ 1 / (x - A) over cosets
+// Montgomery batch inversion: each thread owns `ch` points strided by the block size (coalesced), keeps the
+// running prefix products in the output buffer itself, inverts once (Fermat chain), and unwinds.
+__global__ void __launch_bounds__(256) k_inv_x_minus(unsigned log_n, int j0, int jstep, int nj, const Fp* __restrict__ A,
+                                                     Fp* __restrict__ out, int ch, Fp g, const Fp* __restrict__ uniA,
+                                                     const Fp* __restrict__ uniB) {
+  const size_t n = (size_t)1 << log_n;
+  const int jj = blockIdx.y, a = blockIdx.z, j = j0 + jstep * jj;
+  const size_t i0 = (size_t)blockIdx.x * 256 * ch + threadIdx.x;
+  const int sh = SPG_UNI_LOG - (int)log_n - SPG_LOG_BLOWUP;
+  Fp x = fp_mul(g, spg_uni_pow(uniA, uniB, ((unsigned long long)j + 8ull * i0) << sh));
+  const unsigned long long step_e = (256ull << (SPG_UNI_LOG - log_n));
+  const Fp step = spg_uni_pow(uniA, uniB, step_e), stepinv = spg_uni_pow(uniA, uniB, 0ull - step_e);
+  const Fp av = A[a];
+  Fp* o = out + (((size_t)a * nj + jj) << log_n);
+  Fp acc = fp_one();
+  for (int k = 0; k < ch; k++) {
+    const size_t i = i0 + 256ull * k;
+    if (i < n) {
+      o[i] = acc;
+      acc = fp_mul(acc, fp_sub(x, av));
+    }
+    x = fp_mul(x, step);
+  }
+  Fp inv = fp_inv_chain(acc);
+  for (int k = ch - 1; k >= 0; k--) {
+    x = fp_mul(x, stepinv);
+    const size_t i = i0 + 256ull * k;
+    if (i < n) {
+      const Fp pre = o[i];
+      o[i] = fp_reduce(fp_mul(inv, pre));
+      inv = fp_mul(inv, fp_sub(x, av));
+    }
+  }
+}
+
+static Fp host_gen() { uint64_t three[4] = {3, 0, 0, 0}; return spg_host_from_u64(three); }
+
+int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int nj, const Fp* d_A, int n_a, Fp* out) {
+  const size_t n = (size_t)1 << log_n;
+  int ch = (int)(n / 256 / 8);
+  if (ch < 1) ch = 1;
+  if (ch > 64) ch = 64;
+  const unsigned tiles = (unsigned)((n + 256ull * ch - 1) / (256ull * ch));
+  dim3 grid(tiles, (unsigned)nj, (unsigned)n_a);
+  k_inv_x_minus<<<grid, 256, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
+  SPG_LAUNCH_CHECK();
+  return SPG_OK;
+}
+
+// ------------------------------------------------------------------ DEEP quotient
+__global__ void __launch_bounds__(256) k_deep(unsigned log_n, const Fp* __restrict__ t_lde, const Fp* __restrict__ h_lde,
+                                              const Fp* __restrict__ inv3, const Fp* __restrict__ gamma,
+                                              const Fp* __restrict__ K, Fp* __restrict__ out) {
+  const size_t n = (size_t)1 << log_n;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 8 * n) return;
+  const size_t j = idx >> log_n, i = idx & (n - 1);
+  Fp a = fp_zero(), b = fp_zero(), c = fp_zero();
+  const Fp* tp = t_lde + (j * SPG_AIR_COLS << log_n) + i;
+#pragma unroll 5
+  for (int col = 0; col < SPG_AIR_COLS; col++) {
+    const Fp v = tp[(size_t)col << log_n];
+    a = fp_add(a, fp_mul(v, gamma[col]));
+    b = fp_add(b, fp_mul(v, gamma[SPG_AIR_COLS + col]));
+  }
+  const Fp* hp = h_lde + (j * 4 << log_n) + i;
+#pragma unroll
+  for (int m = 0; m < 4; m++) c = fp_add(c, fp_mul(hp[(size_t)m << log_n], gamma[2 * SPG_AIR_COLS + m]));
+  a = fp_sub(a, K[0]); b = fp_sub(b, K[1]); c = fp_sub(c, K[2]);
+  const Fp i1 = inv3[idx], i2 = inv3[idx + 8 * n], i3 = inv3[idx + 16 * n];
+  Fp q = fp_add(fp_add(fp_mul(a, i1), fp_mul(b, i2)), fp_mul(c, i3));
+  out[idx] = fp_reduce(q);
+}
+
+int spg_deep_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, const Fp* inv3, const Fp* d_gamma,
+                    const Fp* d_K, Fp* out) {
+  const size_t total = (size_t)8 << log_n;
+  k_deep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_lde, h_lde, inv3, d_gamma, d_K, out);
+  SPG_LAUNCH_CHECK();
+  return SPG_OK;
+}
+
+// ------------------------------------------------------------------ FRI fold by 8
+struct FoldConsts {
+  Fp zi1, zi2, zi3;   // w_8^-1, w_8^-2, w_8^-3
+  Fp inv8;
+  Fp bg;              // beta / g_l
+};
+
+__global__ void __launch_bounds__(256) k_fri_fold8(const Fp* __restrict__ in, unsigned log_rows, FoldConsts K,
+                                                   Fp* __restrict__ out, const Fp* __restrict__ uniA,
+                                                   const Fp* __restrict__ uniB) {
+  const unsigned log_g = log_rows - 3;
+  const size_t g = (size_t)1 << log_g;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 8 * g) return;
+  const size_t j = idx >> log_g, ip = idx & (g - 1);
+  const Fp* p = in + (j << log_rows) + ip;
+  Fp v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) v[k] = p[(size_t)k << log_g];
+  // size-8 inverse DFT, s[m] = sum_k w_8^(-m k) v[k]
+  Fp a[4], b[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) { a[k] = fp_add(v[k], v[k + 4]); b[k] = fp_sub(v[k], v[k + 4]); }
+  b[1] = fp_mul(b[1], K.zi1); b[2] = fp_mul(b[2], K.zi2); b[3] = fp_mul(b[3], K.zi3);
+  Fp s[8];
+  {
+    // even m = 2 m': size-4 inverse DFT of a;  odd m = 2 m' + 1: of b
+    Fp t0 = fp_add(a[0], a[2]), t1 = fp_sub(a[0], a[2]), t2 = fp_add(a[1], a[3]);
+    Fp t3 = fp_mul(fp_sub(a[1], a[3]), K.zi2);           // w_4^-1 = w_8^-2
+    s[0] = fp_add(t0, t2); s[4] = fp_sub(t0, t2); s[2] = fp_add(t1, t3); s[6] = fp_sub(t1, t3);
+    t0 = fp_add(b[0], b[2]); t1 = fp_sub(b[0], b[2]); t2 = fp_add(b[1], b[3]);
+    t3 = fp_mul(fp_sub(b[1], b[3]), K.zi2);
+    s[1] = fp_add(t0, t2); s[5] = fp_sub(t0, t2); s[3] = fp_add(t1, t3); s[7] = fp_sub(t1, t3);
+  }
+  // t = beta / x,  x = g_l * w_{8 rows}^(j + 8 ip)
+  const int sh = SPG_UNI_LOG - (int)log_rows - SPG_LOG_BLOWUP;
+  const unsigned long long e = ((unsigned long long)j + 8ull * ip) << sh;
+  const Fp t = fp_mul(K.bg, spg_uni_pow(uniA, uniB, 0ull - e));
+  Fp acc = s[7];
+#pragma unroll
+  for (int m = 6; m >= 0; m--) acc = fp_add(fp_mul(acc, t), s[m]);
+  out[idx] = fp_reduce(fp_mul(acc, K.inv8));
+}
+
+int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp& beta_over_g, Fp* out) {
+  SPG_ARG(log_rows >= 3 && log_rows + SPG_LOG_BLOWUP <= SPG_UNI_LOG, "fri fold: size");
+  FoldConsts K;
+  const Fp z = spg_host_root_of_unity(3), zi = fp_inv(z);
+  K.zi1 = zi; K.zi2 = fp_mul(zi, zi); K.zi3 = fp_mul(K.zi2, zi);
+  uint64_t eight[4] = {8, 0, 0, 0};
+  K.inv8 = fp_inv(spg_host_from_u64(eight));
+  K.bg = beta_over_g;
+  const size_t total = (size_t)1 << log_rows;   // 8 * rows/8 outputs
+  k_fri_fold8<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in, log_rows, K, out, ctx->uniA, ctx->uniB);
+  SPG_LAUNCH_CHECK();
+  return SPG_OK;
+}
+
+// ------------------------------------------------------------------ out-of-domain evaluation
+#define SPG_EVAL_T 10
+__global__ void k_eval_tables(const Fp* __restrict__ pts, int n_pts, unsigned log_n, unsigned t, Fp* __restrict__ A,
+                              Fp* __restrict__ B) {
+  const size_t na = (size_t)1 << t, nb = (size_t)1 << (log_n - t);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (na + nb) * n_pts) return;
+  const int p = (int)(idx / (na + nb));
+  const size_t r = idx - (size_t)p * (na + nb);
+  const Fp w = pts[p];
+  if (r < na) {
+    const uint64_t e = (uint64_t)spg_bitrev((unsigned)r, (int)t) << (log_n - t);
+    A[(size_t)p * na + r] = e ? fp_pow_u64(w, e) : fp_one();
+  } else {
+    const size_t hi = r - na;
+    const uint64_t e = spg_bitrev((unsigned)hi, (int)(log_n - t));
+    B[(size_t)p * nb + hi] = e ? fp_pow_u64(w, e) : fp_one();
+  }
+}
+
+__device__ __forceinline__ Fp block_sum(Fp v, Fp* sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (tid < s) sh[tid] = fp_add(sh[tid], sh[tid + s]);
+    __syncthreads();
+  }
+  return sh[0];
+}
+
+__global__ void __launch_bounds__(256) k_poly_eval_partial(const Fp* const* __restrict__ cols, const int* __restrict__ pt_idx,
+                                                           unsigned log_n, unsigned t, const Fp* __restrict__ A,
+                                                           const Fp* __restrict__ B, Fp* __restrict__ partial) {
+  __shared__ Fp sh[256];
+  const size_t hi = blockIdx.x, n_hi = gridDim.x;
+  const int item = blockIdx.y, p = pt_idx[item];
+  const size_t L = (size_t)1 << t;
+  const Fp* col = cols[item] + (hi << t);
+  const Fp* a = A + (size_t)p * L;
+  Fp acc = fp_zero();
+  for (size_t lo = threadIdx.x; lo < L; lo += 256) acc = fp_add(acc, fp_mul(col[lo], a[lo]));
+  const Fp s = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[(size_t)item * n_hi + hi] = fp_mul(s, B[(size_t)p * n_hi + hi]);
+}
+
+__global__ void __launch_bounds__(256) k_poly_eval_final(const Fp* __restrict__ partial, size_t n_hi, Fp* __restrict__ out) {
+  __shared__ Fp sh[256];
+  const int item = blockIdx.x;
+  Fp acc = fp_zero();
+  for (size_t h = threadIdx.x; h < n_hi; h += 256) acc = fp_add(acc, partial[(size_t)item * n_hi + h]);
+  const Fp s = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[item] = fp_reduce(s);
+}
+
+int spg_poly_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* const* h_cols, const int* h_pt_idx, int n_items,
+                         const Fp* h_pts, int n_pts, Fp* h_out) {
+  const unsigned t = log_n < SPG_EVAL_T ? log_n : SPG_EVAL_T;
+  const size_t na = (size_t)1 << t, nb = (size_t)1 << (log_n - t);
+  DevBuf dpts, dA, dB, dcols, dpidx, dpart, dout;
+  SPG_CUDA(dpts.alloc(n_pts * sizeof(Fp))); SPG_CUDA(dA.alloc(n_pts * na * sizeof(Fp))); SPG_CUDA(dB.alloc(n_pts * nb * sizeof(Fp)));
+  SPG_CUDA(dcols.alloc(n_items * sizeof(Fp*))); SPG_CUDA(dpidx.alloc(n_items * sizeof(int)));
+  SPG_CUDA(dpart.alloc(n_items * nb * sizeof(Fp))); SPG_CUDA(dout.alloc(n_items * sizeof(Fp)));
+  SPG_CUDA(cudaMemcpyAsync(dpts.p, h_pts, n_pts * sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(dcols.p, h_cols, n_items * sizeof(Fp*), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(dpidx.p, h_pt_idx, n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  const size_t nt = (na + nb) * n_pts;
+  k_eval_tables<<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(dpts.as<Fp>(), n_pts, log_n, t, dA.as<Fp>(), dB.as<Fp>());
+  SPG_LAUNCH_CHECK();
+  dim3 grid((unsigned)nb, (unsigned)n_items);
+  k_poly_eval_partial<<<grid, 256, 0, ctx->stream>>>((const Fp* const*)dcols.p, dpidx.as<int>(), log_n, t, dA.as<Fp>(),
+                                                     dB.as<Fp>(), dpart.as<Fp>());
+  SPG_LAUNCH_CHECK();
+  k_poly_eval_final<<<n_items, 256, 0, ctx->stream>>>(dpart.as<Fp>(), nb, dout.as<Fp>());
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaMemcpyAsync(h_out, dout.p, n_items * sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}

@@ -12,34 +12,46 @@
 #include "common.h"
 #include "ntt.cuh"
 
-static int ensure_scale_tables(spg_ctx* ctx, unsigned log_n, const uint64_t* offset) {
-  if (ctx->lde_log_n == (int)log_n && memcmp(ctx->lde_offset, offset, 32) == 0) return SPG_OK;
+static int ensure_scale_tables(spg_ctx* ctx, unsigned log_n, const uint64_t* offset, int mont, const Fp** lo_out,
+                               const Fp** hi_out) {
+  for (auto& t : ctx->lde_tables)
+    if (t.log_n == (int)log_n && t.mont == mont && memcmp(t.offset, offset, 32) == 0) {
+      *lo_out = t.lo; *hi_out = t.hi;
+      return SPG_OK;
+    }
   std::vector<Fp> lo, hi;
   spg_lde_scale_tables(log_n, spg_host_from_u64(offset), lo, hi);
+  if (mont) for (auto& v : lo) v = fp_mul(v, fp_r2());     // extra factor R: canonical in -> Montgomery out
   const size_t R = lo.size(), B = hi.size();
-  cudaFree(ctx->lde_lo); cudaFree(ctx->lde_hi);
-  ctx->lde_lo = ctx->lde_hi = nullptr; ctx->lde_log_n = -1;
-  SPG_CUDA(cudaMalloc((void**)&ctx->lde_lo, R * sizeof(Fp)));
-  SPG_CUDA(cudaMalloc((void**)&ctx->lde_hi, B * sizeof(Fp)));
-  SPG_CUDA(cudaMemcpy(ctx->lde_lo, lo.data(), R * sizeof(Fp), cudaMemcpyHostToDevice));
-  SPG_CUDA(cudaMemcpy(ctx->lde_hi, hi.data(), B * sizeof(Fp), cudaMemcpyHostToDevice));
-  ctx->lde_log_n = (int)log_n;
-  memcpy(ctx->lde_offset, offset, 32);
+  if (ctx->lde_tables.size() >= 8) {   // tiny cache: drop the oldest entry
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->lde_tables[0].lo); cudaFree(ctx->lde_tables[0].hi);
+    ctx->lde_tables.erase(ctx->lde_tables.begin());
+  }
+  spg_ctx::LdeTables t;
+  t.log_n = (int)log_n; t.mont = mont; memcpy(t.offset, offset, 32); t.lo = t.hi = nullptr;
+  SPG_CUDA(cudaMalloc((void**)&t.lo, R * sizeof(Fp)));
+  SPG_CUDA(cudaMalloc((void**)&t.hi, B * sizeof(Fp)));
+  SPG_CUDA(cudaMemcpy(t.lo, lo.data(), R * sizeof(Fp), cudaMemcpyHostToDevice));
+  SPG_CUDA(cudaMemcpy(t.hi, hi.data(), B * sizeof(Fp), cudaMemcpyHostToDevice));
+  ctx->lde_tables.push_back(t);
+  *lo_out = t.lo; *hi_out = t.hi;
   return SPG_OK;
 }
 
 // phase A: columns -> scaled coefficient columns  g^k c_k  (bit-reversed order)
 int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, const uint64_t* offset_canon,
-                          Fp* coeffs) {
+                          Fp* coeffs, int mont) {
   static const uint64_t three[4] = {3, 0, 0, 0};
   const uint64_t* off = offset_canon ? offset_canon : three;
-  int rc = ensure_scale_tables(ctx, log_n, off);
+  const Fp *lo, *hi;
+  int rc = ensure_scale_tables(ctx, log_n, off, mont, &lo, &hi);
   if (rc) return rc;
   const size_t n = (size_t)1 << log_n;
   for (size_t c0 = 0; c0 < C; c0 += 32768) {
     const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
     rc = spg_ntt_device(ctx, trace + c0 * n, coeffs + c0 * n, log_n, nc, n, n, /*inverse=*/1, /*dit=*/0, 0,
-                        ctx->lde_lo, ctx->lde_hi);
+                        lo, hi);
     if (rc) return rc;
   }
   return SPG_OK;
@@ -65,7 +77,7 @@ int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t
 }
 
 int spg_lde_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, unsigned log_blowup,
-                   const uint64_t* offset_canon, Fp* out, Fp* coeffs) {
+                   const uint64_t* offset_canon, Fp* out, Fp* coeffs, int mont) {
   SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG, "spg_lde: log_n + log_blowup above 26");
   const size_t n = (size_t)1 << log_n;
   if (!coeffs) {
@@ -73,15 +85,9 @@ int spg_lde_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, unsi
     SPG_CUDA(spg_scratch(ctx, 0, C * n * sizeof(Fp), &p));
     coeffs = (Fp*)p;
   }
-  spg_stage_begin(ctx, 0);
-  int rc = spg_lde_coeffs_device(ctx, trace, log_n, C, offset_canon, coeffs);
+  int rc = spg_lde_coeffs_device(ctx, trace, log_n, C, offset_canon, coeffs, mont);
   if (rc) return rc;
-  spg_stage_end(ctx, 0);
-  spg_stage_begin(ctx, 1);
-  rc = spg_lde_cosets_device(ctx, coeffs, log_n, C, log_blowup, 0, (size_t)1 << log_blowup, out);
-  if (rc) return rc;
-  spg_stage_end(ctx, 1);
-  return SPG_OK;
+  return spg_lde_cosets_device(ctx, coeffs, log_n, C, log_blowup, 0, (size_t)1 << log_blowup, out);
 }
 
 // common tail of the device-pointer entry points
@@ -137,8 +143,16 @@ extern "C" int spg_lde(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size
   }
   spg_stage_reset(ctx);
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = spg_lde_device(ctx, din, log_n, n_cols, log_blowup, coset_offset, dout, nullptr);
+  void* cf;
+  SPG_CUDA(spg_scratch(ctx, 0, in_bytes, &cf));
+  spg_stage_begin(ctx, 0);
+  int rc = spg_lde_coeffs_device(ctx, din, log_n, n_cols, coset_offset, (Fp*)cf, 0);
   if (rc) return rc;
+  spg_stage_end(ctx, 0);
+  spg_stage_begin(ctx, 1);
+  rc = spg_lde_cosets_device(ctx, (const Fp*)cf, log_n, n_cols, log_blowup, 0, (size_t)1 << log_blowup, dout);
+  if (rc) return rc;
+  spg_stage_end(ctx, 1);
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!(flags & SPG_DEVICE_PTRS))
     SPG_CUDA(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,423 @@
+// STARK prover for the Pedersen hash-chain AIR: host orchestration, Fiat-Shamir channel, proof assembly.
+// Stages (all on the device): LDE -> Merkle -> composition (AIR) -> chunk split + LDE -> Merkle ->
+// out-of-domain evaluation -> DEEP quotient -> FRI (fold by 8 + Merkle per layer) -> query openings.
+// Protocol: DESIGN.md "Protocol"; CPU restatement and verifier: oracle/stark.py.  The reference repository has
+// no prover; its only description of the prover boundary is the cairo-run artefact
+// list of src/starkware/cairo/lang/cairo_cmake_rules.cmake:72-110 -- here the "runner output" is the trace.
+#include <string.h>
+
+#include "blake2s.cuh"
+#include "stark_kernels.cuh"
+
+// ------------------------------------------------------------------ host helpers
+static void ser_fp(const Fp& a /*canonical representative of the Montgomery form*/, uint8_t* out) {
+  for (int k = 0; k < 8; k++) {
+    const uint32_t w = a.v[7 - k];
+    out[4 * k] = (uint8_t)(w >> 24); out[4 * k + 1] = (uint8_t)(w >> 16); out[4 * k + 2] = (uint8_t)(w >> 8); out[4 * k + 3] = (uint8_t)w;
+  }
+}
+static void put_u32(std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; i++) v.push_back((uint8_t)(x >> (8 * i))); }
+static void put_fp(std::vector<uint8_t>& v, const Fp& a) { uint8_t b[32]; ser_fp(a, b); v.insert(v.end(), b, b + 32); }
+static void put_bytes(std::vector<uint8_t>& v, const uint8_t* p, size_t n) { v.insert(v.end(), p, p + n); }
+
+struct Channel {
+  uint8_t state[32];
+  uint64_t counter = 0;
+  explicit Channel(const std::vector<uint8_t>& seed) {
+    std::vector<uint8_t> b;
+    const char* tag = "spg-stark-v1";
+    b.insert(b.end(), tag, tag + 12);
+    b.insert(b.end(), seed.begin(), seed.end());
+    b2s_hash_bytes(b.data(), b.size(), state);
+  }
+  void absorb(const uint8_t* data, size_t len) {
+    std::vector<uint8_t> b(state, state + 32);
+    b.insert(b.end(), data, data + len);
+    b2s_hash_bytes(b.data(), b.size(), state);
+    counter = 0;
+  }
+  void draw(uint8_t out[32]) {
+    uint8_t b[40];
+    memcpy(b, state, 32);
+    for (int i = 0; i < 8; i++) b[32 + i] = (uint8_t)(counter >> (8 * i));
+    b2s_hash_bytes(b, 40, out);
+    counter++;
+  }
+  Fp draw_felt() {   // Montgomery form of the drawn value (251 bits, always < p)
+    uint8_t d[32];
+    draw(d);
+    uint64_t w[4];
+    for (int k = 0; k < 4; k++) { w[k] = 0; for (int b = 7; b >= 0; b--) w[k] = (w[k] << 8) | d[8 * k + b]; }
+    w[3] &= (1ull << 59) - 1;
+    return spg_host_from_u64(w);
+  }
+  uint64_t draw_index(uint64_t n) {
+    uint8_t d[32];
+    draw(d);
+    uint64_t v = 0;
+    for (int b = 7; b >= 0; b--) v = (v << 8) | d[b];
+    return v % n;
+  }
+};
+
+// bump allocator over one cached device block
+struct Arena {
+  char* base; size_t cap, off;
+  template <class T> T* get(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (off + bytes > cap) return nullptr;
+    T* p = (T*)(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+// in-place radix-2 inverse NTT on the host (natural order in and out), n = 2^log_n
+static void host_intt(std::vector<Fp>& a, int log_n) {
+  const size_t n = a.size();
+  for (size_t i = 0; i < n; i++) { size_t r = spg_bitrev((unsigned)i, log_n); if (r > i) std::swap(a[i], a[r]); }
+  const Fp w = fp_inv(spg_host_root_of_unity(log_n));
+  for (size_t h = 1; h < n; h *= 2) {
+    const Fp wh = fp_pow_u64(w, n / (2 * h));
+    for (size_t b = 0; b < n; b += 2 * h) {
+      Fp t = fp_one();
+      for (size_t k = 0; k < h; k++) {
+        const Fp u = a[b + k], v = fp_mul(a[b + k + h], t);
+        a[b + k] = fp_add(u, v); a[b + k + h] = fp_sub(u, v);
+        t = fp_mul(t, wh);
+      }
+    }
+  }
+  uint64_t nn[4] = {(uint64_t)n, 0, 0, 0};
+  const Fp ninv = fp_inv(spg_host_from_u64(nn));
+  for (auto& x : a) x = fp_mul(x, ninv);
+}
+
+enum { ST_LDE = 0, ST_MERKLE_T, ST_AIR, ST_HLDE, ST_MERKLE_H, ST_OODS, ST_DEEP, ST_FRI, ST_QUERY, ST_H2D };
+
+// d_trace: [25][N] canonical felts on the device.  Appends the proof to `proof`.
+static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigned chain_log, const uint64_t* x0_canon,
+                        unsigned n_queries, std::vector<uint8_t>& proof) {
+  SPG_ARG(log_n >= 9 && log_n + SPG_LOG_BLOWUP <= SPG_UNI_LOG, "spg_prove: log_n must be in [9, 23]");
+  SPG_ARG(9 + chain_log <= log_n, "spg_prove: chain_log");
+  SPG_ARG(n_queries >= 1 && n_queries <= 1024, "spg_prove: n_queries");
+  const size_t n = (size_t)1 << log_n;
+  const int C = SPG_AIR_COLS;
+  // FRI layer sizes
+  std::vector<unsigned> log_rows = {log_n};
+  while ((1u << log_rows.back()) > SPG_FRI_LAST_MAX) log_rows.push_back(log_rows.back() - 3);
+  const int n_folds = (int)log_rows.size() - 1;
+  // ---- arena
+  size_t need = 0;
+  auto add = [&](size_t bytes) { need += (bytes + 255) & ~(size_t)255; };
+  add(C * n * 32); add(8 * C * n * 32); add(2 * n * 32);                 // t_coef, t_lde, tree_t
+  add(4 * n * 32); add(4 * n * 32); add(4 * n * 32); add(8 * 4 * n * 32); add(2 * n * 32);   // cp, hev, h_coef, h_lde, tree_h
+  add(3 * 8 * n * 32); add(8 * n * 32);                                  // inv3, layer0
+  for (int l = 1; l <= n_folds; l++) { add(((size_t)8 << log_rows[l]) * 32); add(((size_t)2 << log_rows[l]) * 32); }
+  add(4096 * 32);                                                         // small constants
+  add(n_queries * 4 * (2 + n_folds) + 4096);
+  add((size_t)n_queries * (8 * C + 8 * 4 + 8 * n_folds) * 32 + (size_t)n_queries * (2 + n_folds) * log_n * 32 + 4096);
+  void* block;
+  SPG_CUDA(spg_scratch(ctx, 1, need + 65536, &block));
+  Arena ar{(char*)block, need + 65536, 0};
+  Fp* t_coef = ar.get<Fp>(C * n); Fp* t_lde = ar.get<Fp>(8 * C * n); uint32_t* tree_t = ar.get<uint32_t>(16 * n);
+  Fp* cp = ar.get<Fp>(4 * n); Fp* hev = ar.get<Fp>(4 * n); Fp* h_coef = ar.get<Fp>(4 * n); Fp* h_lde = ar.get<Fp>(32 * n);
+  uint32_t* tree_h = ar.get<uint32_t>(16 * n);
+  Fp* inv3 = ar.get<Fp>(24 * n); Fp* layer0 = ar.get<Fp>(8 * n);
+  std::vector<Fp*> layers(n_folds + 1); std::vector<uint32_t*> trees(n_folds + 1, nullptr);
+  layers[0] = layer0;
+  for (int l = 1; l <= n_folds; l++) { layers[l] = ar.get<Fp>((size_t)8 << log_rows[l]); trees[l] = ar.get<uint32_t>((size_t)16 << log_rows[l]); }
+  Fp* d_small = ar.get<Fp>(4096);
+  SPG_ARG(d_small != nullptr, "arena sizing");
+  spg_stage_reset(ctx);
+
+  // ---- public input, channel
+  Fp h_last[SPG_AIR_LANES];
+  for (int l = 0; l < SPG_AIR_LANES; l++)
+    SPG_CUDA(cudaMemcpyAsync(&h_last[l], d_trace + ((size_t)(5 * l) << log_n) + (n - 1), sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  AirPublic pub;
+  for (int l = 0; l < SPG_AIR_LANES; l++) {
+    pub.x0[l] = spg_host_from_u64(x0_canon + 4 * l);
+    uint64_t w[4]; fp_to_u64(h_last[l], w);
+    pub.outs[l] = spg_host_from_u64(w);
+  }
+  std::vector<uint8_t> seed;
+  put_u32(seed, log_n); put_u32(seed, chain_log); put_u32(seed, n_queries);
+  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.x0[l]);
+  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.outs[l]);
+  Channel ch(seed);
+  proof.insert(proof.end(), {'S', 'P', 'G', 'P'});
+  put_u32(proof, 1); put_u32(proof, log_n); put_u32(proof, chain_log); put_u32(proof, n_queries); put_u32(proof, (uint32_t)n_folds);
+  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.x0[l]);
+  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.outs[l]);
+
+  int rc;
+  uint8_t root[32];
+  // ---- 1. trace LDE (canonical in, Montgomery out) + commitment
+  spg_stage_begin(ctx, ST_LDE);
+  if ((rc = spg_lde_device(ctx, d_trace, log_n, C, SPG_LOG_BLOWUP, nullptr, t_lde, t_coef, /*mont=*/1))) return rc;
+  spg_stage_end(ctx, ST_LDE);
+  spg_stage_begin(ctx, ST_MERKLE_T);
+  if ((rc = spg_merkle_build_device(ctx, t_lde, C, n, tree_t))) return rc;
+  spg_stage_end(ctx, ST_MERKLE_T);
+  SPG_CUDA(cudaMemcpyAsync(root, tree_t + 8 * (2 * n - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ch.absorb(root, 32);
+  put_bytes(proof, root, 32);
+  // ---- 2. composition polynomial on cosets 0, 2, 4, 6; chunk split; chunk LDE; commitment
+  const Fp alpha = ch.draw_felt();
+  Fp apows[SPG_AIR_LANES * SPG_AIR_NCONSTR];
+  apows[0] = fp_one();
+  for (int k = 1; k < SPG_AIR_LANES * SPG_AIR_NCONSTR; k++) apows[k] = fp_mul(apows[k - 1], alpha);
+  spg_stage_begin(ctx, ST_AIR);
+  if ((rc = spg_air_eval_device(ctx, log_n, chain_log, t_lde, pub, apows, cp))) return rc;
+  spg_stage_end(ctx, ST_AIR);
+  spg_stage_begin(ctx, ST_HLDE);
+  if ((rc = spg_cp_split_device(ctx, log_n, cp, hev))) return rc;
+  {
+    // chunk values live on g^4 <w_N>; evaluate on g w_{8N}^j <w_N>: offset g / g^4 = g^-3
+    uint64_t three[4] = {3, 0, 0, 0}, off[4];
+    const Fp g = spg_host_from_u64(three);
+    spg_host_to_u64(fp_inv(fp_mul(fp_mul(g, g), g)), off);
+    if ((rc = spg_lde_device(ctx, hev, log_n, 4, SPG_LOG_BLOWUP, off, h_lde, h_coef, /*mont=*/0))) return rc;
+  }
+  spg_stage_end(ctx, ST_HLDE);
+  spg_stage_begin(ctx, ST_MERKLE_H);
+  if ((rc = spg_merkle_build_device(ctx, h_lde, 4, n, tree_h))) return rc;
+  spg_stage_end(ctx, ST_MERKLE_H);
+  SPG_CUDA(cudaMemcpyAsync(root, tree_h + 8 * (2 * n - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ch.absorb(root, 32);
+  put_bytes(proof, root, 32);
+  // ---- 3. out-of-domain sampling
+  const Fp z = ch.draw_felt();
+  const Fp wn = spg_host_root_of_unity((int)log_n);
+  const Fp zw = fp_mul(z, wn), z2 = fp_sqr(z), z4 = fp_sqr(z2);
+  Fp oods[SPG_N_OODS];
+  {
+    uint64_t three[4] = {3, 0, 0, 0};
+    const Fp ginv = fp_inv(spg_host_from_u64(three));
+    Fp pts[3] = {fp_mul(z, ginv), fp_mul(zw, ginv), fp_mul(z4, ginv)};
+    const Fp* cols[SPG_N_OODS]; int pidx[SPG_N_OODS];
+    for (int c = 0; c < C; c++) { cols[c] = t_coef + ((size_t)c << log_n); pidx[c] = 0; cols[C + c] = cols[c]; pidx[C + c] = 1; }
+    for (int m = 0; m < 4; m++) { cols[2 * C + m] = h_coef + ((size_t)m << log_n); pidx[2 * C + m] = 2; }
+    spg_stage_begin(ctx, ST_OODS);
+    if ((rc = spg_poly_eval_device(ctx, log_n, cols, pidx, SPG_N_OODS, pts, 3, oods))) return rc;
+    spg_stage_end(ctx, ST_OODS);
+  }
+  {
+    // self-check: the composition recomputed on the host from the trace values at z must equal sum z^m H_m(z^4)
+    const Fp lhs = spg_air_composition_at_host(log_n, chain_log, pub, apows, z, oods, oods + C, ctx->h_const_points);
+    Fp rhs = fp_zero(), zp = fp_one();
+    for (int m = 0; m < 4; m++) { rhs = fp_add(rhs, fp_mul(zp, oods[2 * C + m])); zp = fp_mul(zp, z); }
+    if (!fp_eq(lhs, rhs)) { ctx->err = "trace does not satisfy the AIR (composition mismatch at the out-of-domain point)"; return SPG_E_PROOF; }
+  }
+  {
+    std::vector<uint8_t> b;
+    for (int k = 0; k < SPG_N_OODS; k++) put_fp(b, oods[k]);
+    ch.absorb(b.data(), b.size());
+    put_bytes(proof, b.data(), b.size());
+  }
+  // ---- 4. DEEP quotient
+  const Fp gamma = ch.draw_felt();
+  {
+    Fp gp[SPG_N_OODS + 6];
+    gp[0] = fp_one();
+    for (int k = 1; k < SPG_N_OODS; k++) gp[k] = fp_mul(gp[k - 1], gamma);
+    Fp K[3] = {fp_zero(), fp_zero(), fp_zero()};
+    for (int c = 0; c < C; c++) { K[0] = fp_add(K[0], fp_mul(gp[c], oods[c])); K[1] = fp_add(K[1], fp_mul(gp[C + c], oods[C + c])); }
+    for (int m = 0; m < 4; m++) K[2] = fp_add(K[2], fp_mul(gp[2 * C + m], oods[2 * C + m]));
+    gp[SPG_N_OODS] = K[0]; gp[SPG_N_OODS + 1] = K[1]; gp[SPG_N_OODS + 2] = K[2];
+    gp[SPG_N_OODS + 3] = z; gp[SPG_N_OODS + 4] = zw; gp[SPG_N_OODS + 5] = z4;
+    SPG_CUDA(cudaMemcpyAsync(d_small, gp, sizeof(gp), cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    spg_stage_begin(ctx, ST_DEEP);
+    if ((rc = spg_inv_x_minus_device(ctx, log_n, 0, 1, 8, d_small + SPG_N_OODS + 3, 3, inv3))) return rc;
+    if ((rc = spg_deep_device(ctx, log_n, t_lde, h_lde, inv3, d_small, d_small + SPG_N_OODS, layer0))) return rc;
+    spg_stage_end(ctx, ST_DEEP);
+  }
+  // ---- 5. FRI
+  std::vector<uint8_t> fri_roots;
+  {
+    uint64_t three[4] = {3, 0, 0, 0};
+    Fp g_l = spg_host_from_u64(three);
+    spg_stage_begin(ctx, ST_FRI);
+    for (int l = 1; l <= n_folds; l++) {
+      const Fp beta = ch.draw_felt();
+      if ((rc = spg_fri_fold8_device(ctx, layers[l - 1], log_rows[l - 1], fp_mul(beta, fp_inv(g_l)), layers[l]))) return rc;
+      if ((rc = spg_merkle_build_device(ctx, layers[l], 1, (size_t)1 << log_rows[l], trees[l]))) return rc;
+      SPG_CUDA(cudaMemcpyAsync(root, trees[l] + 8 * (((size_t)2 << log_rows[l]) - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
+      SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+      ch.absorb(root, 32);
+      put_bytes(fri_roots, root, 32);
+      for (int k = 0; k < 3; k++) g_l = fp_sqr(g_l);
+    }
+    spg_stage_end(ctx, ST_FRI);
+    put_bytes(proof, fri_roots.data(), fri_roots.size());
+    // last layer -> coefficients
+    const unsigned lr = log_rows[n_folds];
+    const size_t n_last = (size_t)1 << lr;
+    std::vector<Fp> vals(8 * n_last), flat(8 * n_last);
+    SPG_CUDA(cudaMemcpyAsync(vals.data(), layers[n_folds], vals.size() * sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t j = 0; j < 8; j++) for (size_t i = 0; i < n_last; i++) flat[j + 8 * i] = vals[j * n_last + i];
+    host_intt(flat, (int)lr + 3);
+    const Fp gli = fp_inv(g_l);
+    Fp s = fp_one();
+    for (size_t k = 0; k < flat.size(); k++) { flat[k] = fp_mul(flat[k], s); s = fp_mul(s, gli); }
+    for (size_t k = n_last; k < flat.size(); k++)
+      if (!fp_is_zero(flat[k])) { ctx->err = "trace does not satisfy the AIR (FRI last layer is not of low degree)"; return SPG_E_PROOF; }
+    std::vector<uint8_t> b;
+    for (size_t k = 0; k < n_last; k++) put_fp(b, flat[k]);
+    ch.absorb(b.data(), b.size());
+    put_bytes(proof, b.data(), b.size());
+  }
+  // ---- 6. queries
+  spg_stage_begin(ctx, ST_QUERY);
+  {
+    const int nt = 2 + n_folds;    // tables opened per query
+    std::vector<uint32_t> idx((size_t)nt * n_queries);
+    for (unsigned q = 0; q < n_queries; q++) {
+      const uint64_t id = ch.draw_index(n);
+      idx[q] = idx[n_queries + q] = (uint32_t)id;
+      uint64_t j = id / (n / 8), ip = id % (n / 8);
+      for (int l = 1; l <= n_folds; l++) {
+        const uint64_t g8 = ((uint64_t)1 << log_rows[l]) / 8;
+        ip %= g8;
+        idx[(size_t)(1 + l) * n_queries + q] = (uint32_t)(j * g8 + ip);
+      }
+    }
+    uint32_t* d_idx = ar.get<uint32_t>(idx.size() + 64);
+    // per table: leaf words and path words
+    std::vector<size_t> leaf_words(nt), path_words(nt), leaf_off(nt), path_off(nt);
+    size_t total_words = 0;
+    for (int t = 0; t < nt; t++) {
+      const int ncols = t == 0 ? C : (t == 1 ? 4 : 1);
+      const unsigned lg = t < 2 ? log_n : log_rows[t - 1];
+      leaf_words[t] = (size_t)8 * ncols * 8; path_words[t] = (size_t)lg * 8;
+      leaf_off[t] = total_words; total_words += leaf_words[t] * n_queries;
+      path_off[t] = total_words; total_words += path_words[t] * n_queries;
+    }
+    uint32_t* d_open = ar.get<uint32_t>(total_words + 64);
+    SPG_ARG(d_idx && d_open, "arena sizing (queries)");
+    SPG_CUDA(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (int t = 0; t < nt; t++) {
+      const Fp* table = t == 0 ? t_lde : (t == 1 ? h_lde : layers[t - 1]);
+      const uint32_t* tree = t == 0 ? tree_t : (t == 1 ? tree_h : trees[t - 1]);
+      const int ncols = t == 0 ? C : (t == 1 ? 4 : 1);
+      const size_t rows = (size_t)1 << (t < 2 ? log_n : log_rows[t - 1]);
+      if ((rc = spg_merkle_open_device(ctx, table, ncols, rows, tree, d_idx + (size_t)t * n_queries, (int)n_queries,
+                                       d_open + leaf_off[t], d_open + path_off[t]))) return rc;
+    }
+    std::vector<uint32_t> open(total_words);
+    SPG_CUDA(cudaMemcpyAsync(open.data(), d_open, total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    const uint8_t* ob = (const uint8_t*)open.data();
+    for (unsigned q = 0; q < n_queries; q++)
+      for (int t = 0; t < nt; t++) {
+        put_bytes(proof, ob + 4 * (leaf_off[t] + leaf_words[t] * q), 4 * leaf_words[t]);
+        put_bytes(proof, ob + 4 * (path_off[t] + path_words[t] * q), 4 * path_words[t]);
+      }
+  }
+  spg_stage_end(ctx, ST_QUERY);
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  spg_stage_collect(ctx);
+  return SPG_OK;
+}
+
+// ------------------------------------------------------------------ C-ABI
+extern "C" int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+                         unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags) {
+  SPG_ARG(ctx && trace && x0 && proof_len, "spg_prove: null");
+  SPG_ARG(log_n >= 9 && log_n <= 23, "spg_prove: log_n must be in [9, 23]");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)1 << log_n, bytes = (size_t)SPG_AIR_COLS * n * 32;
+  const Fp* d_trace = (const Fp*)trace;
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    void* p;
+    SPG_CUDA(spg_scratch(ctx, 2, bytes, &p));
+    SPG_CUDA(cudaMemcpyAsync(p, trace, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_trace = (const Fp*)p;
+  }
+  std::vector<uint8_t> proof;
+  int rc = prove_device(ctx, d_trace, log_n, chain_log, x0, n_queries, proof);
+  if (rc) return rc;
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  *proof_len = proof.size();
+  if (proof_out) {
+    SPG_ARG(proof_cap >= proof.size(), "spg_prove: proof buffer too small (call with proof_out = NULL for the size)");
+    memcpy(proof_out, proof.data(), proof.size());
+  }
+  return SPG_OK;
+}
+
+extern "C" int spg_pedersen_chain_trace(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+                                        const uint64_t* ys, uint64_t* trace_out, int flags) {
+  SPG_ARG(ctx && x0 && ys && trace_out, "spg_pedersen_chain_trace: null");
+  SPG_ARG(log_n >= 9 && log_n <= 23 && 9 + chain_log <= log_n, "spg_pedersen_chain_trace: size");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)1 << log_n, inst = n >> 9, bytes = (size_t)SPG_AIR_COLS * n * 32;
+  DevBuf dx, dy, dt, ds;
+  SPG_CUDA(dx.alloc(SPG_AIR_LANES * 32)); SPG_CUDA(ds.alloc(4));
+  SPG_CUDA(cudaMemcpyAsync(dx.p, x0, SPG_AIR_LANES * 32, cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaMemsetAsync(ds.p, 0, 4, ctx->stream));
+  const Fp* dys = (const Fp*)ys;
+  Fp* dtr = (Fp*)trace_out;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(dy.alloc(SPG_AIR_LANES * inst * 32)); SPG_CUDA(dt.alloc(bytes));
+    SPG_CUDA(cudaMemcpyAsync(dy.p, ys, SPG_AIR_LANES * inst * 32, cudaMemcpyHostToDevice, ctx->stream));
+    dys = dy.as<Fp>(); dtr = dt.as<Fp>();
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  int rc = spg_pedersen_trace_device(ctx, log_n, chain_log, dx.as<Fp>(), dys, dtr, ds.as<uint8_t>());
+  if (rc) return rc;
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS)) SPG_CUDA(cudaMemcpyAsync(trace_out, dtr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  uint32_t st = 0;
+  SPG_CUDA(cudaMemcpyAsync(&st, ds.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  if (st & 1) { ctx->err = "spg_pedersen_chain_trace: an input is >= p"; return SPG_E_ARG; }
+  if (st & 2) { ctx->err = "spg_pedersen_chain_trace: Unhashable input."; return SPG_E_ARG; }
+  return SPG_OK;
+}
+
+// composition polynomial of a trace on the cosets j = 0, 2, 4, 6 (parity / bench entry point for the AIR stage):
+// trace [25][N] canonical -> cp [4][N] canonical;  alpha canonical.
+extern "C" int spg_air_eval(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+                            const uint64_t* outs, const uint64_t* alpha, uint64_t* cp_out, int flags) {
+  SPG_ARG(ctx && trace && x0 && outs && alpha && cp_out, "spg_air_eval: null");
+  SPG_ARG(log_n >= 9 && log_n <= 23 && 9 + chain_log <= log_n, "spg_air_eval: size");
+  SPG_ARG(!(flags & SPG_DEVICE_PTRS), "spg_air_eval: host pointers only");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)1 << log_n;
+  DevBuf dt, dl, dc, dcp;
+  SPG_CUDA(dt.alloc(SPG_AIR_COLS * n * 32)); SPG_CUDA(dl.alloc(8 * SPG_AIR_COLS * n * 32)); SPG_CUDA(dc.alloc(SPG_AIR_COLS * n * 32));
+  SPG_CUDA(dcp.alloc(4 * n * 32));
+  SPG_CUDA(cudaMemcpyAsync(dt.p, trace, SPG_AIR_COLS * n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  AirPublic pub;
+  for (int l = 0; l < SPG_AIR_LANES; l++) { pub.x0[l] = spg_host_from_u64(x0 + 4 * l); pub.outs[l] = spg_host_from_u64(outs + 4 * l); }
+  Fp apows[SPG_AIR_LANES * SPG_AIR_NCONSTR];
+  const Fp a = spg_host_from_u64(alpha);
+  apows[0] = fp_one();
+  for (int k = 1; k < SPG_AIR_LANES * SPG_AIR_NCONSTR; k++) apows[k] = fp_mul(apows[k - 1], a);
+  int rc = spg_lde_device(ctx, dt.as<Fp>(), log_n, SPG_AIR_COLS, SPG_LOG_BLOWUP, nullptr, dl.as<Fp>(), dc.as<Fp>(), 1);
+  if (rc) return rc;
+  spg_stage_reset(ctx);
+  spg_stage_begin(ctx, ST_AIR);
+  rc = spg_air_eval_device(ctx, log_n, chain_log, dl.as<Fp>(), pub, apows, dcp.as<Fp>());
+  if (rc) return rc;
+  spg_stage_end(ctx, ST_AIR);
+  // Montgomery -> canonical for the caller
+  rc = spg_from_mont_device(ctx, dcp.as<Fp>(), 4 * n);
+  if (rc) return rc;
+  SPG_CUDA(cudaMemcpyAsync(cp_out, dcp.p, 4 * n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  spg_stage_collect(ctx);
+  ctx->last_ms = ctx->stage_ms[ST_AIR];
+  return SPG_OK;
+}
