@@ -4,16 +4,16 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun by the driver)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-One "step" = one pass of the hot path over one synthetic 2^20-row, 25-column trace (BASELINE.json
-configs[2], the configuration the metric is quoted on).  The trace is FIXED as N grows (strong scaling):
-columns are sharded for interpolation, one NCCL all-gather exchanges the coefficient columns, cosets are
-sharded for evaluation.
+One "step" = one full proof (trace LDE blowup 8 -> Merkle -> AIR composition -> chunk LDE -> Merkle -> OODS ->
+DEEP -> FRI -> queries) of one synthetic but VALID 2^20-row, 25-column Pedersen hash-chain trace -- the
+configuration BASELINE.json's metric is quoted on ("2^20-step trace", configs[2] plus the FRI/Merkle stages of
+configs[3]).  The trace is FIXED as N grows (strong scaling).
 
 Prints ONE JSON line on rank 0.  `value` = algorithmic 252-bit field multiplications per second over the
-whole job with inputs resident in HBM; `e2e` = the same through the host-buffer C-ABI call (H2D of the
-trace and D2H of the result inside the timed region).  `--impl reference` times the CPU restatement
-(oracle/c, OpenMP on all host cores) -- the reference repository itself contains no prover to time
-(SURVEY.md section 0), so kind = "port".
+whole job with the trace resident in HBM; `proof_gen_s` = seconds per proof; `e2e` = the same through the
+host-buffer C-ABI call spg_prove (H2D of the 840 MB trace and D2H of the proof inside the timed region).
+`--impl reference` times the CPU restatement (oracle/c, OpenMP on all host cores) on a bounded sample -- the
+reference repository itself contains no prover to time, so kind = "port".
 """
 import argparse
 import json
@@ -29,27 +29,40 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-METRIC = "field_mul_per_s_2^20_trace_prove_path"
+METRIC = "field_mul_per_s_2^20_trace_proof"
 UNIT = "252-bit field-mul/s"
+STAGES = ["lde_trace", "merkle_trace", "air_composition", "lde_chunks", "merkle_chunks", "oods_eval", "deep_quotient",
+          "fri", "queries"]
 
 
 def workload_cfg(args):
-    return {"log_n": args.log_n, "n_cols": args.cols, "log_blowup": args.log_blowup}
+    return {"log_n": args.log_n, "n_cols": 25, "log_blowup": 3, "chain_log": args.chain_log, "n_queries": args.queries}
 
 
-def algorithmic_muls(cfg, stages):
-    """butterflies (N/2 log2 N per transform) + one multiplication per point for
-    scaling / coset shift, per column; plus the counted multiplications of the later stages."""
-    n, c, b, ln = 1 << cfg["log_n"], cfg["n_cols"], 1 << cfg["log_blowup"], cfg["log_n"]
-    total = c * n * ((1 + b) * ln / 2.0 + (1 + b))
-    for s in stages:
-        total += s
-    return total
+def lde_muls(n_cols, log_n, blowup=8):
+    """butterflies (N/2 log2 N per transform) + one multiplication per point for the
+    scaling / coset shift, per column."""
+    n = 1 << log_n
+    return n_cols * n * ((1 + blowup) * log_n / 2.0 + (1 + blowup))
 
 
-def host_trace(cfg, seed):
+def proof_muls(cfg):
+    """Algorithmic multiplication count of one proof, stage by stage (DESIGN.md "Work per proof")."""
+    n, ln = 1 << cfg["log_n"], cfg["log_n"]
+    st = {
+        "lde_trace": lde_muls(25, ln),
+        "air_composition": 4 * n * (5 * 21 + 8) + n * 12,     # 21 per lane + 8 zerofier products; chunk split
+        "lde_chunks": lde_muls(4, ln),
+        "oods_eval": 54 * n,
+        "deep_quotient": 8 * n * (54 + 3) + 3 * 8 * n * 5,    # quotient + batched inversion (5 per point)
+        "fri": 15 * n * 8 / 7.0,                              # fold-by-8 layers, geometric
+    }
+    return sum(st.values()), st
+
+
+def host_trace_random(n_cols, log_n, seed):
     from conftest import rand_felts
-    return rand_felts(cfg["n_cols"] << cfg["log_n"], seed)
+    return rand_felts(n_cols << log_n, seed)
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -64,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -92,20 +105,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_sample(cfg, cores_cols=None):
-    """Time the C oracle (OpenMP) on a bounded sample: as many columns of the same 2^log_n trace as there
-    are host threads (one column per thread), full blowup.  Returns (muls_per_s, cores, description)."""
+def cpu_sample(cfg):
+    """Time the C oracle (OpenMP) on a bounded sample of the proof's dominant stage: the blowup-8 LDE of as
+    many 2^log_n columns as there are host threads (one per thread).  Returns (mul/s, cores, text, seconds)."""
     from oracle import clib
     cores = clib.num_threads()
-    sample_cols = min(cfg["n_cols"], cores_cols or cores)
-    sub = dict(cfg, n_cols=sample_cols)
-    tr = host_trace(sub, 4242)
+    sample_cols = max(1, min(25, cores))
+    tr = host_trace_random(sample_cols, cfg["log_n"], 4242)
     t0 = time.perf_counter()
     clib.lde(tr, cfg["log_n"], sample_cols, cfg["log_blowup"])
     dt = time.perf_counter() - t0
-    muls = algorithmic_muls(sub, [])
-    return muls / dt, cores, "%d of %d columns of the 2^%d trace, blowup %d, C oracle (OpenMP, %d threads), %.1f s" % (
-        sample_cols, cfg["n_cols"], cfg["log_n"], 1 << cfg["log_blowup"], cores, dt), dt
+    muls = lde_muls(sample_cols, cfg["log_n"])
+    return muls / dt, cores, ("LDE stage (%.0f%% of a proof's multiplications) of %d of the 25 columns of the 2^%d trace, "
+                              "blowup 8, plain-C oracle with OpenMP on %d threads, %.1f s") % (
+        100 * lde_muls(25, cfg["log_n"]) / proof_muls(cfg)[0], sample_cols, cfg["log_n"], cores, dt), dt
 
 
 def reference_arm(args):
@@ -113,7 +126,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     cfg = workload_cfg(args)
-    vals, dts = [], []
+    vals, dts, desc, cores = [], [], "", 1
     for i in range(args.warmup + args.steps):
         v, cores, desc, dt = cpu_sample(cfg)
         if i >= args.warmup:
@@ -121,15 +134,16 @@ def reference_arm(args):
         if sum(dts) > 150:      # keep the whole run within a few minutes
             break
     v = float(np.mean(vals))
+    total, _ = proof_muls(cfg)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u256 (4x u64 Montgomery)",
-            "data": "synthetic", "config": dict(workload="lde_2^%d_x%d_blowup%d" % (cfg["log_n"], cfg["n_cols"], 1 << cfg["log_blowup"]),
-                                                  **cfg),
+            "data": "synthetic", "config": dict(workload="stark_proof_2^%d_x25_blowup8" % cfg["log_n"], **cfg),
+            "proof_gen_s_extrapolated": total / v,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "the reference repository has no prover (SURVEY.md section 0); this is the repo's own plain-C "
-                    "restatement of the same stages, all host threads"}
+                    "restatement, all host threads, on a bounded sample (one step = the sample)"}
     print(json.dumps(line))
     return 0
 
@@ -142,10 +156,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log-n", dest="log_n", type=int, default=20)
-    ap.add_argument("--cols", type=int, default=25)
-    ap.add_argument("--log-blowup", dest="log_blowup", type=int, default=3)
+    ap.add_argument("--chain-log", dest="chain_log", type=int, default=2)
+    ap.add_argument("--queries", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle verification of one proof")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -154,6 +169,7 @@ def main():
     import torch
     import torch.distributed as dist
     import stark_perpetual_b200 as spg
+    from stark_perpetual_b200 import prover
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,55 +179,50 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = workload_cfg(args)
-    n, C, B = 1 << cfg["log_n"], cfg["n_cols"], 1 << cfg["log_blowup"]
-    assert B % world == 0, "blowup must be a multiple of the GPU count"
+    log_n, n = cfg["log_n"], 1 << cfg["log_n"]
     ctx = spg.Context(local)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    pv = prover.Prover(ctx, rank=rank, world=world)
 
-    # column shard of this rank for phase A (contiguous blocks; the last ranks may hold one column less)
-    per = (C + world - 1) // world
-    c0, c1 = min(C, rank * per), min(C, (rank + 1) * per)
-    my_cols = c1 - c0
-    cosets = B // world
-    full = host_trace(cfg, 1003)                      # seed of SURVEY.md section 8(d) cfg 3a
-    host = torch.from_numpy(full.view(np.int64)).reshape(C, n, 4)
-    pinned = host[c0:c1].contiguous().pin_memory() if my_cols else None
-    trace = torch.empty((max(my_cols, 1), n, 4), dtype=torch.int64, device=dev)
-    if my_cols:
-        trace[:my_cols].copy_(pinned)
-    coeffs = torch.empty((per * world, n, 4), dtype=torch.int64, device=dev)   # padded to equal shards
-    out = torch.empty((cosets, C, n, 4), dtype=torch.int64, device=dev)
+    # ---- synthetic but valid trace (seed 1003, SURVEY.md section 8(d) cfg 3a): witness generated on the device
+    rng = np.random.Generator(np.random.PCG64(1003))
+    from conftest import rand_felts
+    inst = n >> 9
+    x0_limbs = rand_felts(5, 1003)
+    ys_limbs = rand_felts(5 * inst, 1004)
+    from stark_perpetual_b200._lib import limbs_to_ints
+    x0 = limbs_to_ints(x0_limbs)
+    trace_host = ctx.pedersen_chain_trace(log_n, cfg["chain_log"], x0, ys_limbs)          # (25 N, 4) uint64
+    pinned = torch.from_numpy(trace_host.view(np.int64)).pin_memory()
+    trace = torch.empty_like(pinned, device=dev)
+    trace.copy_(pinned)
+    torch.cuda.synchronize()
     launches_before = ctx.launch_count
 
     def step():
-        if world == 1:
-            ctx.lde_device(trace.data_ptr(), cfg["log_n"], C, cfg["log_blowup"], out.data_ptr(), sync=False)
-        else:
-            mine = coeffs[rank * per:(rank + 1) * per]
-            if my_cols:
-                ctx.lde_coeffs_device(trace.data_ptr(), cfg["log_n"], my_cols, mine.data_ptr(), sync=False)
-            dist.all_gather_into_tensor(coeffs, mine)           # the single exchange step
-            ctx.lde_cosets_device(coeffs.data_ptr(), cfg["log_n"], C, cfg["log_blowup"], rank * cosets, cosets,
-                                  out.data_ptr(), sync=False)
+        return pv.prove_device(trace.data_ptr(), log_n, cfg["chain_log"], x0, cfg["n_queries"])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    proof = None
     for _ in range(args.warmup):
-        step()
+        proof = step()
     barrier()
     launches_per_step = (ctx.launch_count - launches_before) // args.warmup
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = np.zeros(len(STAGES))
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        step()
+        proof = step()
+        stage_ms += np.array([ctx.stage_ms(i) for i in range(len(STAGES))])
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -220,40 +231,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     clocks = sampler.stop() if rank == 0 else None
+    stage_ms /= args.steps
 
-    # dominant kernel (k_ntt_pass) live timing: one synchronous step, stage events inside the library
-    if world == 1:
-        ctx.lde_device(trace.data_ptr(), cfg["log_n"], C, cfg["log_blowup"], out.data_ptr(), sync=True)
-        ntt_ms = ctx.stage_ms(0) + ctx.stage_ms(1)
-        n_pass_launches = launches_per_step
-    else:
-        ntt_ms, n_pass_launches = None, launches_per_step
-
-    # e2e: host buffers through the C-ABI (pinned host memory), H2D + compute + D2H inside the timed region
+    # ---- e2e: host trace through the C-ABI (pinned host memory): H2D + proof + D2H of the proof bytes
     e2e = None
     if not args.no_e2e:
-        h2d = my_cols * n * 32
-        d2h = cosets * C * n * 32
-        res_host = torch.empty((cosets, C, n, 4), dtype=torch.int64).pin_memory()
-        def step_e2e():
-            if my_cols:
-                trace[:my_cols].copy_(pinned, non_blocking=True)
-            step()
-            res_host.copy_(out, non_blocking=True)
-        step_e2e(); barrier()
+        pv.prove_host(pinned.numpy().view(np.uint64), log_n, cfg["chain_log"], x0, cfg["n_queries"])
+        barrier()
         e0.record(stream)
         for _ in range(args.steps):
-            step_e2e()
+            pr2 = pv.prove_host(pinned.numpy().view(np.uint64), log_n, cfg["chain_log"], x0, cfg["n_queries"])
         e1.record(stream)
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item()) / args.steps
-        e2e = {"ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        e2e = {"ms_per_step": float(t.item()) / args.steps, "h2d_bytes_per_step": 25 * n * 32,
+               "d2h_bytes_per_step": len(pr2) if pr2 is not None else 0}
 
     if rank == 0:
-        muls = algorithmic_muls(cfg, [])
+        muls, per_stage = proof_muls(cfg)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -264,29 +261,44 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u256 (8x u32 limbs, Montgomery)",
                 "data": "synthetic",
-                "config": dict(workload="lde_2^%d_x%d_blowup%d" % (cfg["log_n"], C, B), **cfg,
+                "config": dict(workload="stark_proof_2^%d_x25_blowup8" % log_n, **cfg,
                                l2="working set %.1f GB per step, far above the 126 MB L2; no flush needed" % (
-                                   (1 + B) * C * n * 32 / 1e9),
-                               parallelism="columns->all_gather->cosets x%d" % world),
-                "proof_gen_s": None, "stage_s": {"lde": ms_per_step * 1e-3},
+                                   (1 + 8) * 29 * n * 32 / 1e9),
+                               parallelism=pv.parallelism()),
+                "proof_gen_s": ms_per_step * 1e-3, "proof_bytes": len(proof) if proof else None,
+                "stage_ms": {s: round(float(v), 4) for s, v in zip(STAGES, stage_ms)},
+                "algorithmic_muls_per_step": muls,
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
-        if ntt_ms:
-            # every k_ntt_pass launch reads and writes each element of its columns once: 64 B per element
-            passes = 2 if cfg["log_n"] > 10 else 1
-            bytes_total = (1 + B) * C * n * 64.0 * passes
+        # dominant kernel: k_ntt_pass (all launches of the two LDE stages); every launch reads and writes each
+        # element of its columns once -> 64 B per element per pass
+        ntt_ms = float(stage_ms[0] + stage_ms[3])
+        if ntt_ms > 0 and world == 1:
+            passes = 2 if log_n > 10 else 1
+            bytes_total = (1 + 8) * 29 * n * 64.0 * passes
+            n_launch = (1 + 8) * 2 * passes
             ach = bytes_total / (ntt_ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "kernel": "k_ntt_pass", "achieved": ach, "peak": peak, "unit": "GB/s",
                                 "frac": ach / peak, "traffic": None,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
-                                "launches": n_pass_launches, "avg_launch_ms": ntt_ms / max(1, n_pass_launches),
-                                "field_mul_per_s": muls / (ntt_ms * 1e-3)}
+                                "launches_per_step": n_launch, "avg_launch_ms": ntt_ms / n_launch,
+                                "share_of_step": ntt_ms / ms_per_step,
+                                "field_mul_per_s": (per_stage["lde_trace"] + per_stage["lde_chunks"]) / (ntt_ms * 1e-3),
+                                "note": "integer-ALU bound (SURVEY.md section 8d): ~200 SASS instructions per 252-bit "
+                                        "multiplication; see DESIGN.md for the IMAD ceiling"}
         if e2e:
             line["e2e"] = {"value": muls / (e2e["ms_per_step"] * 1e-3), "unit": UNIT,
-                           "h2d_bytes_per_step": e2e["h2d_bytes_per_step"] * world if world > 1 else e2e["h2d_bytes_per_step"],
-                           "d2h_bytes_per_step": e2e["d2h_bytes_per_step"] * world, "ms_per_step": e2e["ms_per_step"]}
+                           "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
+                           "ms_per_step": e2e["ms_per_step"], "proof_gen_s": e2e["ms_per_step"] * 1e-3}
+        if not args.no_verify and proof is not None:
+            from oracle import stark as ostark
+            t0 = time.perf_counter()
+            ostark.verify(proof)
+            line["verified_by_oracle"] = True
+            line["verify_s"] = round(time.perf_counter() - t0, 3)
         if world == 1 and not args.no_cpu:
             v, cores, desc, _dt = cpu_sample(cfg)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                                    "proof_gen_s_extrapolated": muls / v}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

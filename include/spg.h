@@ -122,8 +122,8 @@ int spg_air_eval(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned c
 /* Full proof.  trace: [25][2^log_n] canonical felts (host, or device with SPG_DEVICE_PTRS); x0 [5] canonical
  * (host).  Writes the proof bytes (format: DESIGN.md "Proof") to proof_out (capacity proof_cap) and their
  * number to *proof_len; with proof_out = NULL only the length is returned.  SPG_E_PROOF if the trace does
- * not satisfy the AIR.  Stages for spg_stage_ms: 0 trace LDE, 1 trace Merkle, 2 AIR/composition, 3 chunk
- * split + LDE, 4 chunk Merkle, 5 out-of-domain evaluation, 6 DEEP quotient, 7 FRI, 8 query openings. */
+ * not satisfy the AIR.  Stages for spg_stage_ms: 0 trace LDE, 1 trace Merkle, 2 AIR/composition + chunk
+ * split, 3 chunk LDE, 4 chunk Merkle, 5 out-of-domain evaluation, 6 DEEP quotient, 7 FRI, 8 query openings. */
 int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
               unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
 

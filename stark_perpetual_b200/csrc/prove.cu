@@ -172,9 +172,9 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
   for (int k = 1; k < SPG_AIR_LANES * SPG_AIR_NCONSTR; k++) apows[k] = fp_mul(apows[k - 1], alpha);
   spg_stage_begin(ctx, ST_AIR);
   if ((rc = spg_air_eval_device(ctx, log_n, chain_log, t_lde, pub, apows, cp))) return rc;
+  if ((rc = spg_cp_split_device(ctx, log_n, cp, hev))) return rc;
   spg_stage_end(ctx, ST_AIR);
   spg_stage_begin(ctx, ST_HLDE);
-  if ((rc = spg_cp_split_device(ctx, log_n, cp, hev))) return rc;
   {
     // chunk values live on g^4 <w_N>; evaluate on g w_{8N}^j <w_N>: offset g / g^4 = g^-3
     uint64_t three[4] = {3, 0, 0, 0}, off[4];
