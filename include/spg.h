@@ -78,6 +78,20 @@ int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, const uint8_t*
 int spg_pedersen_chain_batch(spg_ctx* ctx, const uint64_t* elems, size_t chain_len, uint64_t* out, uint8_t* status,
                              size_t n, int flags);
 
+/* ---- STARK-curve ECDSA (BASELINE.json configs[4]) ---------------------------------
+ * Replaces signature.py:217-260 verify(msg_hash, r, s, public_key).  All operands are 256-bit values as 4 x u64
+ * LE limbs.  pub_y_or_null = NULL: x-only keys (signature.py:229-238: y = smaller root, then -y).
+ * status[i]: 1 valid; 0 invalid (the reference returns False, incl. every assertion inside the three
+ * mimic_ec_mult_air calls, signature.py:251-257, and keys that are not on the curve as x-only keys);
+ *            2 a precondition is violated and the reference RAISES (signature.py:219, :225-227, :241), or a key
+ *              coordinate is not a field element. */
+int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
+                           const uint64_t* pub_x, const uint64_t* pub_y_or_null, uint8_t* status, size_t n, int flags);
+/* signature.py:99-110 private_key_to_ec_point_on_stark_curve / private_to_stark_key: (pub_x[i], pub_y[i]) =
+ * priv[i] * G (pub_y_or_null may be NULL); status 1 if priv is outside (0, n). */
+int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv, uint64_t* pub_x, uint64_t* pub_y_or_null,
+                                   uint8_t* status, size_t n, int flags);
+
 /* ---- NTT over the STARK prime (no reference symbol, field from signature.py:41-42) */
 /* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
  * inverse != 0 uses omega^-1 and scales by 2^-log_n. */

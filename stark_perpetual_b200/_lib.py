@@ -54,6 +54,8 @@ def _load():
             "spg_pedersen_chain_trace": (C.c_int, [vp, C.c_uint, C.c_uint, vp, vp, vp, C.c_int]),
             "spg_air_eval": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, vp, vp, vp, C.c_int]),
             "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
+            "spg_ecdsa_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_private_to_stark_key_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_set_stream": (C.c_int, [vp, vp]),
             "spg_stage_ms": (C.c_double, [vp, C.c_int]),
             "spg_lde": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, vp, vp, C.c_int]),
@@ -182,6 +184,31 @@ class Context:
         st = np.empty(n, dtype=np.uint8)
         self._check(self._lib.spg_pedersen_chain_batch(self._h, _ptr(e), chain_len, _ptr(out), _ptr(st), n, 0))
         return out, st
+
+    # ---- ECDSA ----
+    def ecdsa_verify(self, msg, r, s, pub_x, pub_y=None):
+        """All arguments (n, 4) uint64.  Returns status (n,) uint8: 1 valid, 0 invalid, 2 the reference raises."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in (msg, r, s, pub_x)]
+        n = arrs[0].shape[0]
+        assert all(a.shape[0] == n for a in arrs)
+        yp = None
+        if pub_y is not None:
+            pub_y = np.ascontiguousarray(pub_y, dtype=np.uint64).reshape(-1, 4)
+            assert pub_y.shape[0] == n
+            yp = _ptr(pub_y)
+        st = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.spg_ecdsa_verify_batch(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), _ptr(arrs[3]),
+                                                     yp, _ptr(st), n, 0))
+        return st
+
+    def private_to_stark_key(self, priv, want_y=False):
+        p = np.ascontiguousarray(priv, dtype=np.uint64).reshape(-1, 4)
+        out = np.empty_like(p)
+        outy = np.empty_like(p) if want_y else None
+        st = np.empty(p.shape[0], dtype=np.uint8)
+        self._check(self._lib.spg_private_to_stark_key_batch(self._h, _ptr(p), _ptr(out), _ptr(outy) if want_y else None,
+                                                             _ptr(st), p.shape[0], 0))
+        return (out, outy, st) if want_y else (out, st)
 
     # ---- NTT ----
     def ntt(self, data, log_n, inverse=False, order=NTT_NAT_TO_NAT):

@@ -1,0 +1,195 @@
+"""GPU-backed mirror of the reference's `starkware.crypto.signature.signature`
+(src/starkware/crypto/signature/signature.py): same names, same argument meaning, same exceptions.
+
+pedersen_hash (:296), verify (:217), private_to_stark_key (:109), get_y_coordinate-dependent x-only keys and
+sign (:137; the nonce derivation is host-side RFC 6979 as in :117-134, the curve multiplication k*G runs on
+the GPU) call libspg through stark_perpetual_b200; batched variants (`*_batch`) are what a service would use.
+There is no CPU fallback: without a CUDA device the first call raises SpgError.
+"""
+import hashlib
+import hmac
+import json
+import math
+import os
+from typing import Optional, Tuple, Union
+
+import stark_perpetual_b200 as _spg
+from stark_perpetual_b200._lib import ints_to_limbs, limbs_to_ints
+
+_P = json.load(open(os.path.join(os.path.dirname(_spg.__file__), "data", "curve_params.json")))
+FIELD_PRIME = int(_P["FIELD_PRIME"], 16)
+FIELD_GEN = _P["FIELD_GEN"]
+ALPHA = _P["ALPHA"]
+BETA = int(_P["BETA"], 16)
+EC_ORDER = int(_P["EC_ORDER"], 16)
+N_ELEMENT_BITS_ECDSA = math.floor(math.log(FIELD_PRIME, 2))
+assert N_ELEMENT_BITS_ECDSA == 251
+N_ELEMENT_BITS_HASH = FIELD_PRIME.bit_length()
+assert N_ELEMENT_BITS_HASH == 252
+SHIFT_POINT = tuple(int(v, 16) for v in _P["BASE_POINTS"]["SHIFT_POINT"])
+MINUS_SHIFT_POINT = (SHIFT_POINT[0], FIELD_PRIME - SHIFT_POINT[1])
+EC_GEN = tuple(int(v, 16) for v in _P["BASE_POINTS"]["EC_GEN"])
+
+ECPoint = Tuple[int, int]
+ECSignature = Tuple[int, int]
+
+
+class InvalidPublicKeyError(Exception):
+    def __init__(self):
+        super().__init__("Given x coordinate does not represent any point on the elliptic curve.")
+
+
+def _ctx():
+    return _spg.get_context(0)
+
+
+# ---------------------------------------------------------------------------------- Pedersen hash
+def pedersen_hash_batch(xs, ys):
+    """[pedersen_hash(x, y) for x, y in zip(xs, ys)] in one launch."""
+    for v in list(xs) + list(ys):
+        assert 0 <= v < FIELD_PRIME                                  # signature.py:307
+    out, st = _ctx().pedersen_hash2(ints_to_limbs(xs), ints_to_limbs(ys))
+    assert not (st == 1).any()
+    assert not (st == 2).any(), "Unhashable input."                  # signature.py:313
+    return limbs_to_ints(out)
+
+
+def pedersen_hash(*elements: int) -> int:
+    # signature.py:296-318; the shipped table supports at most two elements (:308-310)
+    assert len(elements) <= 2, "pedersen_params.json holds constant points for two elements only"
+    for x in elements:
+        assert 0 <= x < FIELD_PRIME
+    if len(elements) == 0:
+        return SHIFT_POINT[0]
+    out, st = _ctx().pedersen_chain(ints_to_limbs(list(elements)), len(elements))
+    assert st[0] != 1
+    assert st[0] != 2, "Unhashable input."
+    return limbs_to_ints(out)[0]
+
+
+# ---------------------------------------------------------------------------------- keys
+def private_key_to_ec_point_on_stark_curve(priv_key: int) -> ECPoint:
+    assert 0 < priv_key < EC_ORDER                                    # signature.py:105
+    x, y, st = _ctx().private_to_stark_key(ints_to_limbs([priv_key]), want_y=True)
+    assert st[0] == 0
+    return limbs_to_ints(x)[0], limbs_to_ints(y)[0]
+
+
+def private_to_stark_key(priv_key: int) -> int:
+    assert 0 < priv_key < EC_ORDER
+    out, st = _ctx().private_to_stark_key(ints_to_limbs([priv_key]))
+    assert st[0] == 0
+    return limbs_to_ints(out)[0]
+
+
+def private_to_stark_key_batch(priv_keys):
+    for k in priv_keys:
+        assert 0 < k < EC_ORDER
+    out, st = _ctx().private_to_stark_key(ints_to_limbs(priv_keys))
+    assert not st.any()
+    return limbs_to_ints(out)
+
+
+def inv_mod_curve_size(x: int) -> int:
+    return pow(x, -1, EC_ORDER)                                       # signature.py:113-114 (div_mod(1, x, n))
+
+
+# ---------------------------------------------------------------------------------- verify
+def verify_batch(msg_hashes, rs, ss, public_keys):
+    """public_keys: all ints (x-only) or all (x, y) tuples.  Returns a list of bool; raises AssertionError if the
+    reference would raise for any element (signature.py:219, :225-227, :241)."""
+    n = len(msg_hashes)
+    if n == 0:
+        return []
+    point = not isinstance(public_keys[0], int)
+    vals = list(msg_hashes) + list(rs) + list(ss)
+    keys_x = [k[0] if point else k for k in public_keys]
+    keys_y = [k[1] for k in public_keys] if point else None
+    for v in vals + keys_x + (keys_y or []):
+        assert 0 <= v < 2**256, "operand does not fit 256 bits"
+    st = _ctx().ecdsa_verify(ints_to_limbs(msg_hashes), ints_to_limbs(rs), ints_to_limbs(ss), ints_to_limbs(keys_x),
+                             ints_to_limbs(keys_y) if point else None)
+    assert not (st == 2).any(), "precondition violated (s, r, w or msg_hash out of range, or key not on curve)"
+    return [bool(v) for v in st]
+
+
+def verify(msg_hash: int, r: int, s: int, public_key: Union[int, ECPoint]) -> bool:
+    # signature.py:217-260 -- range assertions first, in the reference's order, with its messages
+    assert 1 <= s < EC_ORDER, "s = %s" % s
+    w = inv_mod_curve_size(s)
+    assert 1 <= r < 2**N_ELEMENT_BITS_ECDSA, "r = %s" % r
+    assert 1 <= w < 2**N_ELEMENT_BITS_ECDSA, "w = %s" % w
+    assert 0 <= msg_hash < 2**N_ELEMENT_BITS_ECDSA, "msg_hash = %s" % msg_hash
+    return verify_batch([msg_hash], [r], [s], [public_key])[0]
+
+
+# ---------------------------------------------------------------------------------- sign
+def _bits2int(data, qlen):
+    x = int.from_bytes(data, "big")
+    l = len(data) * 8
+    return x >> (l - qlen) if l > qlen else x
+
+
+def _rfc6979_generate_k(order, secexp, hash_func, data, extra_entropy=b""):
+    """RFC 6979 section 3.2 (what the reference gets from ecdsa.rfc6979.generate_k, signature.py:25,128)."""
+    qlen = order.bit_length()
+    holen = hash_func().digest_size
+    rolen = (qlen + 7) // 8
+    z1 = _bits2int(data, qlen)
+    z2 = z1 - order if z1 >= order else z1
+    bx = secexp.to_bytes(rolen, "big") + z2.to_bytes(rolen, "big") + extra_entropy
+    v, k = b"\x01" * holen, b"\x00" * holen
+    k = hmac.new(k, v + b"\x00" + bx, hash_func).digest()
+    v = hmac.new(k, v, hash_func).digest()
+    k = hmac.new(k, v + b"\x01" + bx, hash_func).digest()
+    v = hmac.new(k, v, hash_func).digest()
+    while True:
+        t = b""
+        while len(t) < rolen:
+            v = hmac.new(k, v, hash_func).digest()
+            t += v
+        secret = _bits2int(t, qlen)
+        if 1 <= secret < order:
+            return secret
+        k = hmac.new(k, v + b"\x00", hash_func).digest()
+        v = hmac.new(k, v, hash_func).digest()
+
+
+def generate_k_rfc6979(msg_hash: int, priv_key: int, seed: Optional[int] = None) -> int:
+    # signature.py:117-134
+    if 1 <= msg_hash.bit_length() % 8 <= 4 and msg_hash.bit_length() >= 248:
+        msg_hash *= 16
+    extra = b"" if seed is None else seed.to_bytes(math.ceil(seed.bit_length() / 8), "big")
+    return _rfc6979_generate_k(EC_ORDER, priv_key, hashlib.sha256,
+                               msg_hash.to_bytes(math.ceil(msg_hash.bit_length() / 8), "big"), extra_entropy=extra)
+
+
+def sign(msg_hash: int, priv_key: int, seed: Optional[int] = None) -> ECSignature:
+    # signature.py:137-173; x(k*G) on the GPU
+    assert 0 <= msg_hash < 2**N_ELEMENT_BITS_ECDSA, "Message not signable."
+    while True:
+        k = generate_k_rfc6979(msg_hash, priv_key, seed)
+        seed = 1 if seed is None else seed + 1
+        r = private_to_stark_key(k)
+        if not (1 <= r < 2**N_ELEMENT_BITS_ECDSA):
+            continue
+        if (msg_hash + r * priv_key) % EC_ORDER == 0:
+            continue
+        w = k * pow(msg_hash + r * priv_key, -1, EC_ORDER) % EC_ORDER
+        if not (1 <= w < 2**N_ELEMENT_BITS_ECDSA):
+            continue
+        return r, inv_mod_curve_size(w)
+
+
+def grind_key(key_seed: int, key_value_limit: int) -> int:
+    # signature.py:263-288 (host-side hashing only)
+    max_allowed = 2**256 - (2**256 % key_value_limit)
+
+    def nb(x):
+        return x.to_bytes(max(1, -(-x.bit_length() // 8)), "big")
+    index = 0
+    while True:
+        key = int(hashlib.sha256(nb(key_seed) + nb(index)).hexdigest(), 16)
+        if key < max_allowed:
+            return key % key_value_limit
+        index += 1

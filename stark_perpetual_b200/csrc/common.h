@@ -26,6 +26,9 @@ struct spg_ctx {
   Fp* const_points = nullptr;   // 506 x (x, y) Montgomery
   Fp* gen_doubles = nullptr;    // G * 2^t, t < 251, (x, y) Montgomery
   std::vector<Fp> h_const_points;   // host copy of const_points
+  std::vector<Fp> h_gen_doubles;    // host copy of gen_doubles
+  Fp* sqrt_tables = nullptr;        // ECDSA square-root tables: L[256], D[24][256], Dh[24][256]
+  std::vector<Fp> h_sqrt_tables;
   // scratch cache
   std::vector<void*> owned;
   bool own_stream = true;

@@ -35,10 +35,11 @@ int spg_curve_tables_init(spg_ctx* ctx) {
   ctx->h_const_points.assign((const Fp*)pts.data(), (const Fp*)pts.data() + 2 * pts.size());
   SPG_CUDA(cudaMalloc((void**)&ctx->const_points, pts.size() * sizeof(APoint)));
   SPG_CUDA(cudaMemcpy(ctx->const_points, pts.data(), pts.size() * sizeof(APoint), cudaMemcpyHostToDevice));
-  // doubling chain of the generator for ECDSA: G * 2^t, t < 251
-  std::vector<APoint> gd(SPG_ECDSA_BITS);
+  // doubling chain of the generator for ECDSA / key derivation: G * 2^t, t < 252
+  std::vector<APoint> gd(SPG_ECDSA_BITS + 1);
   APoint g = base(1);
-  for (int t = 0; t < SPG_ECDSA_BITS; t++) { gd[t] = g; g = ec_affine_double(g); }
+  for (int t = 0; t <= SPG_ECDSA_BITS; t++) { gd[t] = g; g = ec_affine_double(g); }
+  ctx->h_gen_doubles.assign((const Fp*)gd.data(), (const Fp*)gd.data() + 2 * gd.size());
   SPG_CUDA(cudaMalloc((void**)&ctx->gen_doubles, gd.size() * sizeof(APoint)));
   SPG_CUDA(cudaMemcpy(ctx->gen_doubles, gd.data(), gd.size() * sizeof(APoint), cudaMemcpyHostToDevice));
   return SPG_OK;

@@ -1,0 +1,160 @@
+// Batched STARK-curve ECDSA verification and key derivation (BASELINE.json
+// configs[4]).  Reference: src/starkware/crypto/signature/signature.py:217-260 (verify), :104-110
+// (private_to_stark_key).  One thread per signature; per-signature code in ecdsa.cuh.
+#include "common.h"
+#include "curve_params.inc"
+#include "ecdsa.cuh"
+
+static int ensure_ecdsa_tables(spg_ctx* ctx) {
+  if (ctx->sqrt_tables) return SPG_OK;
+  // c = 3^q, q = 2^59 + 17, generates the subgroup of order 2^192
+  uint64_t three[4] = {3, 0, 0, 0};
+  const Fp g = spg_host_from_u64(three);
+  const Fp c = fp_pow_u64(g, (1ull << 59) + 17), ci = fp_inv(c);
+  std::vector<Fp> tab(256 + 2 * 24 * 256, fp_one());
+  Fp cl = c;
+  for (int k = 0; k < 184; k++) cl = fp_sqr(cl);
+  for (int k = 1; k < 256; k++) tab[k] = fp_mul(tab[k - 1], cl);
+  Fp* D = tab.data() + 256;
+  Fp* Dh = D + 24 * 256;
+  Fp base = ci, base_h = ci;   // base = ci^(2^(8i)); base_h = ci^(2^(8i-1)) for i >= 1
+  for (int i = 0; i < 24; i++) {
+    for (int k = 1; k < 256; k++) D[i * 256 + k] = fp_mul(D[i * 256 + k - 1], base);
+    if (i == 0) {
+      for (int k = 2; k < 256; k += 2) Dh[k] = fp_mul(Dh[k - 2], ci);       // ci^(k/2), even k only
+    } else {
+      for (int k = 1; k < 256; k++) Dh[i * 256 + k] = fp_mul(Dh[i * 256 + k - 1], base_h);
+    }
+    base_h = base;
+    for (int k = 0; k < 7; k++) base_h = fp_sqr(base_h);                     // ci^(2^(8i+7)) = ci^(2^(8(i+1)-1))
+    for (int k = 0; k < 8; k++) base = fp_sqr(base);
+  }
+  ctx->h_sqrt_tables = tab;
+  SPG_CUDA(cudaMalloc((void**)&ctx->sqrt_tables, tab.size() * sizeof(Fp)));
+  SPG_CUDA(cudaMemcpy(ctx->sqrt_tables, tab.data(), tab.size() * sizeof(Fp), cudaMemcpyHostToDevice));
+  return SPG_OK;
+}
+
+static EcdsaTables make_tables(spg_ctx* ctx, bool device) {
+  EcdsaTables T;
+  const Fp* cp = ctx->h_const_points.data();
+  T.shift.x = cp[0]; T.shift.y = cp[1];
+  T.minus_shift.x = cp[0]; T.minus_shift.y = fp_neg(cp[1]);
+  T.beta = spg_host_from_u64(SPG_BETA);
+  // 2^512 mod n
+  static const uint32_t r2[8] = {0xea1c688du, 0x6021b3f1u, 0x14ce60b9u, 0x509cf64du, 0xf78bbabbu, 0xbaf0ab4cu, 0x2333766eu, 0x07d9e57cu};
+  for (int i = 0; i < 8; i++) T.r2_n.v[i] = r2[i];
+  T.ninv = SPG_N_INV32;
+  if (device) {
+    T.gen_doubles = (const APoint*)ctx->gen_doubles;
+    T.sq_L = ctx->sqrt_tables; T.sq_D = ctx->sqrt_tables + 256; T.sq_Dh = ctx->sqrt_tables + 256 + 24 * 256;
+  } else {
+    T.gen_doubles = (const APoint*)ctx->h_gen_doubles.data();
+    T.sq_L = ctx->h_sqrt_tables.data(); T.sq_D = T.sq_L + 256; T.sq_Dh = T.sq_D + 24 * 256;
+  }
+  return T;
+}
+
+__device__ __forceinline__ void load8(const uint64_t* src, uint32_t (&x)[8]) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  const uint4 lo = s[0], hi = s[1];
+  x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
+}
+
+__global__ void __launch_bounds__(64) k_ecdsa_verify(const uint64_t* __restrict__ msg, const uint64_t* __restrict__ r,
+                                                     const uint64_t* __restrict__ s, const uint64_t* __restrict__ px,
+                                                     const uint64_t* __restrict__ py, uint8_t* __restrict__ status,
+                                                     size_t n, EcdsaTables T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t m[8], rr[8], ss[8], x[8], y[8];
+  load8(msg + 4 * i, m); load8(r + 4 * i, rr); load8(s + 4 * i, ss); load8(px + 4 * i, x);
+  if (py) load8(py + 4 * i, y);
+  status[i] = (uint8_t)ecdsa_verify_one(m, rr, ss, x, py ? y : nullptr, T);
+}
+
+// status: 0 ok, 1 key outside (0, n)  (signature.py:105 asserts 0 < priv_key < EC_ORDER)
+__global__ void __launch_bounds__(128) k_private_to_public(const uint64_t* __restrict__ priv, uint64_t* __restrict__ pub_x,
+                                                           uint64_t* __restrict__ pub_y, uint8_t* __restrict__ status,
+                                                           size_t n, EcdsaTables T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[8];
+  load8(priv + 4 * i, k);
+  Fp res = fp_zero(), resy = fp_zero();
+  uint8_t st = 0;
+  if (u256_is_zero(k) || fn_geq_n(k)) st = 1;
+  else { const APoint q = gen_mult(k, T); res = fp_from_mont(q.x); resy = fp_from_mont(q.y); }
+  uint4* o = reinterpret_cast<uint4*>(pub_x + 4 * i);
+  o[0] = make_uint4(res.v[0], res.v[1], res.v[2], res.v[3]);
+  o[1] = make_uint4(res.v[4], res.v[5], res.v[6], res.v[7]);
+  if (pub_y) {
+    o = reinterpret_cast<uint4*>(pub_y + 4 * i);
+    o[0] = make_uint4(resy.v[0], resy.v[1], resy.v[2], resy.v[3]);
+    o[1] = make_uint4(resy.v[4], resy.v[5], resy.v[6], resy.v[7]);
+  }
+  status[i] = st;
+}
+
+extern "C" int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
+                                      const uint64_t* pub_x, const uint64_t* pub_y_or_null, uint8_t* status, size_t n,
+                                      int flags) {
+  SPG_ARG(ctx && msg && r && s && pub_x && status, "spg_ecdsa_verify_batch: null");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  int rc = ensure_ecdsa_tables(ctx);
+  if (rc) return rc;
+  const uint64_t *dm = msg, *dr = r, *ds = s, *dx = pub_x, *dy = pub_y_or_null;
+  uint8_t* dst = status;
+  DevBuf b[5], bs;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    const uint64_t* src[5] = {msg, r, s, pub_x, pub_y_or_null};
+    const uint64_t** dstp[5] = {&dm, &dr, &ds, &dx, &dy};
+    for (int k = 0; k < 5; k++) {
+      if (!src[k]) continue;
+      SPG_CUDA(b[k].alloc(n * 32));
+      SPG_CUDA(cudaMemcpyAsync(b[k].p, src[k], n * 32, cudaMemcpyHostToDevice, ctx->stream));
+      *dstp[k] = b[k].as<uint64_t>();
+    }
+    SPG_CUDA(bs.alloc(n));
+    dst = bs.as<uint8_t>();
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_ecdsa_verify<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(dm, dr, ds, dx, dy, dst, n, make_tables(ctx, true));
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS)) SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if ((flags & SPG_NO_SYNC) && (flags & SPG_DEVICE_PTRS)) return SPG_OK;
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}
+
+extern "C" int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv, uint64_t* pub_x, uint64_t* pub_y_or_null,
+                                              uint8_t* status, size_t n, int flags) {
+  SPG_ARG(ctx && priv && pub_x && status, "spg_private_to_stark_key_batch: null");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  int rc = ensure_ecdsa_tables(ctx);
+  if (rc) return rc;
+  const uint64_t* dp = priv; uint64_t* dx = pub_x; uint64_t* dy = pub_y_or_null; uint8_t* dst = status;
+  DevBuf bp, bx, by, bs;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(bp.alloc(n * 32)); SPG_CUDA(bx.alloc(n * 32)); SPG_CUDA(bs.alloc(n));
+    if (pub_y_or_null) { SPG_CUDA(by.alloc(n * 32)); dy = by.as<uint64_t>(); }
+    SPG_CUDA(cudaMemcpyAsync(bp.p, priv, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    dp = bp.as<uint64_t>(); dx = bx.as<uint64_t>(); dst = bs.as<uint8_t>();
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_private_to_public<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(dp, dx, dy, dst, n, make_tables(ctx, true));
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(cudaMemcpyAsync(pub_x, dx, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pub_y_or_null) SPG_CUDA(cudaMemcpyAsync(pub_y_or_null, dy, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}

@@ -1,0 +1,126 @@
+"""GPU parity: batched ECDSA verification / key derivation / the reference-compatible signature module against
+golden vectors generated from the reference (signature.py:217-260) and the Python oracle -- exact statuses."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ecdsa as oecdsa
+from oracle.params import EC_ORDER, FIELD_PRIME as P
+from stark_perpetual_b200._lib import ints_to_limbs, limbs_to_ints
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def compat():
+    sys.path.insert(0, os.path.join(ROOT, "stark_perpetual_b200", "compat"))
+    from starkware.crypto.signature import signature
+    return signature
+
+
+def test_verify_golden_all_statuses(ctx, golden):
+    xonly = [v for v in golden["verify"] if isinstance(v[3], str)]
+    point = [v for v in golden["verify"] if not isinstance(v[3], str)]
+    st = ctx.ecdsa_verify(ints_to_limbs([int(v[0], 16) for v in xonly]), ints_to_limbs([int(v[1], 16) for v in xonly]),
+                          ints_to_limbs([int(v[2], 16) for v in xonly]), ints_to_limbs([int(v[3], 16) for v in xonly]))
+    assert list(st) == [v[4] for v in xonly], [v[5] for v in xonly]
+    st = ctx.ecdsa_verify(ints_to_limbs([int(v[0], 16) for v in point]), ints_to_limbs([int(v[1], 16) for v in point]),
+                          ints_to_limbs([int(v[2], 16) for v in point]), ints_to_limbs([int(v[3][0], 16) for v in point]),
+                          ints_to_limbs([int(v[3][1], 16) for v in point]))
+    assert list(st) == [v[4] for v in point], [v[5] for v in point]
+
+
+def test_private_to_public_golden(ctx, golden):
+    privs = [int(a, 16) for a, _b in golden["keys"]]
+    out, st = ctx.private_to_stark_key(ints_to_limbs(privs))
+    assert not st.any()
+    assert limbs_to_ints(out) == [int(b, 16) for _a, b in golden["keys"]]
+    # large keys (bit 251 set) and range statuses
+    ks = [EC_ORDER - 1, EC_ORDER - 2, 2**251, 1, 2]
+    x, y, st = ctx.private_to_stark_key(ints_to_limbs(ks), want_y=True)
+    assert not st.any()
+    for k, gx, gy in zip(ks, limbs_to_ints(x), limbs_to_ints(y)):
+        assert (gx, gy) == oecdsa.private_key_to_ec_point_on_stark_curve(k)
+    _o, st = ctx.private_to_stark_key(ints_to_limbs([0, EC_ORDER, 2**256 - 1]))
+    assert list(st) == [1, 1, 1]
+
+
+def make_orders(n, n_keys, seed, corrupt_every=0):
+    rng = random.Random(seed)
+    privs = [rng.randrange(1, EC_ORDER) for _ in range(n_keys)]
+    pubs = [oecdsa.private_to_stark_key(k) for k in privs]
+    msgs, rs, ss, keys, want = [], [], [], [], []
+    for i in range(n):
+        k = i % n_keys
+        m = rng.randrange(2**251)
+        r, s = oecdsa.sign(m, privs[k])
+        ok = True
+        if corrupt_every and i % corrupt_every == 0:
+            which = rng.randrange(4)
+            if which == 0:
+                m ^= 1 << rng.randrange(250)
+            elif which == 1:
+                r ^= 1 << rng.randrange(250)
+                r = r or 1
+            elif which == 2:
+                s = (s ^ (1 << rng.randrange(250))) % EC_ORDER or 1
+            else:
+                k = (k + 1) % n_keys
+            ok = False
+        msgs.append(m); rs.append(r); ss.append(s); keys.append(pubs[k]); want.append(ok)
+    return msgs, rs, ss, keys, want
+
+
+def test_batch_verify_synthetic_orders(ctx):
+    """Config-5 shape at a size the Python oracle signs in seconds: 96 signatures, 8 keys, every 5th corrupted;
+    statuses equal the oracle's verify on every element."""
+    msgs, rs, ss, keys, want = make_orders(96, 8, 1005, corrupt_every=5)
+    st = ctx.ecdsa_verify(ints_to_limbs(msgs), ints_to_limbs(rs), ints_to_limbs(ss), ints_to_limbs(keys))
+    got = [int(v) for v in st]
+    for i in range(96):
+        try:
+            ref = 1 if oecdsa.verify(msgs[i], rs[i], ss[i], keys[i]) else 0
+        except AssertionError:
+            ref = 2
+        assert got[i] == ref, i
+    assert sum(got) >= 70
+
+
+def test_batch_verify_large_replicated(ctx):
+    """65536 signatures (BASELINE.json configs[4] size) built by replicating 64 distinct ones: every copy must
+    get the status of its original (determinism across the whole grid)."""
+    msgs, rs, ss, keys, want = make_orders(64, 4, 77, corrupt_every=7)
+    reps = 1024
+    st = ctx.ecdsa_verify(np.tile(ints_to_limbs(msgs), (reps, 1)), np.tile(ints_to_limbs(rs), (reps, 1)),
+                          np.tile(ints_to_limbs(ss), (reps, 1)), np.tile(ints_to_limbs(keys), (reps, 1)))
+    base = [1 if w else 0 for w in want]
+    assert st.reshape(reps, 64).tolist() == [base] * reps
+
+
+def test_compat_signature_module(ctx, golden):
+    sig = compat()
+    # Pedersen KATs of the reference (signature_test_data.json:190-201 via the golden file)
+    for a, b, o, tag in golden["pedersen"][:6]:
+        assert sig.pedersen_hash(int(a, 16), int(b, 16)) == int(o, 16)
+    with pytest.raises(AssertionError):
+        sig.pedersen_hash(P, 1)
+    # deterministic signing: the 4 JS RFC 6979 KATs (signature.spec.js:96-137)
+    for mh, priv, er, es in golden["sign_js_kat"]:
+        assert sig.sign(int(mh, 16), int(priv, 16)) == (int(er, 16), int(es, 16))
+    for msg, priv, r, s in golden["sign"][:4]:
+        assert sig.sign(int(msg, 16), int(priv, 16)) == (int(r, 16), int(s, 16))
+        pub = sig.private_to_stark_key(int(priv, 16))
+        assert sig.verify(int(msg, 16), int(r, 16), int(s, 16), pub)
+        assert sig.verify(int(msg, 16), int(r, 16), int(s, 16), sig.private_key_to_ec_point_on_stark_curve(int(priv, 16)))
+        assert not sig.verify(int(msg, 16) ^ 1, int(r, 16), int(s, 16), pub)
+    # exceptions exactly where the reference raises
+    for msg, r, s, pub, res, tag in golden["verify"]:
+        pk = int(pub, 16) if isinstance(pub, str) else (int(pub[0], 16), int(pub[1], 16))
+        if res == 2:
+            with pytest.raises(AssertionError):
+                sig.verify(int(msg, 16), int(r, 16), int(s, 16), pk)
+        else:
+            assert sig.verify(int(msg, 16), int(r, 16), int(s, 16), pk) == bool(res), tag

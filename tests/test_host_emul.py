@@ -46,3 +46,25 @@ def test_emulated_pedersen_vs_reference_golden(golden):
         h, st = line.split()
         assert st == "0" and int(h, 16) == int(o, 16), (a, b)
     assert out[len(vec)].split()[1] == "1"
+
+
+def test_emulated_ecdsa_vs_reference_golden(golden):
+    """The per-thread ECDSA code of the CUDA kernel (csrc/ecdsa.cuh: mod-n inversion, square root, the three
+    mimic_ec_mult_air loops with every assertion) run on the host against all 65 golden verify vectors
+    (True / False / raises) and the 30 reference key pairs."""
+    exe = _build("emul_ecdsa")
+    lines = []
+    for msg, r, s, pub, _res, _tag in golden["verify"]:
+        if isinstance(pub, str):
+            lines.append("%s %s %s %s -" % (msg[2:], r[2:], s[2:], pub[2:]))
+        else:
+            lines.append("%s %s %s %s %s" % (msg[2:], r[2:], s[2:], pub[0][2:], pub[1][2:]))
+    for priv, _pub in golden["keys"]:
+        lines.append("K %s" % priv[2:])
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout.split()
+    nv = len(golden["verify"])
+    assert len(out) == nv + len(golden["keys"])
+    for v, o in zip(golden["verify"], out[:nv]):
+        assert int(o) == v[4], v[5]
+    for (_priv, pub), o in zip(golden["keys"], out[nv:]):
+        assert int(o, 16) == int(pub, 16)
