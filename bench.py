@@ -194,14 +194,27 @@ def main():
     from stark_perpetual_b200._lib import limbs_to_ints
     x0 = limbs_to_ints(x0_limbs)
     trace_host = ctx.pedersen_chain_trace(log_n, cfg["chain_log"], x0, ys_limbs)          # (25 N, 4) uint64
-    pinned = torch.from_numpy(trace_host.view(np.int64)).pin_memory()
+    # every rank pins and uploads only its own block of columns (world = 1: the whole trace)
+    c0, c1 = pv.column_block()
+    tr3 = trace_host.reshape(25, n, 4)
+    outs = limbs_to_ints(tr3[[5 * l for l in range(5)], n - 1])
+    my = tr3[c0:c1] if c1 > c0 else tr3[:1]
+    pinned = torch.from_numpy(np.ascontiguousarray(my).view(np.int64)).pin_memory()
     trace = torch.empty_like(pinned, device=dev)
     trace.copy_(pinned)
     torch.cuda.synchronize()
     launches_before = ctx.launch_count
 
     def step():
-        return pv.prove_device(trace.data_ptr(), log_n, cfg["chain_log"], x0, cfg["n_queries"])
+        if world == 1:
+            return pv.prove_device(trace.data_ptr(), log_n, cfg["chain_log"], x0, cfg["n_queries"])
+        return pv.prove_sharded_device(trace, log_n, cfg["chain_log"], x0, outs, cfg["n_queries"])
+
+    def step_e2e():
+        if world == 1:
+            return pv.prove_host(pinned.numpy().view(np.uint64), log_n, cfg["chain_log"], x0, cfg["n_queries"])
+        trace.copy_(pinned, non_blocking=True)
+        return pv.prove_sharded_device(trace, log_n, cfg["chain_log"], x0, outs, cfg["n_queries"])
 
     def barrier():
         if world > 1:
@@ -236,17 +249,17 @@ def main():
     # ---- e2e: host trace through the C-ABI (pinned host memory): H2D + proof + D2H of the proof bytes
     e2e = None
     if not args.no_e2e:
-        pv.prove_host(pinned.numpy().view(np.uint64), log_n, cfg["chain_log"], x0, cfg["n_queries"])
+        step_e2e()
         barrier()
         e0.record(stream)
         for _ in range(args.steps):
-            pr2 = pv.prove_host(pinned.numpy().view(np.uint64), log_n, cfg["chain_log"], x0, cfg["n_queries"])
+            pr2 = step_e2e()
         e1.record(stream)
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"ms_per_step": float(t.item()) / args.steps, "h2d_bytes_per_step": 25 * n * 32,
+        e2e = {"ms_per_step": float(t.item()) / args.steps, "h2d_bytes_per_step": 25 * n * 32,   # summed over ranks
                "d2h_bytes_per_step": len(pr2) if pr2 is not None else 0}
 
     if rank == 0:

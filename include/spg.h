@@ -32,6 +32,8 @@ typedef struct spg_ctx spg_ctx;
 #define SPG_E_PROOF (-5)     /* prover could not build a proof (e.g. trace does not satisfy the AIR) */
 
 #define SPG_DEVICE_PTRS 1    /* flags: buffers are device pointers */
+#define SPG_MONT_OUT 4       /* flags (spg_lde_coeffs): additionally multiply by R = 2^256, so that a canonical trace
+                                yields Montgomery-form coefficients / evaluations (what the prover stages consume) */
 #define SPG_NO_SYNC 2        /* flags (with SPG_DEVICE_PTRS): enqueue on the context stream and return; the
                                 caller synchronises (spg_synchronize / its own events) */
 
@@ -140,6 +142,24 @@ int spg_air_eval(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned c
  * split, 3 chunk LDE, 4 chunk Merkle, 5 out-of-domain evaluation, 6 DEEP quotient, 7 FRI, 8 query openings. */
 int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
               unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
+
+/* ---- stage-level entry points for the multi-GPU host driver (device pointers; DESIGN.md "Multi-GPU") ----------
+ * A GPU owns n_cosets consecutive cosets starting at first_coset; its tables hold exactly those cosets,
+ * [n_cosets][n_cols][rows].  Scalars (alpha, z, gamma, beta, x0, outs, oods) are canonical felts in host memory.
+ * Same kernels as spg_prove; with first_coset = 0, n_cosets = 8 they reproduce its stages one by one. */
+int spg_stage_merkle(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, int n_cosets, uint8_t* tree_out);
+int spg_stage_air(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* t_lde, int first_coset, int jj0,
+                  int n_even, const uint64_t* x0, const uint64_t* outs, const uint64_t* alpha, uint64_t* cp_out);
+int spg_stage_cp_split(spg_ctx* ctx, unsigned log_n, const uint64_t* cp, int jj0, int n_even, uint64_t* hev);
+int spg_stage_poly_eval(spg_ctx* ctx, unsigned log_n, const uint64_t* const* cols, const int* pt_idx, int n_items,
+                        const uint64_t* pts, int n_pts, uint64_t* out);
+int spg_stage_deep(spg_ctx* ctx, unsigned log_n, const uint64_t* t_lde, const uint64_t* h_lde, int first_coset,
+                   int n_cosets, const uint64_t* z, const uint64_t* gamma, const uint64_t* oods, uint64_t* inv_scratch,
+                   uint64_t* out);
+int spg_stage_fri_fold(spg_ctx* ctx, const uint64_t* in, unsigned log_rows, int first_coset, int n_cosets,
+                       const uint64_t* beta, int layer_index, uint64_t* out);
+int spg_stage_open(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, int n_cosets, const uint8_t* tree,
+                   const uint32_t* idx, int count, uint8_t* leaves_out, uint8_t* paths_out);
 
 #ifdef __cplusplus
 }

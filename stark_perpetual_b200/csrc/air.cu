@@ -111,18 +111,18 @@ struct AirEvalConsts {
 __global__ void __launch_bounds__(128) k_air_eval(unsigned log_n, unsigned log_seg, const Fp* __restrict__ t_lde,
                                                   const AirEvalConsts* __restrict__ K, const Fp* __restrict__ izt,
                                                   const Fp* __restrict__ plde, const Fp* __restrict__ ilast,
-                                                  Fp* __restrict__ cp) {
+                                                  Fp* __restrict__ cp, int first_coset, int jj0, int n_even) {
   const size_t n = (size_t)1 << log_n, seg = (size_t)1 << log_seg;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 4 * n) return;
-  const size_t jj = idx >> log_n, i = idx & (n - 1), j = 2 * jj;
+  if (idx >= (size_t)n_even * n) return;
+  const size_t jj = (idx >> log_n) + jj0, i = idx & (n - 1), j = 2 * jj;
   const size_t in = (i + 1) & (n - 1);
   const Fp px = plde[(j * 2 + 0) * 512 + (i & 511)], py = plde[(j * 2 + 1) * 512 + (i & 511)];
   const Fp one = fp_one();
   // accumulators per zerofier group
   Fp a_step = fp_zero(), a_act = fp_zero(), a_pad = fp_zero(), a_mid = fp_zero(), a_link = fp_zero(),
      a_inst = fp_zero(), a_seg = fp_zero(), a_last = fp_zero();
-  const Fp* base = t_lde + (j * SPG_AIR_COLS << log_n);
+  const Fp* base = t_lde + ((j - first_coset) * SPG_AIR_COLS << log_n);
 #pragma unroll 1
   for (int l = 0; l < SPG_AIR_LANES; l++) {
     const Fp* c0 = base + ((size_t)(5 * l) << log_n);
@@ -163,12 +163,14 @@ __global__ void __launch_bounds__(128) k_air_eval(unsigned log_n, unsigned log_s
   acc = fp_add(acc, fp_mul(a_link, izt[4 * stride + zi]));
   acc = fp_add(acc, fp_mul(a_inst, izt[5 * stride + zi]));
   acc = fp_add(acc, fp_mul(a_seg, izt[6 * stride + zi]));
-  acc = fp_add(acc, fp_mul(a_last, ilast[idx]));
+  acc = fp_add(acc, fp_mul(a_last, ilast[(jj << log_n) + i]));
   cp[idx] = fp_reduce(acc);
 }
 
 int spg_air_eval_device(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const Fp* t_lde, const AirPublic& pub,
-                        const Fp* h_alpha_pows, Fp* cp) {
+                        const Fp* h_alpha_pows, Fp* cp, int first_coset, int jj0, int n_even) {
+  if (n_even <= 0) return SPG_OK;
+  SPG_ARG(2 * jj0 >= first_coset && jj0 + n_even <= 4, "air eval: coset range");
   SPG_ARG(log_n >= 9 && log_n + SPG_LOG_BLOWUP <= SPG_UNI_LOG && 9 + chain_log <= log_n, "air eval: size");
   int rc = ensure_air_tables(ctx, log_n, chain_log);
   if (rc) return rc;
@@ -180,9 +182,10 @@ int spg_air_eval_device(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const 
   SPG_CUDA(spg_scratch(ctx, 7, sizeof(AirEvalConsts), &dk));
   SPG_CUDA(cudaMemcpyAsync(dk, &K, sizeof(K), cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));   // K is a stack object
-  const size_t total = (size_t)4 << log_n;
+  const size_t total = (size_t)n_even << log_n;
   k_air_eval<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(log_n, 9 + chain_log, t_lde, (const AirEvalConsts*)dk,
-                                                                      ctx->air_izt, ctx->air_plde, ctx->air_ilast, cp);
+                                                                      ctx->air_izt, ctx->air_plde, ctx->air_ilast, cp,
+                                                                      first_coset, jj0, n_even);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
@@ -192,12 +195,12 @@ int spg_air_eval_device(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const 
 //   H_m(x^4) x^m = 1/4 sum_k w_4^(-m k) CP(x w_4^k),  and  x w_4^k  is row i + k N/4 of the same coset.
 __global__ void __launch_bounds__(256) k_cp_split(unsigned log_n, const Fp* __restrict__ cp, Fp* __restrict__ hev, Fp ginv,
                                                   Fp inv4, Fp iota_inv, const Fp* __restrict__ uniA,
-                                                  const Fp* __restrict__ uniB) {
+                                                  const Fp* __restrict__ uniB, int jj0, int n_even) {
   const size_t n = (size_t)1 << log_n, q = n >> 2;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const size_t jj = idx / q, ip = idx - jj * q;
-  const Fp* p = cp + (jj << log_n) + ip;
+  if (idx >= (size_t)n_even * q) return;
+  const size_t e_loc = idx / q, ip = idx - e_loc * q, jj = e_loc + jj0;
+  const Fp* p = cp + (e_loc << log_n) + ip;
   const Fp v0 = p[0], v1 = p[q], v2 = p[2 * q], v3 = p[3 * q];
   const Fp t0 = fp_add(v0, v2), t1 = fp_sub(v0, v2), t2 = fp_add(v1, v3), t3 = fp_mul(fp_sub(v1, v3), iota_inv);
   const Fp s0 = fp_add(t0, t2), s2 = fp_sub(t0, t2), s1 = fp_add(t1, t3), s3 = fp_sub(t1, t3);
@@ -212,11 +215,13 @@ __global__ void __launch_bounds__(256) k_cp_split(unsigned log_n, const Fp* __re
   hev[3 * n + pos] = fp_reduce(fp_mul(fp_mul(s3, inv4), xi3));
 }
 
-int spg_cp_split_device(spg_ctx* ctx, unsigned log_n, const Fp* cp, Fp* hev) {
+int spg_cp_split_device(spg_ctx* ctx, unsigned log_n, const Fp* cp, Fp* hev, int jj0, int n_even) {
+  if (n_even <= 0) return SPG_OK;
   const Fp ginv = fp_inv(h_from_small(3)), inv4 = fp_inv(h_from_small(4));
   const Fp iota_inv = fp_inv(spg_host_root_of_unity(2));
-  const size_t n = (size_t)1 << log_n;
-  k_cp_split<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(log_n, cp, hev, ginv, inv4, iota_inv, ctx->uniA, ctx->uniB);
+  const size_t total = ((size_t)1 << log_n) / 4 * n_even;
+  k_cp_split<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, cp, hev, ginv, inv4, iota_inv, ctx->uniA,
+                                                                        ctx->uniB, jj0, n_even);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }

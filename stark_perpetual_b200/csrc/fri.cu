@@ -56,10 +56,10 @@ int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int 
 // ------------------------------------------------------------------ DEEP quotient
 __global__ void __launch_bounds__(256) k_deep(unsigned log_n, const Fp* __restrict__ t_lde, const Fp* __restrict__ h_lde,
                                               const Fp* __restrict__ inv3, const Fp* __restrict__ gamma,
-                                              const Fp* __restrict__ K, Fp* __restrict__ out) {
+                                              const Fp* __restrict__ K, Fp* __restrict__ out, int n_cosets) {
   const size_t n = (size_t)1 << log_n;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 8 * n) return;
+  if (idx >= (size_t)n_cosets * n) return;
   const size_t j = idx >> log_n, i = idx & (n - 1);
   Fp a = fp_zero(), b = fp_zero(), c = fp_zero();
   const Fp* tp = t_lde + (j * SPG_AIR_COLS << log_n) + i;
@@ -73,15 +73,15 @@ __global__ void __launch_bounds__(256) k_deep(unsigned log_n, const Fp* __restri
 #pragma unroll
   for (int m = 0; m < 4; m++) c = fp_add(c, fp_mul(hp[(size_t)m << log_n], gamma[2 * SPG_AIR_COLS + m]));
   a = fp_sub(a, K[0]); b = fp_sub(b, K[1]); c = fp_sub(c, K[2]);
-  const Fp i1 = inv3[idx], i2 = inv3[idx + 8 * n], i3 = inv3[idx + 16 * n];
+  const Fp i1 = inv3[idx], i2 = inv3[idx + (size_t)n_cosets * n], i3 = inv3[idx + 2 * (size_t)n_cosets * n];
   Fp q = fp_add(fp_add(fp_mul(a, i1), fp_mul(b, i2)), fp_mul(c, i3));
   out[idx] = fp_reduce(q);
 }
 
 int spg_deep_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, const Fp* inv3, const Fp* d_gamma,
-                    const Fp* d_K, Fp* out) {
-  const size_t total = (size_t)8 << log_n;
-  k_deep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_lde, h_lde, inv3, d_gamma, d_K, out);
+                    const Fp* d_K, Fp* out, int n_cosets) {
+  const size_t total = (size_t)n_cosets << log_n;
+  k_deep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_lde, h_lde, inv3, d_gamma, d_K, out, n_cosets);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
@@ -95,13 +95,13 @@ struct FoldConsts {
 
 __global__ void __launch_bounds__(256) k_fri_fold8(const Fp* __restrict__ in, unsigned log_rows, FoldConsts K,
                                                    Fp* __restrict__ out, const Fp* __restrict__ uniA,
-                                                   const Fp* __restrict__ uniB) {
+                                                   const Fp* __restrict__ uniB, int first_coset, int n_cosets) {
   const unsigned log_g = log_rows - 3;
   const size_t g = (size_t)1 << log_g;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 8 * g) return;
-  const size_t j = idx >> log_g, ip = idx & (g - 1);
-  const Fp* p = in + (j << log_rows) + ip;
+  if (idx >= (size_t)n_cosets * g) return;
+  const size_t jl = idx >> log_g, ip = idx & (g - 1), j = jl + first_coset;
+  const Fp* p = in + (jl << log_rows) + ip;
   Fp v[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) v[k] = p[(size_t)k << log_g];
@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(256) k_fri_fold8(const Fp* __restrict__ in, un
   out[idx] = fp_reduce(fp_mul(acc, K.inv8));
 }
 
-int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp& beta_over_g, Fp* out) {
+int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp& beta_over_g, Fp* out, int first_coset,
+                         int n_cosets) {
   SPG_ARG(log_rows >= 3 && log_rows + SPG_LOG_BLOWUP <= SPG_UNI_LOG, "fri fold: size");
   FoldConsts K;
   const Fp z = spg_host_root_of_unity(3), zi = fp_inv(z);
@@ -138,8 +139,9 @@ int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp
   uint64_t eight[4] = {8, 0, 0, 0};
   K.inv8 = fp_inv(spg_host_from_u64(eight));
   K.bg = beta_over_g;
-  const size_t total = (size_t)1 << log_rows;   // 8 * rows/8 outputs
-  k_fri_fold8<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in, log_rows, K, out, ctx->uniA, ctx->uniB);
+  const size_t total = ((size_t)1 << (log_rows - 3)) * n_cosets;
+  k_fri_fold8<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in, log_rows, K, out, ctx->uniA, ctx->uniB,
+                                                                         first_coset, n_cosets);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }

@@ -109,7 +109,7 @@ extern "C" int spg_lde_coeffs(spg_ctx* ctx, const uint64_t* trace, unsigned log_
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n_cols == 0) return SPG_OK;
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = spg_lde_coeffs_device(ctx, (const Fp*)trace, log_n, n_cols, coset_offset, (Fp*)coeffs);
+  int rc = spg_lde_coeffs_device(ctx, (const Fp*)trace, log_n, n_cols, coset_offset, (Fp*)coeffs, (flags & SPG_MONT_OUT) ? 1 : 0);
   if (rc) return rc;
   return finish(ctx, flags);
 }

@@ -9,9 +9,9 @@
 #include "common.h"
 
 __global__ void __launch_bounds__(128) k_merkle_leaves(const Fp* __restrict__ table, int ncols, size_t rows,
-                                                       uint32_t* __restrict__ out) {
+                                                       size_t n_leaves, uint32_t* __restrict__ out) {
   const size_t leaf = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (leaf >= rows) return;
+  if (leaf >= n_leaves) return;
   const size_t g = rows >> 3;
   const size_t j = leaf / g, ip = leaf - j * g;
   const Fp* base = table + j * (size_t)ncols * rows + ip;
@@ -49,13 +49,16 @@ __global__ void __launch_bounds__(128) k_merkle_nodes(const uint32_t* __restrict
   o[1] = make_uint4(s.h[4], s.h[5], s.h[6], s.h[7]);
 }
 
-// tree: `rows` leaves followed by rows/2, rows/4, ... 1 nodes: 2*rows - 1 digests of 32 bytes.
-// Level l (0 = leaves) starts at digest offset  2*rows - (2*rows >> l).
-int spg_merkle_build_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows, uint32_t* tree) {
+// tree over L = n_cosets * rows / 8 leaves (the table holds n_cosets consecutive cosets; 8 = the whole table,
+// fewer = the sub-tree one GPU owns): L leaf digests followed by L/2, L/4, ... 1 nodes: 2L - 1 digests of
+// 32 bytes.  Level l (0 = leaves) starts at digest offset  2L - (2L >> l).
+int spg_merkle_build_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows, uint32_t* tree, int n_cosets) {
   SPG_ARG(rows >= 8 && (rows & (rows - 1)) == 0, "merkle: rows must be a power of two >= 8");
-  k_merkle_leaves<<<(unsigned)((rows + 127) / 128), 128, 0, ctx->stream>>>(table, ncols, rows, tree);
+  SPG_ARG(n_cosets == 1 || n_cosets == 2 || n_cosets == 4 || n_cosets == 8, "merkle: n_cosets");
+  const size_t n_leaves = (rows >> 3) * n_cosets;
+  k_merkle_leaves<<<(unsigned)((n_leaves + 127) / 128), 128, 0, ctx->stream>>>(table, ncols, rows, n_leaves, tree);
   SPG_LAUNCH_CHECK();
-  size_t off = 0, n = rows;
+  size_t off = 0, n = n_leaves;
   while (n > 1) {
     const size_t n_out = n / 2;
     k_merkle_nodes<<<(unsigned)((n_out + 127) / 128), 128, 0, ctx->stream>>>(tree + 8 * off, tree + 8 * (off + n), n_out);
@@ -67,12 +70,12 @@ int spg_merkle_build_device(spg_ctx* ctx, const Fp* table, int ncols, size_t row
 }
 
 // gather `count` authentication paths: for query q with leaf index idx[q], out[q][l] = sibling at level l
-__global__ void k_merkle_paths(const uint32_t* __restrict__ tree, size_t rows, int levels, const uint32_t* __restrict__ idx,
+__global__ void k_merkle_paths(const uint32_t* __restrict__ tree, size_t n_leaves, int levels, const uint32_t* __restrict__ idx,
                                int count, uint32_t* __restrict__ out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count * levels) return;
   const int q = t / levels, l = t % levels;
-  const size_t off = 2 * rows - ((2 * rows) >> l);
+  const size_t off = 2 * n_leaves - ((2 * n_leaves) >> l);
   const size_t node = ((size_t)idx[q] >> l) ^ 1;
   const uint4* src = reinterpret_cast<const uint4*>(tree + 8 * (off + node));
   uint4* dst = reinterpret_cast<uint4*>(out + 8 * (size_t)t);
@@ -98,14 +101,15 @@ __global__ void k_merkle_open_leaves(const Fp* __restrict__ table, int ncols, si
 }
 
 int spg_merkle_open_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows, const uint32_t* tree,
-                           const uint32_t* d_idx, int count, uint32_t* d_leaves, uint32_t* d_paths) {
+                           const uint32_t* d_idx, int count, uint32_t* d_leaves, uint32_t* d_paths, int n_cosets) {
+  const size_t n_leaves = (rows >> 3) * n_cosets;
   int levels = 0;
-  while (((size_t)1 << levels) < rows) levels++;
+  while (((size_t)1 << levels) < n_leaves) levels++;
   const int nf = 8 * ncols;
   k_merkle_open_leaves<<<(count * nf + 127) / 128, 128, 0, ctx->stream>>>(table, ncols, rows, d_idx, count, d_leaves);
   SPG_LAUNCH_CHECK();
   if (levels > 0) {
-    k_merkle_paths<<<(count * levels + 127) / 128, 128, 0, ctx->stream>>>(tree, rows, levels, d_idx, count, d_paths);
+    k_merkle_paths<<<(count * levels + 127) / 128, 128, 0, ctx->stream>>>(tree, n_leaves, levels, d_idx, count, d_paths);
     SPG_LAUNCH_CHECK();
   }
   return SPG_OK;
@@ -132,7 +136,7 @@ extern "C" int spg_merkle_commit(spg_ctx* ctx, const uint64_t* table, size_t n_c
     dtree = btree.as<uint32_t>();
   }
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = spg_merkle_build_device(ctx, dt, (int)n_cols, rows, dtree);
+  int rc = spg_merkle_build_device(ctx, dt, (int)n_cols, rows, dtree, 8);
   if (rc) return rc;
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SPG_CUDA(cudaMemcpyAsync(root32, dtree + 8 * (2 * rows - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));

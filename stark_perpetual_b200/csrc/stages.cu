@@ -1,0 +1,115 @@
+// Stage-level C-ABI of the prover (device pointers only): the building blocks the multi-GPU host driver
+// (stark_perpetual_b200/prover.py) sequences around its collectives.  Each GPU owns `n_cosets` consecutive
+// cosets of the 8, starting at `first_coset`; tables passed here hold exactly those cosets.
+// Scalars cross the boundary as canonical felts (4 x u64, host memory).  DESIGN.md "Multi-GPU".
+#include <string.h>
+
+#include "blake2s.cuh"
+#include "stark_kernels.cuh"
+
+static Fp gen_mont() { uint64_t three[4] = {3, 0, 0, 0}; return spg_host_from_u64(three); }
+
+extern "C" int spg_stage_merkle(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, int n_cosets,
+                                uint8_t* tree_out) {
+  SPG_ARG(ctx && table && tree_out, "spg_stage_merkle: null");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  return spg_merkle_build_device(ctx, (const Fp*)table, (int)n_cols, rows, (uint32_t*)tree_out, n_cosets);
+}
+
+extern "C" int spg_stage_air(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* t_lde, int first_coset,
+                             int jj0, int n_even, const uint64_t* x0, const uint64_t* outs, const uint64_t* alpha,
+                             uint64_t* cp_out) {
+  SPG_ARG(ctx && t_lde && x0 && outs && alpha && cp_out, "spg_stage_air: null");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  AirPublic pub;
+  for (int l = 0; l < SPG_AIR_LANES; l++) { pub.x0[l] = spg_host_from_u64(x0 + 4 * l); pub.outs[l] = spg_host_from_u64(outs + 4 * l); }
+  Fp apows[SPG_AIR_LANES * SPG_AIR_NCONSTR];
+  const Fp a = spg_host_from_u64(alpha);
+  apows[0] = fp_one();
+  for (int k = 1; k < SPG_AIR_LANES * SPG_AIR_NCONSTR; k++) apows[k] = fp_mul(apows[k - 1], a);
+  return spg_air_eval_device(ctx, log_n, chain_log, (const Fp*)t_lde, pub, apows, (Fp*)cp_out, first_coset, jj0, n_even);
+}
+
+extern "C" int spg_stage_cp_split(spg_ctx* ctx, unsigned log_n, const uint64_t* cp, int jj0, int n_even, uint64_t* hev) {
+  SPG_ARG(ctx && cp && hev, "spg_stage_cp_split: null");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  return spg_cp_split_device(ctx, log_n, (const Fp*)cp, (Fp*)hev, jj0, n_even);
+}
+
+// cols: host array of n_items device pointers (scaled, bit-reversed coefficient columns); pts: [n_pts][4]
+// canonical; out: [n_items][4] canonical.  Evaluates column k at pts[pt_idx[k]] / g.
+extern "C" int spg_stage_poly_eval(spg_ctx* ctx, unsigned log_n, const uint64_t* const* cols, const int* pt_idx,
+                                   int n_items, const uint64_t* pts, int n_pts, uint64_t* out) {
+  SPG_ARG(ctx && cols && pt_idx && pts && out && n_items > 0 && n_items <= 256 && n_pts > 0 && n_pts <= 16, "spg_stage_poly_eval");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  const Fp ginv = fp_inv(gen_mont());
+  std::vector<Fp> p(n_pts), res(n_items);
+  for (int k = 0; k < n_pts; k++) p[k] = fp_mul(spg_host_from_u64(pts + 4 * k), ginv);
+  int rc = spg_poly_eval_device(ctx, log_n, (const Fp* const*)cols, pt_idx, n_items, p.data(), n_pts, res.data());
+  if (rc) return rc;
+  for (int k = 0; k < n_items; k++) spg_host_to_u64(res[k], out + 4 * k);
+  return SPG_OK;
+}
+
+// DEEP quotient on the local cosets.  oods: [54][4] canonical; inv_scratch: device, 3 * n_cosets * N felts.
+extern "C" int spg_stage_deep(spg_ctx* ctx, unsigned log_n, const uint64_t* t_lde, const uint64_t* h_lde, int first_coset,
+                              int n_cosets, const uint64_t* z, const uint64_t* gamma, const uint64_t* oods,
+                              uint64_t* inv_scratch, uint64_t* out) {
+  SPG_ARG(ctx && t_lde && h_lde && z && gamma && oods && inv_scratch && out, "spg_stage_deep: null");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  const int C = SPG_AIR_COLS;
+  const Fp zz = spg_host_from_u64(z), gm = spg_host_from_u64(gamma);
+  const Fp zw = fp_mul(zz, spg_host_root_of_unity((int)log_n)), z4 = fp_sqr(fp_sqr(zz));
+  Fp gp[SPG_N_OODS + 6], o[SPG_N_OODS];
+  for (int k = 0; k < SPG_N_OODS; k++) o[k] = spg_host_from_u64(oods + 4 * k);
+  gp[0] = fp_one();
+  for (int k = 1; k < SPG_N_OODS; k++) gp[k] = fp_mul(gp[k - 1], gm);
+  Fp K[3] = {fp_zero(), fp_zero(), fp_zero()};
+  for (int c = 0; c < C; c++) { K[0] = fp_add(K[0], fp_mul(gp[c], o[c])); K[1] = fp_add(K[1], fp_mul(gp[C + c], o[C + c])); }
+  for (int m = 0; m < 4; m++) K[2] = fp_add(K[2], fp_mul(gp[2 * C + m], o[2 * C + m]));
+  gp[SPG_N_OODS] = K[0]; gp[SPG_N_OODS + 1] = K[1]; gp[SPG_N_OODS + 2] = K[2];
+  gp[SPG_N_OODS + 3] = zz; gp[SPG_N_OODS + 4] = zw; gp[SPG_N_OODS + 5] = z4;
+  void* ds;
+  SPG_CUDA(spg_scratch(ctx, 6, sizeof(gp), &ds));
+  SPG_CUDA(cudaMemcpyAsync(ds, gp, sizeof(gp), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  Fp* d_small = (Fp*)ds;
+  int rc = spg_inv_x_minus_device(ctx, log_n, first_coset, 1, n_cosets, d_small + SPG_N_OODS + 3, 3, (Fp*)inv_scratch);
+  if (rc) return rc;
+  return spg_deep_device(ctx, log_n, (const Fp*)t_lde, (const Fp*)h_lde, (const Fp*)inv_scratch, d_small,
+                         d_small + SPG_N_OODS, (Fp*)out, n_cosets);
+}
+
+// fold layer `layer_index` (0 = the DEEP quotient, rows = 2^log_rows per coset) by 8 with challenge beta
+extern "C" int spg_stage_fri_fold(spg_ctx* ctx, const uint64_t* in, unsigned log_rows, int first_coset, int n_cosets,
+                                  const uint64_t* beta, int layer_index, uint64_t* out) {
+  SPG_ARG(ctx && in && beta && out && layer_index >= 0 && layer_index < 16, "spg_stage_fri_fold");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  Fp g_l = gen_mont();
+  for (int k = 0; k < 3 * layer_index; k++) g_l = fp_sqr(g_l);
+  return spg_fri_fold8_device(ctx, (const Fp*)in, log_rows, fp_mul(spg_host_from_u64(beta), fp_inv(g_l)), (Fp*)out,
+                              first_coset, n_cosets);
+}
+
+// open `count` leaves (LOCAL leaf indices, host array) of a local table: leaves_out [count][8 n_cols 32] bytes,
+// paths_out [count][levels 32] bytes with levels = log2(n_cosets rows / 8)   (host buffers)
+extern "C" int spg_stage_open(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, int n_cosets,
+                              const uint8_t* tree, const uint32_t* idx, int count, uint8_t* leaves_out, uint8_t* paths_out) {
+  SPG_ARG(ctx && table && tree && idx && leaves_out && paths_out && count >= 0, "spg_stage_open");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (count == 0) return SPG_OK;
+  const size_t n_leaves = (rows >> 3) * n_cosets;
+  int levels = 0;
+  while (((size_t)1 << levels) < n_leaves) levels++;
+  const size_t lw = 8 * n_cols * 8, pw = (size_t)levels * 8;
+  DevBuf di, dl, dp;
+  SPG_CUDA(di.alloc(count * 4)); SPG_CUDA(dl.alloc(count * lw * 4)); SPG_CUDA(dp.alloc(count * pw * 4 + 16));
+  SPG_CUDA(cudaMemcpyAsync(di.p, idx, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = spg_merkle_open_device(ctx, (const Fp*)table, (int)n_cols, rows, (const uint32_t*)tree, di.as<uint32_t>(), count,
+                                  dl.as<uint32_t>(), dp.as<uint32_t>(), n_cosets);
+  if (rc) return rc;
+  SPG_CUDA(cudaMemcpyAsync(leaves_out, dl.p, count * lw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (levels) SPG_CUDA(cudaMemcpyAsync(paths_out, dp.p, count * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}

@@ -24,18 +24,20 @@ __device__ __forceinline__ Fp spg_uni_pow(const Fp* __restrict__ uniA, const Fp*
 }
 
 // ---- merkle.cu
-int spg_merkle_build_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows, uint32_t* tree);
+int spg_merkle_build_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows, uint32_t* tree, int n_cosets = 8);
 int spg_merkle_open_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows, const uint32_t* tree,
-                           const uint32_t* d_idx, int count, uint32_t* d_leaves, uint32_t* d_paths);
+                           const uint32_t* d_idx, int count, uint32_t* d_leaves, uint32_t* d_paths, int n_cosets = 8);
 
 // ---- fri.cu
 // out[a][jj][i] = 1 / (x - A[a]),  x = g * w_{8N}^(j0 + jstep*jj + 8 i),  a < n_a, jj < nj, i < N  (Montgomery)
 int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int nj, const Fp* d_A, int n_a, Fp* out);
-// DEEP quotient over the whole LDE domain: layer0[j][i]
-int spg_deep_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, const Fp* inv3 /*[3][8][N]*/,
-                    const Fp* d_gamma /*[54]*/, const Fp* d_K /*[3]*/, Fp* out);
-// one FRI fold by 8: in [8][rows] -> out [8][rows/8]; x = g_l * w_{8 rows}^(j + 8 i)
-int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp& beta_over_g /*beta / g_l, Mont*/, Fp* out);
+// DEEP quotient over n_cosets consecutive cosets of the LDE domain (tables hold exactly those cosets): layer0[j][i]
+int spg_deep_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, const Fp* inv3 /*[3][n_cosets][N]*/,
+                    const Fp* d_gamma /*[54]*/, const Fp* d_K /*[3]*/, Fp* out, int n_cosets = 8);
+// one FRI fold by 8 of n_cosets consecutive cosets starting at first_coset: in [n_cosets][rows] -> out
+// [n_cosets][rows/8]; x = g_l * w_{8 rows}^(j + 8 i)
+int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp& beta_over_g /*beta / g_l, Mont*/, Fp* out,
+                         int first_coset = 0, int n_cosets = 8);
 // evaluate n_items polynomials given as scaled, bit-reversed coefficient columns: item k uses the device
 // column h_cols[k] and the point h_pts[h_pt_idx[k]] (Montgomery):  h_out[k] = sum_pos col[pos] * w^bitrev(pos)
 // (synchronises the stream; h_* are host arrays)
@@ -46,11 +48,14 @@ int spg_poly_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* const* h_cols, 
 struct AirPublic {
   Fp x0[SPG_AIR_LANES], outs[SPG_AIR_LANES];   // Montgomery
 };
-// composition polynomial on the cosets j = 0, 2, 4, 6: cp[jj][i]
+// composition polynomial on the even cosets j = 2 jj, jj in [jj0, jj0 + n_even): cp[jj - jj0][i].  t_lde holds
+// consecutive cosets starting at first_coset.
 int spg_air_eval_device(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const Fp* t_lde, const AirPublic& pub,
-                        const Fp* h_alpha_pows /*[65], host, Mont*/, Fp* cp);
-// split cp (4 cosets) into the 4 chunk columns evaluated on g^4 <w_N>, natural order: hev[m][pos]
-int spg_cp_split_device(spg_ctx* ctx, unsigned log_n, const Fp* cp, Fp* hev);
+                        const Fp* h_alpha_pows /*[65], host, Mont*/, Fp* cp, int first_coset = 0, int jj0 = 0,
+                        int n_even = 4);
+// split cp (even cosets jj0 .. jj0 + n_even) into the 4 chunk columns evaluated on g^4 <w_N>, natural order:
+// hev[m][jj + 4 i'] (only the positions of those cosets are written)
+int spg_cp_split_device(spg_ctx* ctx, unsigned log_n, const Fp* cp, Fp* hev, int jj0 = 0, int n_even = 4);
 // host-side evaluation of the composition at an out-of-domain point (prover self-check)
 Fp spg_air_composition_at_host(unsigned log_n, unsigned chain_log, const AirPublic& pub, const Fp* alpha_pows,
                                const Fp& z, const Fp* tz, const Fp* tzw, const std::vector<Fp>& const_points);

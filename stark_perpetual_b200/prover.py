@@ -1,54 +1,491 @@
 """Host-side driver of the STARK prover (the role Stone's `cpu_air_prover` CLI plays next to cairo-run's
 artefacts, src/starkware/cairo/lang/cairo_cmake_rules.cmake:72-110 -- the reference itself has no prover).
 
-    pv = Prover(ctx)                       # one GPU
-    trace = pv.witness(log_n, chain_log, x0, ys)
-    proof = pv.prove_host(trace, log_n, chain_log, x0)
-    # oracle/stark.py verify(proof) is the independent checker used by the tests
+Single GPU:   Prover(ctx).prove_host(trace, ...) -> libspg's spg_prove (all stages sequenced in C++).
+Multi GPU:    Prover(ctx, rank, world) -- one process per GPU; this module sequences the stage-level C-ABI
+              (spg_stage_*) around torch.distributed collectives.  Sharding (DESIGN.md "Multi-GPU"):
+              * columns are sharded for interpolation, ONE all-gather exchanges the coefficient columns;
+              * each GPU then owns 8/world consecutive cosets of the evaluation domain for everything else
+                (LDE, Merkle sub-trees, AIR, DEEP, FRI folds never leave a coset);
+              * 32-byte sub-tree roots, the four composition chunks (N felts each) and the query openings are
+                the only other traffic.
+              The proof is byte-identical to the single-GPU one.
 
-Multi-GPU (one process per GPU, torch.distributed for the rendezvous): see `Prover(ctx, rank, world)` and
-DESIGN.md "Multi-GPU".
+The stage backend is an interface (`GpuBackend` here); tests/ plugs a CPU stand-in behind the same driver to
+exercise the multi-process logic with gloo.
 """
+import ctypes as C
+import hashlib
+
 import numpy as np
 
-from ._lib import ints_to_limbs
+from ._lib import FIELD_PRIME as P, SPG_DEVICE_PTRS, ints_to_limbs, limbs_to_ints
+
+R_MOD_P = (1 << 256) % P
+LANES, N_COLS, N_CONSTR, BLOWUP, LOG_BLOWUP, GEN = 5, 25, 13, 8, 3, 3
+LAST_LAYER_MAX = 64
+SPG_MONT_OUT = 4
+
+
+# ------------------------------------------------------------------ host-side field / hash / channel helpers
+def ser(v):
+    return (v * R_MOD_P % P).to_bytes(32, "big")
+
+
+def H(b):
+    return hashlib.blake2s(b).digest()
+
+
+def root_of_unity(log_n):
+    return pow(GEN, (P - 1) >> log_n, P)
+
+
+class Channel:
+    def __init__(self, seed):
+        self.state, self.counter = H(b"spg-stark-v1" + seed), 0
+
+    def absorb(self, data):
+        self.state, self.counter = H(self.state + data), 0
+
+    def draw(self):
+        out = H(self.state + self.counter.to_bytes(8, "little"))
+        self.counter += 1
+        return out
+
+    def draw_felt(self):
+        return int.from_bytes(self.draw(), "little") & ((1 << 251) - 1)
+
+    def draw_index(self, n):
+        return int.from_bytes(self.draw()[:8], "little") % n
+
+
+def fri_log_rows(log_n):
+    lr = [log_n]
+    while (1 << lr[-1]) > LAST_LAYER_MAX:
+        lr.append(lr[-1] - 3)
+    return lr
+
+
+def top_levels(roots):
+    """Merkle levels above the per-GPU sub-tree roots."""
+    levels = [list(roots)]
+    while len(levels[-1]) > 1:
+        prev = levels[-1]
+        levels.append([H(prev[2 * i] + prev[2 * i + 1]) for i in range(len(prev) // 2)])
+    return levels
+
+
+def top_path(levels, owner):
+    path, idx = [], owner
+    for lvl in levels[:-1]:
+        path.append(lvl[idx ^ 1])
+        idx >>= 1
+    return path
+
+
+def composition_at(log_n, chain_log, x0, outs, alpha_pows, z, tz, tzw, const_points, shift):
+    """CP(z) from the trace values at z and z*w (prover self-check; same formulas as csrc/air.cu)."""
+    n, seg = 1 << log_n, 512 << chain_log
+    inv = lambda a: pow(a % P, -1, P)   # noqa: E731
+    u256, u512, useg = pow(z, n // 256, P), pow(z, n // 512, P), pow(z, n // seg, P)
+    w256, w512, wseg = root_of_unity(8), root_of_unity(9), root_of_unity(9 + chain_log)
+    iz_all = inv(pow(z, n, P) - 1)
+    z_pad = 1
+    for k in range(252, 256):
+        z_pad = z_pad * (u256 - pow(w256, k, P)) % P
+    iz = [(u256 - pow(w256, 255, P)) * iz_all % P, z_pad * iz_all % P, inv(z_pad), inv(u512 - pow(w512, 255, P)),
+          (useg - inv(wseg)) * inv(u512 - pow(w512, 511, P)) % P, inv(u512 - 1), inv(useg - 1),
+          inv(z - inv(root_of_unity(log_n)))]
+    # periodic columns at z (Lagrange over the 512-th roots of unity)
+    c = (pow(u512, 512, P) - 1) * inv(512) % P
+    px = py = 0
+    wr = 1
+    for r in range(512):
+        e, t = r >> 8, r & 255
+        if t < 252:
+            lr = c * wr % P * inv(u512 - wr) % P
+            cx, cy = const_points[2 + 252 * e + t]
+            px, py = (px + lr * cx) % P, (py + lr * cy) % P
+        wr = wr * w512 % P
+    acc = 0
+    for l in range(LANES):
+        X, Y, S, M, I = tz[5 * l:5 * l + 5]
+        Xn, Yn, _s, Mn, _i = tzw[5 * l:5 * l + 5]
+        a = alpha_pows[13 * l:13 * l + 13]
+        bit = (M - 2 * Mn) % P
+        nb = (1 - bit) % P
+        c1 = bit * (bit - 1)
+        c2 = bit * (S * (X - px) - (Y - py))
+        c3 = bit * (S * S - X - px - Xn) + nb * (Xn - X)
+        c4 = bit * (S * (X - Xn) - Y - Yn) + nb * (Yn - Y)
+        acc += (a[0] * c1 + a[1] * c2 + a[2] * c3 + a[3] * c4) % P * iz[0]
+        acc += a[4] * (I * (X - px) - 1) % P * iz[1] + a[5] * M % P * iz[2]
+        acc += (a[6] * (Xn - X) + a[7] * (Yn - Y)) % P * iz[3] + a[8] * (Mn - X) % P * iz[4]
+        acc += (a[9] * (X - shift[0]) + a[10] * (Y - shift[1])) % P * iz[5] + a[11] * (M - x0[l]) % P * iz[6]
+        acc += a[12] * (X - outs[l]) % P * iz[7]
+    return acc % P
+
+
+def host_intt(vals, log_n):
+    """natural-order inverse NTT of python ints (the <= 512-point last FRI layer)."""
+    n = 1 << log_n
+    a = list(vals)
+    bits = log_n
+    for i in range(n):
+        r = int(format(i, "0%db" % bits)[::-1], 2) if bits else 0
+        if r > i:
+            a[i], a[r] = a[r], a[i]
+    w = pow(root_of_unity(log_n), -1, P)
+    h = 1
+    while h < n:
+        wh = pow(w, n // (2 * h), P)
+        for b in range(0, n, 2 * h):
+            t = 1
+            for k in range(h):
+                u, v = a[b + k], a[b + k + h] * t % P
+                a[b + k], a[b + k + h] = (u + v) % P, (u - v) % P
+                t = t * wh % P
+        h *= 2
+    ninv = pow(n, -1, P)
+    return [x * ninv % P for x in a]
+
+
+class ProofError(RuntimeError):
+    pass
+
+
+# ------------------------------------------------------------------ stage backend on libspg
+class GpuBackend:
+    """Stage calls on torch CUDA tensors (int64 limbs, last dimension 4) through the stage-level C-ABI."""
+
+    def __init__(self, ctx):
+        import torch
+        self.torch, self.ctx, self.lib, self.h = torch, ctx, ctx._lib, ctx._h
+        self.dev = torch.device("cuda", ctx.device)
+        # stage kernels and torch's collectives must be ordered on one stream
+        with torch.cuda.device(self.dev):
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        for name, args in {
+            "spg_stage_merkle": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p],
+            "spg_stage_air": [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p],
+            "spg_stage_cp_split": [C.c_void_p, C.c_uint, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+            "spg_stage_poly_eval": [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
+            "spg_stage_deep": [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p],
+            "spg_stage_fri_fold": [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
+            "spg_stage_open": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                               C.c_void_p, C.c_void_p],
+        }.items():
+            fn = getattr(self.lib, name)
+            fn.restype, fn.argtypes = C.c_int, args
+
+    def _chk(self, rc):
+        self.ctx._check(rc)
+
+    @staticmethod
+    def _felts(values):
+        arr = ints_to_limbs(values)
+        return arr, arr.ctypes.data_as(C.c_void_p)
+
+    def felts(self, *shape):
+        return self.torch.empty(tuple(shape) + (4,), dtype=self.torch.int64, device=self.dev)
+
+    def upload(self, np_limbs):
+        return self.torch.from_numpy(np.ascontiguousarray(np_limbs).view(np.int64)).to(self.dev)
+
+    def lde_coeffs(self, cols, log_n, n_cols, out, offset=None, mont=False):
+        keep, op = self._felts([offset]) if offset is not None else (None, None)
+        flags = SPG_DEVICE_PTRS | (SPG_MONT_OUT if mont else 0)
+        self._chk(self.lib.spg_lde_coeffs(self.h, C.c_void_p(cols.data_ptr()), log_n, n_cols, op, C.c_void_p(out.data_ptr()), flags))
+
+    def lde_cosets(self, coeffs, log_n, n_cols, first, count, out):
+        self._chk(self.lib.spg_lde_cosets(self.h, C.c_void_p(coeffs.data_ptr()), log_n, n_cols, LOG_BLOWUP, first, count,
+                                          C.c_void_p(out.data_ptr()), SPG_DEVICE_PTRS))
+
+    def merkle(self, table, n_cols, rows, n_cosets):
+        n_leaves = rows // 8 * n_cosets
+        tree = self.torch.empty((2 * n_leaves - 1) * 32, dtype=self.torch.uint8, device=self.dev)
+        self._chk(self.lib.spg_stage_merkle(self.h, C.c_void_p(table.data_ptr()), n_cols, rows, n_cosets, C.c_void_p(tree.data_ptr())))
+        return tree
+
+    def root(self, tree):
+        return tree[-32:].cpu().numpy().tobytes()
+
+    def air(self, t_lde, log_n, chain_log, first, jj0, n_even, x0, outs, alpha, cp):
+        k1, p1 = self._felts(x0); k2, p2 = self._felts(outs); k3, p3 = self._felts([alpha])
+        self._chk(self.lib.spg_stage_air(self.h, log_n, chain_log, C.c_void_p(t_lde.data_ptr()), first, jj0, n_even, p1, p2, p3,
+                                         C.c_void_p(cp.data_ptr())))
+
+    def cp_split(self, cp, log_n, jj0, n_even, hev):
+        self._chk(self.lib.spg_stage_cp_split(self.h, log_n, C.c_void_p(cp.data_ptr()), jj0, n_even, C.c_void_p(hev.data_ptr())))
+
+    def poly_eval(self, cols, pt_idx, pts, log_n):
+        n = len(cols)
+        ptrs = (C.c_void_p * n)(*[c.data_ptr() for c in cols])
+        idx = (C.c_int * n)(*pt_idx)
+        kp, pp = self._felts(pts)
+        out = np.empty((n, 4), dtype=np.uint64)
+        self._chk(self.lib.spg_stage_poly_eval(self.h, log_n, ptrs, idx, n, pp, len(pts), out.ctypes.data_as(C.c_void_p)))
+        return limbs_to_ints(out)
+
+    def deep(self, t_lde, h_lde, log_n, first, n_cosets, z, gamma, oods, out):
+        scratch = self.felts(3, n_cosets, 1 << log_n)
+        k1, p1 = self._felts([z]); k2, p2 = self._felts([gamma]); k3, p3 = self._felts(oods)
+        self._chk(self.lib.spg_stage_deep(self.h, log_n, C.c_void_p(t_lde.data_ptr()), C.c_void_p(h_lde.data_ptr()), first, n_cosets,
+                                          p1, p2, p3, C.c_void_p(scratch.data_ptr()), C.c_void_p(out.data_ptr())))
+        self.ctx.synchronize()
+
+    def fri_fold(self, layer, log_rows, first, n_cosets, beta, layer_index, out):
+        k1, p1 = self._felts([beta])
+        self._chk(self.lib.spg_stage_fri_fold(self.h, C.c_void_p(layer.data_ptr()), log_rows, first, n_cosets, p1, layer_index,
+                                              C.c_void_p(out.data_ptr())))
+
+    def open(self, table, n_cols, rows, n_cosets, tree, idx):
+        """idx: LOCAL leaf indices.  Returns [(leaf_bytes, path_bytes)] per index."""
+        if not idx:
+            return []
+        n_leaves = rows // 8 * n_cosets
+        levels = n_leaves.bit_length() - 1
+        ia = np.asarray(idx, dtype=np.uint32)
+        lv = np.empty((len(idx), 8 * n_cols * 32), dtype=np.uint8)
+        pa = np.empty((len(idx), max(levels, 1) * 32), dtype=np.uint8)
+        self._chk(self.lib.spg_stage_open(self.h, C.c_void_p(table.data_ptr()), n_cols, rows, n_cosets, C.c_void_p(tree.data_ptr()),
+                                          ia.ctypes.data_as(C.c_void_p), len(idx), lv.ctypes.data_as(C.c_void_p),
+                                          pa.ctypes.data_as(C.c_void_p)))
+        return [(lv[k].tobytes(), pa[k, :levels * 32].tobytes()) for k in range(len(idx))]
+
+    def download_ints(self, t):
+        """device table (Montgomery form) -> canonical python ints"""
+        rinv = pow(R_MOD_P, -1, P)
+        return [v * rinv % P for v in limbs_to_ints(t.reshape(-1, 4).cpu().numpy().view(np.uint64))]
+
+    def const_points(self):
+        import json
+        import os
+        prm = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "curve_params.json")))
+        b = {k: (int(v[0], 16), int(v[1], 16)) for k, v in prm["BASE_POINTS"].items()}
+
+        def dbl(pt):
+            x, y = pt
+            m = (3 * x * x + 1) * pow(2 * y, -1, P) % P
+            nx = (m * m - 2 * x) % P
+            return nx, (m * (x - nx) - y) % P
+        pts = [b["SHIFT_POINT"], b["EC_GEN"]]
+        for name, cnt in zip(("P0", "P1", "P2", "P3"), prm["CHAIN_LENGTHS"]):
+            q = b[name]
+            for _ in range(cnt):
+                pts.append(q)
+                q = dbl(q)
+        return pts
+
+
+class TorchComm:
+    """The collectives the driver needs, on torch.distributed (NCCL for CUDA tensors, gloo on the CPU)."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def all_gather_into(self, out, inp):
+        if self.world == 1:
+            out.copy_(inp.reshape(out.shape))
+            return
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(out, inp)
+
+    def broadcast(self, t, src):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(t, src)
+
+    def all_gather_obj(self, obj):
+        if self.world == 1:
+            return [obj]
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, obj)
+        return out
+
+
+# ------------------------------------------------------------------ the sharded prover
+def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_queries=30, check=True):
+    """trace_cols_local: this rank's block of trace columns, tensor [my_cols][N][4] canonical (columns
+    [rank*per, ...) with per = ceil(25/world)).  Returns the proof bytes on every rank."""
+    rank, world = comm.rank, comm.world
+    assert BLOWUP % world == 0
+    n, cs = 1 << log_n, BLOWUP // world
+    first = rank * cs
+    per = -(-N_COLS // world)
+    c0, c1 = min(N_COLS, rank * per), min(N_COLS, (rank + 1) * per)
+    my_cols = c1 - c0
+    log_rows = fri_log_rows(log_n)
+    n_folds = len(log_rows) - 1
+
+    seed = (log_n.to_bytes(4, "little") + chain_log.to_bytes(4, "little") + n_queries.to_bytes(4, "little")
+            + b"".join(ser(v) for v in x0) + b"".join(ser(v) for v in outs))
+    ch = Channel(seed)
+    proof = [b"SPGP", (1).to_bytes(4, "little"), log_n.to_bytes(4, "little"), chain_log.to_bytes(4, "little"),
+             n_queries.to_bytes(4, "little"), n_folds.to_bytes(4, "little")] + [ser(v) for v in x0] + [ser(v) for v in outs]
+
+    def commit(table, n_cols, rows):
+        tree = be.merkle(table, n_cols, rows, cs)
+        roots = comm.all_gather_obj(be.root(tree))
+        top = top_levels(roots)
+        return tree, top
+
+    # 1. interpolation (column-sharded) -> ONE all-gather -> coset evaluation (coset-sharded) + commitment
+    mine = be.felts(per, n)
+    if my_cols:
+        be.lde_coeffs(trace_cols_local, log_n, my_cols, mine, mont=True)
+    coefs = be.felts(per * world, n)
+    comm.all_gather_into(coefs, mine)
+    t_lde = be.felts(cs, N_COLS, n)
+    be.lde_cosets(coefs, log_n, N_COLS, first, cs, t_lde)
+    tree_t, top_t = commit(t_lde, N_COLS, n)
+    root_t = top_t[-1][0]
+    ch.absorb(root_t)
+    # 2. composition on the even cosets this rank owns; chunk split; chunk exchange; chunk LDE + commitment
+    alpha = ch.draw_felt()
+    apows = [pow(alpha, k, P) for k in range(LANES * N_CONSTR)]
+    even = [jj for jj in range(4) if first <= 2 * jj < first + cs]
+    hev = be.felts(4, n)
+    if even:
+        cp = be.felts(len(even), n)
+        be.air(t_lde, log_n, chain_log, first, even[0], len(even), x0, outs, alpha, cp)
+        be.cp_split(cp, log_n, even[0], len(even), hev)
+    hv = hev.view(4, n // 4, 4, 4)
+    if world > 1:
+        for jj in range(4):
+            piece = hv[:, :, jj, :].contiguous()
+            comm.broadcast(piece, (2 * jj) // cs)
+            hv[:, :, jj, :] = piece
+    h_coef = be.felts(4, n)
+    be.lde_coeffs(hev, log_n, 4, h_coef, offset=pow(GEN, -3, P), mont=False)
+    h_lde = be.felts(cs, 4, n)
+    be.lde_cosets(h_coef, log_n, 4, first, cs, h_lde)
+    tree_h, top_h = commit(h_lde, 4, n)
+    root_h = top_h[-1][0]
+    ch.absorb(root_h)
+    # 3. out-of-domain values (every rank holds all coefficient columns)
+    z = ch.draw_felt()
+    wn = root_of_unity(log_n)
+    zw, z4 = z * wn % P, pow(z, 4, P)
+    cols = [coefs[c] for c in range(N_COLS)] * 2 + [h_coef[m] for m in range(4)]
+    oods = be.poly_eval(cols, [0] * N_COLS + [1] * N_COLS + [2] * 4, [z, zw, z4], log_n)
+    if check:
+        cpts = be.const_points()
+        lhs = composition_at(log_n, chain_log, x0, outs, apows, z, oods[:25], oods[25:50], cpts, cpts[0])
+        if lhs != sum(pow(z, m, P) * oods[50 + m] for m in range(4)) % P:
+            raise ProofError("trace does not satisfy the AIR (composition mismatch at the out-of-domain point)")
+    ob = b"".join(ser(v) for v in oods)
+    ch.absorb(ob)
+    # 4. DEEP quotient on the local cosets
+    gamma = ch.draw_felt()
+    layers, trees, tops = [be.felts(cs, n)], [None], [None]
+    be.deep(t_lde, h_lde, log_n, first, cs, z, gamma, oods, layers[0])
+    # 5. FRI
+    fri_roots = []
+    for l in range(1, n_folds + 1):
+        beta = ch.draw_felt()
+        nxt = be.felts(cs, 1 << log_rows[l])
+        be.fri_fold(layers[l - 1], log_rows[l - 1], first, cs, beta, l - 1, nxt)
+        tree, top = commit(nxt, 1, 1 << log_rows[l])
+        layers.append(nxt); trees.append(tree); tops.append(top)
+        fri_roots.append(top[-1][0])
+        ch.absorb(top[-1][0])
+    n_last = 1 << log_rows[-1]
+    parts = comm.all_gather_obj(be.download_ints(layers[-1]))          # [cs * n_last] per rank, coset-major
+    flat = [0] * (8 * n_last)
+    for r, part in enumerate(parts):
+        for jl in range(cs):
+            for i in range(n_last):
+                flat[(r * cs + jl) + 8 * i] = part[jl * n_last + i]
+    lc = host_intt(flat, log_rows[-1] + 3)
+    gli = pow(pow(GEN, 8 ** n_folds, P), -1, P)
+    lc = [c * pow(gli, k, P) % P for k, c in enumerate(lc)]
+    if any(lc[n_last:]):
+        raise ProofError("trace does not satisfy the AIR (FRI last layer is not of low degree)")
+    lb = b"".join(ser(v) for v in lc[:n_last])
+    ch.absorb(lb)
+    proof += [root_t, root_h, ob] + fri_roots + [lb]
+    # 6. queries: every rank opens the leaves that live in its cosets
+    tables = [(t_lde, N_COLS, n, tree_t, top_t), (h_lde, 4, n, tree_h, top_h)]
+    tables += [(layers[l], 1, 1 << log_rows[l], trees[l], tops[l]) for l in range(1, n_folds + 1)]
+    qidx = []                              # per query, per table: (j, i')
+    for _ in range(n_queries):
+        idx = ch.draw_index(n)
+        j, ip = idx // (n // 8), idx % (n // 8)
+        row = [(j, ip), (j, ip)]
+        for l in range(1, n_folds + 1):
+            ip %= (1 << log_rows[l]) // 8
+            row.append((j, ip))
+        qidx.append(row)
+    mine_open = {}
+    for t, (table, n_cols, rows, tree, _top) in enumerate(tables):
+        want = [(q, (j - first) * (rows // 8) + ip) for q, rowq in enumerate(qidx) for (j, ip) in [rowq[t]]
+                if first <= j < first + cs]
+        res = be.open(table, n_cols, rows, cs, tree, [w[1] for w in want])
+        for (q, _li), r in zip(want, res):
+            mine_open[(q, t)] = r
+    all_open = {}
+    for part in comm.all_gather_obj(mine_open):
+        all_open.update(part)
+    for q in range(n_queries):
+        for t, (_table, _nc, _rows, _tree, top) in enumerate(tables):
+            leaf, path = all_open[(q, t)]
+            owner = qidx[q][t][0] // cs
+            proof += [leaf, path] + top_path(top, owner)
+    return b"".join(proof)
 
 
 class Prover:
-    def __init__(self, ctx, rank=0, world=1):
+    def __init__(self, ctx, rank=0, world=1, backend=None, comm=None):
         self.ctx, self.rank, self.world = ctx, rank, world
-        if world > 1:
-            self._init_comm()
+        self.comm = comm or TorchComm(rank, world)
+        self._be = backend
 
-    # ---- single GPU ------------------------------------------------------------------------------
+    @property
+    def be(self):
+        if self._be is None:
+            self._be = GpuBackend(self.ctx)
+        return self._be
+
+    # ---- witness ---------------------------------------------------------------------------------
     def witness(self, log_n, chain_log, x0, ys):
         """ys: list of 5 lists of ints (or a (5 * inst, 4) uint64 array).  Returns the (25 N, 4) trace."""
         if not isinstance(ys, np.ndarray):
             ys = ints_to_limbs([v for lane in ys for v in lane])
         return self.ctx.pedersen_chain_trace(log_n, chain_log, x0, ys)
 
+    # ---- single GPU: everything inside libspg ------------------------------------------------------
     def prove_host(self, trace, log_n, chain_log, x0, n_queries=30):
         if self.world > 1:
-            return self._prove_sharded(trace, None, log_n, chain_log, x0, n_queries)
+            cols, outs = self.shard_host_trace(trace, log_n)
+            return prove_sharded(self.be, self.comm, cols, log_n, chain_log, x0, outs, n_queries)
         return self.ctx.prove(trace, log_n, chain_log, x0, n_queries)
 
     def prove_device(self, trace_ptr, log_n, chain_log, x0, n_queries=30):
-        if self.world > 1:
-            return self._prove_sharded(None, trace_ptr, log_n, chain_log, x0, n_queries)
+        assert self.world == 1, "multi-GPU: use prove_sharded_device with this rank's column block"
         return self.ctx.prove(None, log_n, chain_log, x0, n_queries, device_ptr=trace_ptr)
+
+    # ---- multi GPU ---------------------------------------------------------------------------------
+    def column_block(self):
+        per = -(-N_COLS // self.world)
+        return min(N_COLS, self.rank * per), min(N_COLS, (self.rank + 1) * per)
+
+    def shard_host_trace(self, trace, log_n):
+        """Upload only this rank's columns of a host trace ((25 N, 4) uint64); returns (device block, outs)."""
+        n = 1 << log_n
+        tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(N_COLS, n, 4)
+        outs = limbs_to_ints(tr[[5 * l for l in range(LANES)], n - 1])
+        c0, c1 = self.column_block()
+        block = self.be.upload(tr[c0:c1]) if c1 > c0 else self.be.felts(1, n)
+        return block, outs
+
+    def prove_sharded_device(self, cols_local, log_n, chain_log, x0, outs, n_queries=30):
+        return prove_sharded(self.be, self.comm, cols_local, log_n, chain_log, x0, outs, n_queries)
 
     def parallelism(self):
         if self.world == 1:
             return "1 GPU"
-        return "%d GPUs: rank 0 proves, the others idle (sharded prover not built yet)" % self.world
-
-    # ---- multi GPU -------------------------------------------------------------------------------
-    def _init_comm(self):
-        pass
-
-    def _prove_sharded(self, trace, trace_ptr, log_n, chain_log, x0, n_queries):
-        if self.rank != 0:
-            return None
-        if trace_ptr is not None:
-            return self.ctx.prove(None, log_n, chain_log, x0, n_queries, device_ptr=trace_ptr)
-        return self.ctx.prove(trace, log_n, chain_log, x0, n_queries)
+        return "%d GPUs: columns -> all_gather(coefficients) -> %d coset(s) per GPU" % (self.world, BLOWUP // self.world)

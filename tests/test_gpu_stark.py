@@ -124,3 +124,18 @@ def test_invalid_trace_is_refused(ctx):
     # wrong public seed
     with pytest.raises(SpgError, match="does not satisfy the AIR"):
         ctx.prove(tr, log_n, chain_log, [x0[0] + 1] + x0[1:], n_queries=4)
+
+
+@pytest.mark.parametrize("log_n,chain_log", [(10, 1), (14, 2)])
+def test_stage_driver_equals_monolithic_prover(ctx, log_n, chain_log):
+    """The multi-GPU driver (prover.prove_sharded over the spg_stage_* entry points) with world = 1 must
+    produce exactly the bytes of spg_prove."""
+    from stark_perpetual_b200 import prover
+    x0, ys = make_inputs(log_n, 90 + log_n)
+    tr = ctx.pedersen_chain_trace(log_n, chain_log, x0, ys_limbs(ys))
+    want = ctx.prove(tr, log_n, chain_log, x0, n_queries=9)
+    pv = prover.Prover(ctx)
+    block, outs = pv.shard_host_trace(tr, log_n)
+    got = pv.prove_sharded_device(block, log_n, chain_log, x0, outs, n_queries=9)
+    assert got == want
+    stark.verify(got)

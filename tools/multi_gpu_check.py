@@ -1,0 +1,43 @@
+#!/usr/bin/env python3
+"""torchrun --nproc-per-node G tools/multi_gpu_check.py [log_n]: the sharded prover on G GPUs must emit the
+same bytes as the single-GPU spg_prove (computed on rank 0) and the proof must verify under the oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import stark_perpetual_b200 as spg  # noqa: E402
+from stark_perpetual_b200 import prover  # noqa: E402
+from stark_perpetual_b200._lib import limbs_to_ints  # noqa: E402
+from conftest import rand_felts  # noqa: E402
+
+
+def main():
+    log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 14
+    chain_log = 2
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = spg.Context(local)
+    pv = prover.Prover(ctx, rank, world)
+    x0 = limbs_to_ints(rand_felts(5, 11))
+    ys = rand_felts(5 * ((1 << log_n) >> 9), 12)
+    trace = ctx.pedersen_chain_trace(log_n, chain_log, x0, ys)
+    block, outs = pv.shard_host_trace(trace, log_n)
+    proof = pv.prove_sharded_device(block, log_n, chain_log, x0, outs, 30)
+    dist.barrier()
+    if rank == 0:
+        from oracle import stark
+        want = ctx.prove(trace, log_n, chain_log, x0, 30)
+        stark.verify(proof)
+        print("MULTI_GPU_CHECK world=%d log_n=%d bytes=%d %s" % (world, log_n, len(proof), "MATCH" if proof == want else "MISMATCH"))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
