@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""Throughput of the batched crypto kernels on the GPU box (BASELINE.json configs[0] and configs[4] shapes):
+Pedersen hash2 of n pairs and STARK-curve ECDSA verification of n (msg, r, s, pub_x) tuples.  Signatures are
+random (almost all invalid): the kernel's work does not depend on validity except for early precondition exits,
+which random in-range operands do not trigger."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import stark_perpetual_b200 as spg  # noqa: E402
+from conftest import rand_felts  # noqa: E402
+
+
+def main():
+    ctx = spg.get_context(0)
+    out = {}
+    for n in (1024, 65536, 1 << 20):
+        x, y = rand_felts(n, 21), rand_felts(n, 22)
+        ctx.pedersen_hash2(x[:256], y[:256])
+        t0 = time.perf_counter()
+        _, st = ctx.pedersen_hash2(x, y)
+        wall = time.perf_counter() - t0
+        out["pedersen_hash2_n%d" % n] = {"kernel_ms": ctx.last_kernel_ms, "wall_ms": wall * 1e3,
+                                         "hash_per_s_kernel": n / (ctx.last_kernel_ms * 1e-3),
+                                         "hash_per_s_e2e": n / wall, "bad_status": int((st != 0).sum())}
+    # valid signatures for a slice: derive keys on the device, sign on the host with the oracle (slow), so only a few
+    from oracle import ecdsa as oecdsa
+    from stark_perpetual_b200._lib import ints_to_limbs
+    import random
+    rng = random.Random(5)
+    n_valid = 16
+    privs = [rng.randrange(1, 2**250) for _ in range(n_valid)]
+    msgs = [rng.randrange(1, 2**250) for _ in range(n_valid)]
+    sigs = [oecdsa.sign(m, p) for m, p in zip(msgs, privs)]
+    pubs, stk = ctx.private_to_stark_key(ints_to_limbs(privs))
+    vm, vr, vs = ints_to_limbs(msgs), ints_to_limbs([s[0] for s in sigs]), ints_to_limbs([s[1] for s in sigs])
+    for n in (4096, 65536):
+        msg, r, s = rand_felts(n, 31), rand_felts(n, 32), rand_felts(n, 33)
+        for a in (msg, r, s):
+            a[:, 3] &= np.uint64(0x07ffffffffffffff)       # < 2^251
+        px = np.tile(pubs, (n // n_valid, 1))
+        msg[:n_valid], r[:n_valid], s[:n_valid] = vm, vr, vs
+        ctx.ecdsa_verify(msg[:256], r[:256], s[:256], px[:256])
+        t0 = time.perf_counter()
+        st = ctx.ecdsa_verify(msg, r, s, px)
+        wall = time.perf_counter() - t0
+        out["ecdsa_verify_n%d" % n] = {"kernel_ms": ctx.last_kernel_ms, "wall_ms": wall * 1e3,
+                                       "verify_per_s_kernel": n / (ctx.last_kernel_ms * 1e-3),
+                                       "verify_per_s_e2e": n / wall, "valid": int((st == 1).sum()),
+                                       "invalid": int((st == 0).sum()), "raises": int((st == 2).sum()),
+                                       "first_valid_ok": bool((st[:n_valid] == 1).all())}
+    print(json.dumps(out, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "crypto_bench.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -18,3 +18,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KR
   python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_full.log
 ls -la gpurun_out
+echo "=== crypto bench"; timeout 600 python tools/gpu_crypto_bench.py 2>&1 | tail -60 | tee gpurun_out/${TAG}_crypto.txt
