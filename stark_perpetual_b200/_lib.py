@@ -21,7 +21,8 @@ class SpgError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libspg.so")
+    # SPG_LIB: an alternative build of the same CUDA library (kernel-variant experiments); never a fallback
+    return os.environ.get("SPG_LIB") or os.path.join(_HERE, "libspg.so")
 
 
 def _load():
@@ -139,7 +140,8 @@ class Context:
     # ---- field layer ----
     def field_op(self, op, a, b=None):
         """a, b: (n,4) uint64 canonical felts. op: 'mul','add','sub','inv','pow'."""
-        code = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "pow": 4, "rawmul": 5, "widelo": 6, "widehi": 7, "reduce": 8, "redcdbg": 9}[op]
+        code = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "pow": 4, "rawmul": 5, "widelo": 6, "widehi": 7, "reduce": 8, "sublazy2": 9,
+                "partial": 10, "reducefull": 11, "addraw": 12}[op]
         a = np.ascontiguousarray(a, dtype=np.uint64)
         out = np.empty_like(a)
         bp = None

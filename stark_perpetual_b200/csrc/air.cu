@@ -79,19 +79,19 @@ static int ensure_air_tables(spg_ctx* ctx, unsigned log_n, unsigned chain_log) {
       pcols[512 + 256 * e + t] = ctx->h_const_points[2 * (2 + SPG_HASH_BITS * e + t) + 1];
     }
   DevBuf dp;
-  SPG_CUDA(dp.alloc(pcols.size() * sizeof(Fp)));
+  SPG_CUDA(dp.alloc(ctx, pcols.size() * sizeof(Fp)));
   SPG_CUDA(cudaMemcpyAsync(dp.p, pcols.data(), pcols.size() * sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaMalloc((void**)&ctx->air_plde, 8 * 2 * 512 * sizeof(Fp)));
   uint64_t off[4];
   spg_host_to_u64(K.g512, off);
   DevBuf dcoef;
-  SPG_CUDA(dcoef.alloc(2 * 512 * sizeof(Fp)));
+  SPG_CUDA(dcoef.alloc(ctx, 2 * 512 * sizeof(Fp)));
   int rc = spg_lde_device(ctx, dp.as<Fp>(), 9, 2, SPG_LOG_BLOWUP, off, ctx->air_plde, dcoef.as<Fp>(), 0);
   if (rc) return rc;
   // 1 / (x - w_N^(N-1)) on cosets 0, 2, 4, 6
   const Fp last = fp_inv(spg_host_root_of_unity((int)log_n));   // w^(N-1) = w^-1
   DevBuf dl;
-  SPG_CUDA(dl.alloc(sizeof(Fp)));
+  SPG_CUDA(dl.alloc(ctx, sizeof(Fp)));
   SPG_CUDA(cudaMemcpyAsync(dl.p, &last, sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaMalloc((void**)&ctx->air_ilast, 4 * n * sizeof(Fp)));
   rc = spg_inv_x_minus_device(ctx, log_n, 0, 2, 4, dl.as<Fp>(), 1, ctx->air_ilast);

@@ -36,6 +36,10 @@ struct spg_ctx {
   // growable scratch slots (device), kept until spg_destroy
   void* scratch_p[8] = {nullptr};
   size_t scratch_sz[8] = {0};
+  // recycled temporary device buffers (DevBuf): cudaMalloc / cudaFree synchronise the device and cost
+  // milliseconds, so temporaries of the entry points are kept and reused (all work is ordered on ctx->stream)
+  struct PoolBlock { void* p; size_t size; bool in_use; };
+  std::vector<PoolBlock> pool;
   // LDE scale tables cached per (log_n, offset, mont): lo[R] , hi[B]
   struct LdeTables { int log_n; uint64_t offset[4]; int mont; Fp* lo; Fp* hi; };
   std::vector<LdeTables> lde_tables;
@@ -105,11 +109,39 @@ static inline cudaError_t spg_scratch(spg_ctx* ctx, int slot, size_t bytes, void
     SPG_CUDA(cudaGetLastError());                   \
   } while (0)
 
-// RAII device buffer (freed on scope exit)
+// RAII temporary device buffer, recycled through the context's pool (returned on scope exit, freed by spg_destroy)
 struct DevBuf {
   void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+  spg_ctx* owner = nullptr;
+  ~DevBuf() {
+    if (!p) return;
+    for (auto& b : owner->pool) if (b.p == p) { b.in_use = false; return; }
+  }
+  cudaError_t alloc(spg_ctx* ctx, size_t bytes) {
+    if (bytes < 256) bytes = 256;
+    owner = ctx;
+    spg_ctx::PoolBlock* best = nullptr;
+    for (auto& b : ctx->pool)
+      if (!b.in_use && b.size >= bytes && b.size <= 2 * bytes + (1u << 20) && (!best || b.size < best->size)) best = &b;
+    if (best) { best->in_use = true; p = best->p; return cudaSuccess; }
+    // keep the pool bounded: drop idle blocks before growing it past 64 entries
+    if (ctx->pool.size() >= 64) {
+      for (size_t i = 0; i < ctx->pool.size();) {
+        if (!ctx->pool[i].in_use) { cudaFree(ctx->pool[i].p); ctx->pool.erase(ctx->pool.begin() + i); } else i++;
+      }
+    }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {   // out of memory: release every idle block and retry once
+      for (size_t i = 0; i < ctx->pool.size();) {
+        if (!ctx->pool[i].in_use) { cudaFree(ctx->pool[i].p); ctx->pool.erase(ctx->pool.begin() + i); } else i++;
+      }
+      cudaGetLastError();
+      e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) { p = nullptr; return e; }
+    }
+    ctx->pool.push_back({p, bytes, true});
+    return cudaSuccess;
+  }
   template <class T> T* as() { return (T*)p; }
 };
 

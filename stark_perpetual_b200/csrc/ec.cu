@@ -134,7 +134,7 @@ extern "C" int spg_pedersen_chain_batch(spg_ctx* ctx, const uint64_t* elems, siz
   const uint64_t* de = elems; uint64_t* dout = out; uint8_t* dst = status;
   DevBuf be, bo, bs;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(be.alloc(n * chain_len * 32)); SPG_CUDA(bo.alloc(n * 32)); SPG_CUDA(bs.alloc(n));
+    SPG_CUDA(be.alloc(ctx, n * chain_len * 32)); SPG_CUDA(bo.alloc(ctx, n * 32)); SPG_CUDA(bs.alloc(ctx, n));
     SPG_CUDA(cudaMemcpyAsync(be.p, elems, n * chain_len * 32, cudaMemcpyHostToDevice, ctx->stream));
     de = be.as<uint64_t>(); dout = bo.as<uint64_t>(); dst = bs.as<uint8_t>();
   }
@@ -159,13 +159,13 @@ extern "C" int spg_pedersen_hash2_batch(spg_ctx* ctx, const uint64_t* x, const u
   if (n == 0) return SPG_OK;
   // interleave (x, y) pairs on the device, then run the chain kernel with chain_len = 2
   DevBuf pairs, bo, bs;
-  SPG_CUDA(pairs.alloc(n * 64));
+  SPG_CUDA(pairs.alloc(ctx, n * 64));
   const cudaMemcpyKind kind = (flags & SPG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   SPG_CUDA(cudaMemcpy2DAsync(pairs.p, 64, x, 32, 32, n, kind, ctx->stream));
   SPG_CUDA(cudaMemcpy2DAsync((char*)pairs.p + 32, 64, y, 32, 32, n, kind, ctx->stream));
   uint64_t* dout = out; uint8_t* dst = status;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(bo.alloc(n * 32)); SPG_CUDA(bs.alloc(n));
+    SPG_CUDA(bo.alloc(ctx, n * 32)); SPG_CUDA(bs.alloc(ctx, n));
     dout = bo.as<uint64_t>(); dst = bs.as<uint8_t>();
   }
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -187,8 +187,8 @@ extern "C" int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, con
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
   DevBuf bx, by, lx, ly, lo, bo, bs;
-  SPG_CUDA(bx.alloc(n * 32)); SPG_CUDA(by.alloc(n * 32)); SPG_CUDA(lx.alloc(n * 32)); SPG_CUDA(ly.alloc(n * 32));
-  SPG_CUDA(lo.alloc(n * 32)); SPG_CUDA(bo.alloc(n * 32)); SPG_CUDA(bs.alloc(n));
+  SPG_CUDA(bx.alloc(ctx, n * 32)); SPG_CUDA(by.alloc(ctx, n * 32)); SPG_CUDA(lx.alloc(ctx, n * 32)); SPG_CUDA(ly.alloc(ctx, n * 32));
+  SPG_CUDA(lo.alloc(ctx, n * 32)); SPG_CUDA(bo.alloc(ctx, n * 32)); SPG_CUDA(bs.alloc(ctx, n));
   SPG_CUDA(cudaMemcpyAsync(bx.p, x, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaMemcpyAsync(by.p, y, n * 32, cudaMemcpyHostToDevice, ctx->stream));
   const unsigned blocks = (unsigned)((n + 127) / 128);

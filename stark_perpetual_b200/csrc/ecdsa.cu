@@ -112,11 +112,11 @@ extern "C" int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const u
     const uint64_t** dstp[5] = {&dm, &dr, &ds, &dx, &dy};
     for (int k = 0; k < 5; k++) {
       if (!src[k]) continue;
-      SPG_CUDA(b[k].alloc(n * 32));
+      SPG_CUDA(b[k].alloc(ctx, n * 32));
       SPG_CUDA(cudaMemcpyAsync(b[k].p, src[k], n * 32, cudaMemcpyHostToDevice, ctx->stream));
       *dstp[k] = b[k].as<uint64_t>();
     }
-    SPG_CUDA(bs.alloc(n));
+    SPG_CUDA(bs.alloc(ctx, n));
     dst = bs.as<uint8_t>();
   }
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -140,8 +140,8 @@ extern "C" int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv
   const uint64_t* dp = priv; uint64_t* dx = pub_x; uint64_t* dy = pub_y_or_null; uint8_t* dst = status;
   DevBuf bp, bx, by, bs;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(bp.alloc(n * 32)); SPG_CUDA(bx.alloc(n * 32)); SPG_CUDA(bs.alloc(n));
-    if (pub_y_or_null) { SPG_CUDA(by.alloc(n * 32)); dy = by.as<uint64_t>(); }
+    SPG_CUDA(bp.alloc(ctx, n * 32)); SPG_CUDA(bx.alloc(ctx, n * 32)); SPG_CUDA(bs.alloc(ctx, n));
+    if (pub_y_or_null) { SPG_CUDA(by.alloc(ctx, n * 32)); dy = by.as<uint64_t>(); }
     SPG_CUDA(cudaMemcpyAsync(bp.p, priv, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     dp = bp.as<uint64_t>(); dx = bx.as<uint64_t>(); dst = bs.as<uint8_t>();
   }

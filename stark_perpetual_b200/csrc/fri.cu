@@ -206,9 +206,9 @@ int spg_poly_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* const* h_cols, 
   const unsigned t = log_n < SPG_EVAL_T ? log_n : SPG_EVAL_T;
   const size_t na = (size_t)1 << t, nb = (size_t)1 << (log_n - t);
   DevBuf dpts, dA, dB, dcols, dpidx, dpart, dout;
-  SPG_CUDA(dpts.alloc(n_pts * sizeof(Fp))); SPG_CUDA(dA.alloc(n_pts * na * sizeof(Fp))); SPG_CUDA(dB.alloc(n_pts * nb * sizeof(Fp)));
-  SPG_CUDA(dcols.alloc(n_items * sizeof(Fp*))); SPG_CUDA(dpidx.alloc(n_items * sizeof(int)));
-  SPG_CUDA(dpart.alloc(n_items * nb * sizeof(Fp))); SPG_CUDA(dout.alloc(n_items * sizeof(Fp)));
+  SPG_CUDA(dpts.alloc(ctx, n_pts * sizeof(Fp))); SPG_CUDA(dA.alloc(ctx, n_pts * na * sizeof(Fp))); SPG_CUDA(dB.alloc(ctx, n_pts * nb * sizeof(Fp)));
+  SPG_CUDA(dcols.alloc(ctx, n_items * sizeof(Fp*))); SPG_CUDA(dpidx.alloc(ctx, n_items * sizeof(int)));
+  SPG_CUDA(dpart.alloc(ctx, n_items * nb * sizeof(Fp))); SPG_CUDA(dout.alloc(ctx, n_items * sizeof(Fp)));
   SPG_CUDA(cudaMemcpyAsync(dpts.p, h_pts, n_pts * sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaMemcpyAsync(dcols.p, h_cols, n_items * sizeof(Fp*), cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaMemcpyAsync(dpidx.p, h_pt_idx, n_items * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

@@ -137,7 +137,7 @@ extern "C" int spg_lde(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size
   Fp* dout = (Fp*)out;
   DevBuf bi, bo;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(bi.alloc(in_bytes)); SPG_CUDA(bo.alloc(out_bytes));
+    SPG_CUDA(bi.alloc(ctx, in_bytes)); SPG_CUDA(bo.alloc(ctx, out_bytes));
     SPG_CUDA(cudaMemcpyAsync(bi.p, trace, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     din = bi.as<Fp>(); dout = bo.as<Fp>();
   }

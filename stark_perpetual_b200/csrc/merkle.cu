@@ -127,12 +127,12 @@ extern "C" int spg_merkle_commit(spg_ctx* ctx, const uint64_t* table, size_t n_c
   DevBuf bt, btree;
   uint32_t* dtree = (uint32_t*)tree_out;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(bt.alloc(bytes));
+    SPG_CUDA(bt.alloc(ctx, bytes));
     SPG_CUDA(cudaMemcpyAsync(bt.p, table, bytes, cudaMemcpyHostToDevice, ctx->stream));
     dt = bt.as<Fp>();
   }
   if (!(flags & SPG_DEVICE_PTRS) || !tree_out) {
-    SPG_CUDA(btree.alloc(tree_bytes));
+    SPG_CUDA(btree.alloc(ctx, tree_bytes));
     dtree = btree.as<uint32_t>();
   }
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));

@@ -3,17 +3,28 @@
 #include "common.h"
 #include "ntt.cuh"
 
-#define NTT_LOG_WS 11
-typedef NttTile<NTT_LOG_WS> Tile;
+// Tile shape, chosen by measurement on B200 (profiles/r1e_ntt_variants.md): a 2^10-element workspace (32 KB), radix-4
+// steps (4 elements per thread, 256 threads), 64 registers -> 4 CTAs = 32 warps per SM.  The radix-8 / 2^11 shape
+// needs 128 registers (16 warps per SM) and is 7-9 % slower at 2^20 and above.
+#ifndef NTT_LOG_WS
+#define NTT_LOG_WS 10
+#endif
+#ifndef NTT_LOG_EPT
+#define NTT_LOG_EPT 2
+#endif
+typedef NttTile<NTT_LOG_WS, NTT_LOG_EPT> Tile;
 
+#ifndef NTT_MIN_CTAS
+#define NTT_MIN_CTAS 4
+#endif
 template <bool DIT>
-__global__ void __launch_bounds__(Tile::NT, 2) k_ntt_pass(NttPass P) {
+__global__ void __launch_bounds__(Tile::NT, NTT_MIN_CTAS) k_ntt_pass(NttPass P) {
   extern __shared__ uint4 smem_raw[];
-  Fp* ws = reinterpret_cast<Fp*>(smem_raw);
+  FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
   const int tid = threadIdx.x;
   const unsigned cta = blockIdx.x, col = blockIdx.y;
 #pragma unroll
-  for (int j = 0; j < 8; j++) Tile::load_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
+  for (int j = 0; j < Tile::EPT; j++) Tile::load_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
   __syncthreads();
   const int ns = Tile::n_steps(P);
   for (int k = 0; k < ns; k++) {
@@ -23,7 +34,7 @@ __global__ void __launch_bounds__(Tile::NT, 2) k_ntt_pass(NttPass P) {
     __syncthreads();
   }
 #pragma unroll
-  for (int j = 0; j < 8; j++) Tile::store_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
+  for (int j = 0; j < Tile::EPT; j++) Tile::store_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
 }
 
 __global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
@@ -85,7 +96,7 @@ extern "C" int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batc
   Fp* d = (Fp*)data;
   DevBuf buf, tmp, sc;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(buf.alloc(total * 32));
+    SPG_CUDA(buf.alloc(ctx, total * 32));
     SPG_CUDA(cudaMemcpyAsync(buf.p, data, total * 32, cudaMemcpyHostToDevice, ctx->stream));
     d = buf.as<Fp>();
   }
@@ -96,7 +107,7 @@ extern "C" int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batc
     spg_ntt_last_pass_geometry(log_n, &lr, &lb);
     uint64_t nn[4] = {(uint64_t)n, 0, 0, 0};
     Fp ninv = fp_inv(spg_host_from_u64(nn));
-    SPG_CUDA(sc.alloc(((size_t)1 << lb) * 32));
+    SPG_CUDA(sc.alloc(ctx, ((size_t)1 << lb) * 32));
     k_fill<<<(unsigned)((((size_t)1 << lb) + 255) / 256), 256, 0, ctx->stream>>>(sc.as<Fp>(), ninv, (size_t)1 << lb);
     SPG_LAUNCH_CHECK();
     scale_hi = sc.as<Fp>();
@@ -109,7 +120,7 @@ extern "C" int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batc
     if (rc) return rc;
   }
   if (order == SPG_NTT_NAT_TO_NAT && log_n > 0) {
-    SPG_CUDA(tmp.alloc(total * 32));
+    SPG_CUDA(tmp.alloc(ctx, total * 32));
     int rc = spg_bitrev_device(ctx, d, tmp.as<Fp>(), log_n, batch);
     if (rc) return rc;
     SPG_CUDA(cudaMemcpyAsync(d, tmp.p, total * 32, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -43,6 +43,14 @@ struct NttPass {
   // DIT: applied at the start:  x *= lo[r] * hi[b]   (either may be null)
   const Fp* scale_lo;          // R entries
   const Fp* scale_hi;          // B entries
+  int final_pass;              // last pass of the transform: store canonical values (otherwise any lazy representative)
+};
+
+// One half (16 bytes) of a field element in the shared-memory workspace.  The workspace is PLANAR -- low halves
+// in ws[0 .. WS), high halves in ws[WS .. 2 WS) -- and the slot index is XOR-swizzled, so that a warp's 16-byte
+// accesses hit 8 distinct bank groups per quarter-warp for every power-of-two stride the butterflies use.
+struct alignas(16) FpHalf {
+  uint32_t v[4];
 };
 
 SPG_HD unsigned spg_bitrev(unsigned x, int bits) {
@@ -55,15 +63,39 @@ SPG_HD unsigned spg_bitrev(unsigned x, int bits) {
 #endif
 }
 
-template <int LOG_WS>
+// LOG_EPT: log2 of the elements a thread holds per step (3: radix-8 steps, 2: radix-4 steps -- half the live
+// registers, twice the threads per workspace).
+template <int LOG_WS, int LOG_EPT = 3>
 struct NttTile {
   static constexpr int WS = 1 << LOG_WS;
-  static constexpr int NT = WS / 8;
+  static constexpr int EPT = 1 << LOG_EPT;
+  static constexpr int NT = WS / EPT;
 
   // workspace slot of (row r, column/tile g)
   static SPG_HD int slot(const NttPass& P, int r, int g) {
     return P.log_s ? ((r << P.log_g) | g) : ((g << P.log_r) | r);
   }
+  // swizzled position of a slot: the low 3 bits are XORed with the fold of all higher 3-bit groups
+  static SPG_HD int swz(int s) {
+    int u = s >> 3;
+    return s ^ ((u ^ (u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7);
+  }
+  static SPG_HD Fp ws_load(const FpHalf* ws, int s) {
+    const int i = swz(s);
+    const FpHalf lo = ws[i], hi = ws[WS + i];
+    Fp x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { x.v[k] = lo.v[k]; x.v[4 + k] = hi.v[k]; }
+    return x;
+  }
+  static SPG_HD void ws_store(FpHalf* ws, int s, const Fp& x) {
+    const int i = swz(s);
+    FpHalf lo, hi;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { lo.v[k] = x.v[k]; hi.v[k] = x.v[4 + k]; }
+    ws[i] = lo; ws[WS + i] = hi;
+  }
+
   // global element offset (within a column) of workspace-linear index idx for CTA `cta`
   static SPG_HD unsigned long long gaddr(const NttPass& P, unsigned cta, int idx, int* r_out, int* g_out,
                                          unsigned* b_out, unsigned* c_out) {
@@ -87,28 +119,40 @@ struct NttTile {
     unsigned hi = (unsigned)(E >> SPG_UNI_HALF), lo = (unsigned)(E & ((1u << SPG_UNI_HALF) - 1));
     if (lo == 0) return P.uniA[hi];
     if (hi == 0) return P.uniB[lo];
-    return fp_mul(P.uniA[hi], P.uniB[lo]);
+    return fp_mul_lazy(P.uniA[hi], P.uniB[lo]);
   }
 
-  // factor applied to element (b, r, c): diagonal twiddle and optional scale tables
+  // factor applied to element (b, r, c): diagonal twiddle and optional scale tables.  Whenever the pass has a
+  // factor at all the element IS multiplied (by one if need be): a multiplication is what brings a lazy value
+  // back below 2p, which the butterflies of the next pass rely on.
   static SPG_HD Fp apply_factors(const NttPass& P, Fp x, unsigned b, int r, unsigned c) {
     if (P.use_diag) {
       unsigned long long k = spg_bitrev((unsigned)r, P.log_r);
       unsigned long long E = k * ((unsigned long long)c * P.ec + P.e0);
       if (P.inverse) E = (0ull - E);
-      if (E & ((1ull << SPG_UNI_LOG) - 1)) x = fp_mul(x, uni_pow(P, E));
+      x = fp_mul_lazy(x, uni_pow(P, E));
     }
-    if (P.scale_lo) x = fp_mul(x, P.scale_lo[r]);
-    if (P.scale_hi) x = fp_mul(x, P.scale_hi[b]);
+    if (P.scale_lo) x = fp_mul_lazy(x, P.scale_lo[r]);
+    if (P.scale_hi) x = fp_mul_lazy(x, P.scale_hi[b]);
     return x;
   }
 
-  // one butterfly step of width W bits at bit position sh of r, for thread tid.
-  template <int W, bool DIT>
-  static SPG_HD void step(const NttPass& P, Fp* ws, int tid, int sh) {
-    constexpr int GROUPS = 8 >> W;      // groups of 2^W elements per thread
+  // One butterfly step of width W bits at bit position sh of r, for thread tid.  EDGE = (sh == 0): the step
+  // whose twiddles are partly trivial (first step of a DIT tile, last step of a DIF tile).
+  //
+  // Lazy arithmetic (fp.cuh): sums are plain 256-bit additions, differences add a multiple K*p instead of
+  // branching, and only multiplications (or fp_partial) bring values back below 2p.  bd[] tracks, at compile
+  // time (everything is unrolled), an upper bound in units of p for each register:
+  //   DIT: tile inputs < 2p; the edge step ends below 10p, every later stage adds 2p  (<= 24p at the store);
+  //   DIF: every step starts below 2p, sums grow to <= 16p inside a step and are cut back with fp_partial at
+  //        its end; the edge step leaves <= 16p to the store phase.
+  // Everything stays below 32p < 2^256 and within the operand bound of fp_mul_lazy (a * b < 2^508).
+  template <int W, bool DIT, bool EDGE>
+  static SPG_HD void step(const NttPass& P, FpHalf* ws, int tid, int sh) {
+    constexpr int GROUPS = EPT >> W;    // groups of 2^W elements per thread
     constexpr int GS = 1 << W;
     const int t = P.log_r;
+    if (EDGE) sh = 0;
 #pragma unroll
     for (int gi = 0; gi < GROUPS; gi++) {
       int u = gi * NT + tid;
@@ -119,20 +163,31 @@ struct NttTile {
       int lo = x & ((1 << sh) - 1), hi = x >> sh;
       int rbase = (hi << (sh + W)) | lo;
       Fp v[GS];
+      int bd[GS];
 #pragma unroll
-      for (int f = 0; f < GS; f++) v[f] = ws[slot(P, rbase | (f << sh), g)];
+      for (int f = 0; f < GS; f++) { v[f] = ws_load(ws, slot(P, rbase | (f << sh), g)); bd[f] = 2; }
       if (DIT) {
 #pragma unroll
         for (int s = 0; s < W; s++) {
 #pragma unroll
           for (int f = 0; f < GS; f++) {
             if (f & (1 << s)) continue;
-            int e = (((f & ((1 << s) - 1)) << sh) | lo) << (t - 1 - (sh + s));
-            Fp a = v[f], bb = v[f | (1 << s)];
-            Fp tq = e ? fp_mul(bb, P.tw[e << (SPG_TW_LOG - t)]) : bb;
-            if (!e) tq = bb;
-            v[f] = fp_add(a, tq);
-            v[f | (1 << s)] = fp_sub(a, tq);
+            const int f2 = f | (1 << s);
+            const bool trivial = EDGE && (f & ((1 << s) - 1)) == 0;
+            Fp tq;
+            int btq;
+            if (trivial) {
+              if (bd[f2] > 4) { tq = fp_partial(v[f2]); btq = 2; }
+              else { tq = v[f2]; btq = bd[f2]; }
+            } else {
+              int e = (((f & ((1 << s) - 1)) << sh) | lo) << (t - 1 - (sh + s));
+              tq = fp_mul_lazy(v[f2], P.tw[e << (SPG_TW_LOG - t)]);
+              btq = 2;
+            }
+            const Fp a = v[f];
+            v[f] = fp_add_raw(a, tq);
+            v[f2] = fp_sub_lazy(a, tq, (uint32_t)btq);
+            bd[f] = bd[f2] = bd[f] + btq;
           }
         }
       } else {
@@ -141,61 +196,84 @@ struct NttTile {
 #pragma unroll
           for (int f = 0; f < GS; f++) {
             if (f & (1 << s)) continue;
-            int e = (((f & ((1 << s) - 1)) << sh) | lo) << (t - 1 - (sh + s));
-            Fp a = v[f], bb = v[f | (1 << s)];
-            v[f] = fp_add(a, bb);
-            Fp d = fp_sub(a, bb);
-            v[f | (1 << s)] = e ? fp_mul(d, P.tw[e << (SPG_TW_LOG - t)]) : d;
+            const int f2 = f | (1 << s);
+            const bool trivial = EDGE && (f & ((1 << s) - 1)) == 0;
+            const Fp a = v[f], bb = v[f2];
+            const int bsum = bd[f] + bd[f2];
+            v[f] = fp_add_raw(a, bb);
+            Fp d = fp_sub_lazy(a, bb, (uint32_t)bd[f2]);
+            if (trivial) { v[f2] = d; bd[f2] = bsum; }
+            else {
+              int e = (((f & ((1 << s) - 1)) << sh) | lo) << (t - 1 - (sh + s));
+              v[f2] = fp_mul_lazy(d, P.tw[e << (SPG_TW_LOG - t)]);
+              bd[f2] = 2;
+            }
+            bd[f] = bsum;
           }
+        }
+        if (!EDGE) {
+#pragma unroll
+          for (int f = 0; f < GS; f++)
+            if (bd[f] > 2) v[f] = fp_partial(v[f]);
         }
       }
 #pragma unroll
-      for (int f = 0; f < GS; f++) ws[slot(P, rbase | (f << sh), g)] = v[f];
+      for (int f = 0; f < GS; f++) ws_store(ws, slot(P, rbase | (f << sh), g), v[f]);
     }
   }
 
-  // dispatch on runtime width
+  // dispatch on runtime width / edge
   template <bool DIT>
-  static SPG_HD void step_w(const NttPass& P, Fp* ws, int tid, int w, int sh) {
-    if (w == 3) step<3, DIT>(P, ws, tid, sh);
-    else if (w == 2) step<2, DIT>(P, ws, tid, sh);
-    else step<1, DIT>(P, ws, tid, sh);
+  static SPG_HD void step_w(const NttPass& P, FpHalf* ws, int tid, int w, int sh) {
+    if (sh == 0) {
+      if (LOG_EPT >= 3 && w == 3) step<(LOG_EPT >= 3 ? 3 : 1), DIT, true>(P, ws, tid, 0);
+      else if (w == 2) step<2, DIT, true>(P, ws, tid, 0);
+      else step<1, DIT, true>(P, ws, tid, 0);
+    } else {
+      if (LOG_EPT >= 3 && w == 3) step<(LOG_EPT >= 3 ? 3 : 1), DIT, false>(P, ws, tid, sh);
+      else if (w == 2) step<2, DIT, false>(P, ws, tid, sh);
+      else step<1, DIT, false>(P, ws, tid, sh);
+    }
   }
 
-  // load phase for linear index idx of this CTA
+  // load phase for linear index idx of this CTA.  Values entering the butterflies are below 2p: canonical
+  // input, a multiplied value, or (DIF, pass > 0) what the previous pass stored.
   template <bool DIT>
-  static SPG_HD void load_one(const NttPass& P, Fp* ws, unsigned cta, unsigned col, int idx) {
+  static SPG_HD void load_one(const NttPass& P, FpHalf* ws, unsigned cta, unsigned col, int idx) {
     int r, g; unsigned b, c;
     if (idx >= (1 << (P.log_r + P.log_g))) return;
     unsigned long long off = gaddr(P, cta, idx, &r, &g, &b, &c);
     Fp x = P.in[col * P.in_col_stride + off];
     if (DIT) x = apply_factors(P, x, b, r, c);
-    ws[slot(P, r, g)] = x;
+    ws_store(ws, slot(P, r, g), x);
   }
   template <bool DIT>
-  static SPG_HD void store_one(const NttPass& P, const Fp* ws, unsigned cta, unsigned col, int idx) {
+  static SPG_HD void store_one(const NttPass& P, const FpHalf* ws, unsigned cta, unsigned col, int idx) {
     int r, g; unsigned b, c;
     if (idx >= (1 << (P.log_r + P.log_g))) return;
     unsigned long long off = gaddr(P, cta, idx, &r, &g, &b, &c);
-    Fp x = ws[slot(P, r, g)];
+    Fp x = ws_load(ws, slot(P, r, g));
     if (!DIT) x = apply_factors(P, x, b, r, c);
-    P.out[col * P.out_col_stride + off] = fp_reduce(x);
+    // a DIF pass that is not the last one always has a diagonal factor, so x < 2p there; a DIT pass that is not
+    // the last one is followed by a pass that multiplies every element at its load
+    P.out[col * P.out_col_stride + off] = P.final_pass ? fp_reduce_full(x) : x;
   }
   // number of butterfly steps and the (width, shift) of step k.  DIF walks the bits of r from the
   // top, DIT from the bottom; the short step (log_r mod 3) comes last for DIF and first for DIT... both
   // choices keep strides monotone.
-  static SPG_HD int n_steps(const NttPass& P) { return (P.log_r + 2) / 3; }
+  static SPG_HD int n_steps(const NttPass& P) { return (P.log_r + LOG_EPT - 1) / LOG_EPT; }
   template <bool DIT>
   static SPG_HD void step_geom(const NttPass& P, int k, int* w, int* sh) {
-    int t = P.log_r, rem = t % 3, ns = (t + 2) / 3;
+    constexpr int L = LOG_EPT;
+    int t = P.log_r, rem = t % L, ns = (t + L - 1) / L;
     if (DIT) {
       // ascending strides: first step has width rem (if any)
-      if (rem) { *w = (k == 0) ? rem : 3; *sh = (k == 0) ? 0 : rem + 3 * (k - 1); }
-      else { *w = 3; *sh = 3 * k; }
+      if (rem) { *w = (k == 0) ? rem : L; *sh = (k == 0) ? 0 : rem + L * (k - 1); }
+      else { *w = L; *sh = L * k; }
     } else {
       // descending strides: last step has width rem (if any)
       if (rem && k == ns - 1) { *w = rem; *sh = 0; }
-      else { *w = 3; *sh = t - 3 * (k + 1); }
+      else { *w = L; *sh = t - L * (k + 1); }
     }
   }
 };
@@ -257,6 +335,7 @@ static inline int spg_ntt_make_passes(NttPass* passes, int log_ws, const Fp* in,
     P.use_diag = (log_s != 0) || (dit && coset_exp != 0);
     P.scale_lo = nullptr; P.scale_hi = nullptr;
     if (log_s == 0) { P.scale_lo = scale_lo; P.scale_hi = scale_hi; }
+    P.final_pass = (pi == np - 1);
   }
   return np;
 }

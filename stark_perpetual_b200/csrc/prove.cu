@@ -362,13 +362,13 @@ extern "C" int spg_pedersen_chain_trace(spg_ctx* ctx, unsigned log_n, unsigned c
   SPG_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)1 << log_n, inst = n >> 9, bytes = (size_t)SPG_AIR_COLS * n * 32;
   DevBuf dx, dy, dt, ds;
-  SPG_CUDA(dx.alloc(SPG_AIR_LANES * 32)); SPG_CUDA(ds.alloc(4));
+  SPG_CUDA(dx.alloc(ctx, SPG_AIR_LANES * 32)); SPG_CUDA(ds.alloc(ctx, 4));
   SPG_CUDA(cudaMemcpyAsync(dx.p, x0, SPG_AIR_LANES * 32, cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaMemsetAsync(ds.p, 0, 4, ctx->stream));
   const Fp* dys = (const Fp*)ys;
   Fp* dtr = (Fp*)trace_out;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(dy.alloc(SPG_AIR_LANES * inst * 32)); SPG_CUDA(dt.alloc(bytes));
+    SPG_CUDA(dy.alloc(ctx, SPG_AIR_LANES * inst * 32)); SPG_CUDA(dt.alloc(ctx, bytes));
     SPG_CUDA(cudaMemcpyAsync(dy.p, ys, SPG_AIR_LANES * inst * 32, cudaMemcpyHostToDevice, ctx->stream));
     dys = dy.as<Fp>(); dtr = dt.as<Fp>();
   }
@@ -396,8 +396,8 @@ extern "C" int spg_air_eval(spg_ctx* ctx, const uint64_t* trace, unsigned log_n,
   SPG_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)1 << log_n;
   DevBuf dt, dl, dc, dcp;
-  SPG_CUDA(dt.alloc(SPG_AIR_COLS * n * 32)); SPG_CUDA(dl.alloc(8 * SPG_AIR_COLS * n * 32)); SPG_CUDA(dc.alloc(SPG_AIR_COLS * n * 32));
-  SPG_CUDA(dcp.alloc(4 * n * 32));
+  SPG_CUDA(dt.alloc(ctx, SPG_AIR_COLS * n * 32)); SPG_CUDA(dl.alloc(ctx, 8 * SPG_AIR_COLS * n * 32)); SPG_CUDA(dc.alloc(ctx, SPG_AIR_COLS * n * 32));
+  SPG_CUDA(dcp.alloc(ctx, 4 * n * 32));
   SPG_CUDA(cudaMemcpyAsync(dt.p, trace, SPG_AIR_COLS * n * 32, cudaMemcpyHostToDevice, ctx->stream));
   AirPublic pub;
   for (int l = 0; l < SPG_AIR_LANES; l++) { pub.x0[l] = spg_host_from_u64(x0 + 4 * l); pub.outs[l] = spg_host_from_u64(outs + 4 * l); }

@@ -103,7 +103,7 @@ extern "C" int spg_stage_open(spg_ctx* ctx, const uint64_t* table, size_t n_cols
   while (((size_t)1 << levels) < n_leaves) levels++;
   const size_t lw = 8 * n_cols * 8, pw = (size_t)levels * 8;
   DevBuf di, dl, dp;
-  SPG_CUDA(di.alloc(count * 4)); SPG_CUDA(dl.alloc(count * lw * 4)); SPG_CUDA(dp.alloc(count * pw * 4 + 16));
+  SPG_CUDA(di.alloc(ctx, count * 4)); SPG_CUDA(dl.alloc(ctx, count * lw * 4)); SPG_CUDA(dp.alloc(ctx, count * pw * 4 + 16));
   SPG_CUDA(cudaMemcpyAsync(di.p, idx, count * 4, cudaMemcpyHostToDevice, ctx->stream));
   int rc = spg_merkle_open_device(ctx, (const Fp*)table, (int)n_cols, rows, (const uint32_t*)tree, di.as<uint32_t>(), count,
                                   dl.as<uint32_t>(), dp.as<uint32_t>(), n_cosets);

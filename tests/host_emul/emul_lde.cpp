@@ -16,16 +16,22 @@ static void exp_root(int log_n, uint32_t e[8]) {
 static Fp from_u64(uint64_t x) { uint64_t w[4] = {x, 0, 0, 0}; return fp_to_mont(fp_from_u64(w)); }
 static Fp root(int log_n) { uint32_t e[8]; exp_root(log_n, e); return fp_pow(from_u64(3), e, 8); }
 
-typedef NttTile<11> Tile;
+#ifndef EMUL_LOG_WS
+#define EMUL_LOG_WS 10
+#endif
+#ifndef EMUL_LOG_EPT
+#define EMUL_LOG_EPT 2
+#endif
+typedef NttTile<EMUL_LOG_WS, EMUL_LOG_EPT> Tile;
 
 template <bool DIT>
 static void run_pass(const NttPass& P, unsigned ncols) {
   const size_t ctas = ((size_t)1 << P.log_n) >> (P.log_r + P.log_g);
-  std::vector<Fp> ws(Tile::WS);
+  std::vector<FpHalf> ws(2 * Tile::WS);
   for (unsigned col = 0; col < ncols; col++)
     for (unsigned cta = 0; cta < ctas; cta++) {
       for (int tid = 0; tid < Tile::NT; tid++)
-        for (int j = 0; j < 8; j++) Tile::load_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
+        for (int j = 0; j < Tile::EPT; j++) Tile::load_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
       int ns = Tile::n_steps(P);
       for (int k = 0; k < ns; k++) {
         int w, sh;
@@ -33,7 +39,7 @@ static void run_pass(const NttPass& P, unsigned ncols) {
         for (int tid = 0; tid < Tile::NT; tid++) Tile::step_w<DIT>(P, ws.data(), tid, w, sh);
       }
       for (int tid = 0; tid < Tile::NT; tid++)
-        for (int j = 0; j < 8; j++) Tile::store_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
+        for (int j = 0; j < Tile::EPT; j++) Tile::store_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
     }
 }
 
@@ -64,12 +70,12 @@ int main(int argc, char** argv) {
   std::vector<Fp> lo, hi;
   spg_lde_scale_tables(log_n, g, lo, hi);
   NttPass passes[8];
-  int np = spg_ntt_make_passes(passes, 11, x.data(), coef.data(), log_n, n, n, 1, 0, 0, lo.data(), hi.data(),
+  int np = spg_ntt_make_passes(passes, EMUL_LOG_WS, x.data(), coef.data(), log_n, n, n, 1, 0, 0, lo.data(), hi.data(),
                                twf.data(), twi.data(), A.data(), B.data());
   for (int pi = 0; pi < np; pi++) run_pass<false>(passes[pi], C);
   for (size_t j = 0; j < nb; j++) {
     unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
-    np = spg_ntt_make_passes(passes, 11, coef.data(), out.data() + j * C * n, log_n, n, n, 0, 1, coset_exp, nullptr,
+    np = spg_ntt_make_passes(passes, EMUL_LOG_WS, coef.data(), out.data() + j * C * n, log_n, n, n, 0, 1, coset_exp, nullptr,
                              nullptr, twf.data(), twi.data(), A.data(), B.data());
     for (int pi = 0; pi < np; pi++) run_pass<true>(passes[pi], C);
   }

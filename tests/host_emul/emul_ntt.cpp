@@ -16,16 +16,22 @@ static void exp_root(int log_n, uint32_t e[8]) {
 static Fp from_u64(uint64_t x) { uint64_t w[4] = {x, 0, 0, 0}; return fp_to_mont(fp_from_u64(w)); }
 static Fp root(int log_n) { uint32_t e[8]; exp_root(log_n, e); return fp_pow(from_u64(3), e, 8); }
 
-typedef NttTile<11> Tile;
+#ifndef EMUL_LOG_WS
+#define EMUL_LOG_WS 10
+#endif
+#ifndef EMUL_LOG_EPT
+#define EMUL_LOG_EPT 2
+#endif
+typedef NttTile<EMUL_LOG_WS, EMUL_LOG_EPT> Tile;
 
 template <bool DIT>
 static void run_pass(const NttPass& P, unsigned ncols) {
   const size_t ctas = ((size_t)1 << P.log_n) >> (P.log_r + P.log_g);
-  std::vector<Fp> ws(Tile::WS);
+  std::vector<FpHalf> ws(2 * Tile::WS);
   for (unsigned col = 0; col < ncols; col++)
     for (unsigned cta = 0; cta < ctas; cta++) {
       for (int tid = 0; tid < Tile::NT; tid++)
-        for (int j = 0; j < 8; j++) Tile::load_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
+        for (int j = 0; j < Tile::EPT; j++) Tile::load_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
       int ns = Tile::n_steps(P);
       for (int k = 0; k < ns; k++) {
         int w, sh;
@@ -33,7 +39,7 @@ static void run_pass(const NttPass& P, unsigned ncols) {
         for (int tid = 0; tid < Tile::NT; tid++) Tile::step_w<DIT>(P, ws.data(), tid, w, sh);
       }
       for (int tid = 0; tid < Tile::NT; tid++)
-        for (int j = 0; j < 8; j++) Tile::store_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
+        for (int j = 0; j < Tile::EPT; j++) Tile::store_one<DIT>(P, ws.data(), cta, col, j * Tile::NT + tid);
     }
 }
 
@@ -42,6 +48,7 @@ int main(int argc, char** argv) {
   int inverse = argc > 2 ? atoi(argv[2]) : 0;
   int dit = argc > 3 ? atoi(argv[3]) : 0;
   int coset_j = argc > 4 ? atoi(argv[4]) : -1;
+  int pattern = argc > 5 ? atoi(argv[5]) : 0;   // 0 random, 1 every element p - 1, 2 alternating p - 1 / 0
   const size_t n = (size_t)1 << log_n;
   const unsigned ncols = 2;
   // tables
@@ -63,6 +70,10 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 4; k++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; wv[k] = s; }
     wv[3] &= 0x07ffffffffffffffull;
     e = fp_from_u64(wv);
+  }
+  if (pattern) {
+    uint64_t pm1[4] = {0, 0, 0, 0x0800000000000011ull};
+    for (size_t i = 0; i < x.size(); i++) x[i] = (pattern == 1 || (i & 1)) ? fp_from_u64(pm1) : fp_zero();
   }
   // reference: O(n log n) textbook, natural in / natural out
   Fp w = root(log_n);
@@ -103,7 +114,7 @@ int main(int argc, char** argv) {
   spg_ntt_last_pass_geometry(log_n, &lr, &lb);
   std::vector<Fp> sc((size_t)1 << lb, inverse ? fp_inv(from_u64(n)) : fp_one());
   NttPass passes[8];
-  int np = spg_ntt_make_passes(passes, 11, in.data(), y.data(), log_n, n, n, inverse, dit, coset_exp, nullptr,
+  int np = spg_ntt_make_passes(passes, EMUL_LOG_WS, in.data(), y.data(), log_n, n, n, inverse, dit, coset_exp, nullptr,
                                inverse ? sc.data() : nullptr, twf.data(), twi.data(), A.data(), B.data());
   for (int pi = 0; pi < np; pi++) {
     if (dit) run_pass<true>(passes[pi], ncols); else run_pass<false>(passes[pi], ncols);

@@ -95,3 +95,29 @@ def test_ntt_linearity_full_size(ctx):
     lhs = ctx.ntt(s, log_n, False, NTT_NAT_TO_REV)
     rhs = ctx.field_op("add", ctx.ntt(a, log_n, False, NTT_NAT_TO_REV), ctx.ntt(b, log_n, False, NTT_NAT_TO_REV))
     assert np.array_equal(lhs, rhs)
+
+
+def test_lazy_field_ops_raw(ctx):
+    """The lazy family of fp.cuh on raw 256-bit operands (no Montgomery conversion): exact integer identities for
+    add_raw / sub_lazy / partial / reduce_full, and the Montgomery product a*b*2^-256 mod p for operands far above p
+    (a < 2^256, b < 2p: inside the a*b < 2^508 contract), including the reduction's borrow / carry corner cases."""
+    rng = random.Random(77)
+    n = 8192
+    big = [rng.randrange(2**256) for _ in range(n)]
+    big[:8] = [0, 1, P - 1, P, P + 1, 2**256 - 1, 2**251, 31 * P]
+    small = [rng.randrange(2 * P) for _ in range(n)]
+    small[:8] = [0, 1, P - 1, 2 * P - 1, P, 2, 2**192, 2**64 - 1]
+    # crafted low halves that make T[192..255] - V borrow / not borrow and T_low == 0
+    for i in range(8, 64):
+        big[i] = (rng.randrange(2**64) << 192) | rng.choice([0, 1, 2**64 - 1, rng.randrange(2**64)])
+        small[i] = rng.choice([1, 2**64 - 1, 2**192, rng.randrange(2 * P)])
+    A, B = ints_to_limbs(big), ints_to_limbs(small)
+    rinv = pow(2**256, -1, P)
+    got = limbs_to_ints(ctx.field_op("rawmul", A, B))
+    for a, b, g in zip(big, small, got):
+        assert g % P == a * b * rinv % P and 0 < g <= P + (a * b >> 256), (hex(a), hex(b))
+    assert limbs_to_ints(ctx.field_op("partial", A)) == [a - max(0, (a >> 251) - 1) * P for a in big]
+    assert limbs_to_ints(ctx.field_op("reducefull", A)) == [a % P for a in big]
+    lo = [a >> 3 for a in big]
+    assert limbs_to_ints(ctx.field_op("addraw", ints_to_limbs(lo), B)) == [a + b for a, b in zip(lo, small)]
+    assert limbs_to_ints(ctx.field_op("sublazy2", ints_to_limbs(lo), B)) == [a + 2 * P - b for a, b in zip(lo, small)]

@@ -9,27 +9,39 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 BUILD = os.path.join(ROOT, "tests", "host_emul", "build")
 
 
-def _build(name):
+# tile shapes (log2 workspace, log2 elements per thread): the shipped kernel shape first, then the radix-8 shape
+SHAPES = [(10, 2), (11, 3), (11, 2)]
+
+
+def _build(name, shape=None):
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(ROOT, "tests", "host_emul", name + ".cpp")
-    exe = os.path.join(BUILD, name)
+    exe = os.path.join(BUILD, name + ("_%d_%d" % shape if shape else ""))
+    defs = ["-DEMUL_LOG_WS=%d" % shape[0], "-DEMUL_LOG_EPT=%d" % shape[1]] if shape else []
     csrc = os.path.join(ROOT, "stark_perpetual_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".inc", ".h"))]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, src])
+        # SPG_EMUL_LAZY: the host arithmetic reproduces the device's lazy representatives and aborts on any
+        # violated bound (fp.cuh), so the butterflies' bound bookkeeping is checked here, without a GPU
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DSPG_EMUL_LAZY"] + defs + ["-o", exe, src])
     return exe
 
 
-@pytest.mark.parametrize("args", ["5 0 0", "11 1 0", "12 0 1", "13 1 1", "14 0 1 3", "9 0 1 5"])
-def test_emulated_ntt_passes(args):
-    exe = _build("emul_ntt")
+@pytest.mark.parametrize("args", ["5 0 0", "11 1 0", "12 0 1", "13 1 1", "14 0 1 3", "9 0 1 5",
+                                  "10 0 0 -1 1", "10 0 1 -1 1", "9 0 1 -1 2", "13 0 0 -1 2", "8 1 1 -1 1", "20 0 1 2 1"])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_emulated_ntt_passes(args, shape):
+    if shape != SHAPES[0] and args.startswith("20"):
+        pytest.skip("2^20 emulation only for the shipped shape")
+    exe = _build("emul_ntt", shape)
     out = subprocess.run([exe] + args.split(), capture_output=True, text=True)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.parametrize("args", ["3 3", "10 1", "12 3"])
-def test_emulated_lde(args):
-    exe = _build("emul_lde")
+@pytest.mark.parametrize("shape", SHAPES)
+def test_emulated_lde(args, shape):
+    exe = _build("emul_lde", shape)
     out = subprocess.run([exe] + args.split(), capture_output=True, text=True)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
