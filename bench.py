@@ -245,6 +245,10 @@ def main():
     ms_per_step = float(t.item()) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     stage_ms /= args.steps
+    sharded_stages = None
+    if world > 1 and rank == 0:
+        # rank 0's view of the LAST proof: device ms and host wall ms per stage of the Python-sequenced driver
+        sharded_stages = {k: [round(v[0], 3), round(v[1], 3)] for k, v in pv.be.stage_times().items()}
 
     # ---- e2e: host trace through the C-ABI (pinned host memory): H2D + proof + D2H of the proof bytes
     e2e = None
@@ -279,7 +283,9 @@ def main():
                                    (1 + 8) * 29 * n * 32 / 1e9),
                                parallelism=pv.parallelism()),
                 "proof_gen_s": ms_per_step * 1e-3, "proof_bytes": len(proof) if proof else None,
-                "stage_ms": {s: round(float(v), 4) for s, v in zip(STAGES, stage_ms)},
+                "stage_ms": ({s: round(float(v), 4) for s, v in zip(STAGES, stage_ms)} if world == 1 else
+                             {k: v[0] for k, v in sharded_stages.items()}),
+                "stage_host_ms": None if world == 1 else {k: v[1] for k, v in sharded_stages.items()},
                 "algorithmic_muls_per_step": muls,
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
         # dominant kernel: k_ntt_pass (all launches of the two LDE stages); every launch reads and writes each

@@ -160,6 +160,13 @@ int spg_stage_fri_fold(spg_ctx* ctx, const uint64_t* in, unsigned log_rows, int 
                        const uint64_t* beta, int layer_index, uint64_t* out);
 int spg_stage_open(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, int n_cosets, const uint8_t* tree,
                    const uint32_t* idx, int count, uint8_t* leaves_out, uint8_t* paths_out);
+/* host-side checks the driver runs between stages (the same routines spg_prove uses): the composition identity at the
+ * out-of-domain point (oods: [54][4] canonical), and the interpolation + low-degree check of the last FRI layer
+ * (vals: [8][2^log_rows_last][4] raw Montgomery limbs as stored on the device, coset-major; coeffs_out: 32 bytes per
+ * coefficient in the proof's serialisation).  Both return SPG_E_PROOF when the trace does not satisfy the AIR. */
+int spg_stage_check_oods(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* x0, const uint64_t* outs,
+                         const uint64_t* alpha, const uint64_t* z, const uint64_t* oods);
+int spg_stage_last_layer(spg_ctx* ctx, const uint64_t* vals, unsigned log_rows_last, int n_folds, uint8_t* coeffs_out);
 
 #ifdef __cplusplus
 }

@@ -249,15 +249,22 @@ Fp spg_air_composition_at_host(unsigned log_n, unsigned chain_log, const AirPubl
   {
     const Fp u512p = fp_sub(fp_pow_u64(u512, 512), one);
     const Fp c = fp_mul(u512p, fp_inv(h_from_small(512)));
-    Fp wr = one;
-    for (int r = 0; r < 512; r++) {
+    // 1 / (u - w^r) for all r with ONE inversion (Montgomery's trick): this check runs once per proof on the host
+    Fp wr[512], den[512], pre[512];
+    wr[0] = one;
+    for (int r = 1; r < 512; r++) wr[r] = fp_mul(wr[r - 1], w512);
+    Fp run = one;
+    for (int r = 0; r < 512; r++) { den[r] = fp_sub(u512, wr[r]); pre[r] = run; run = fp_mul(run, den[r]); }
+    Fp inv_run = fp_inv(run);
+    for (int r = 511; r >= 0; r--) {
+      const Fp inv_r = fp_mul(inv_run, pre[r]);
+      inv_run = fp_mul(inv_run, den[r]);
       const int e = r >> 8, t = r & 255;
       if (t < SPG_HASH_BITS) {
-        const Fp lr = fp_mul(fp_mul(c, wr), fp_inv(fp_sub(u512, wr)));
+        const Fp lr = fp_mul(fp_mul(c, wr[r]), inv_r);
         px = fp_add(px, fp_mul(lr, cpts[2 * (2 + SPG_HASH_BITS * e + t)]));
         py = fp_add(py, fp_mul(lr, cpts[2 * (2 + SPG_HASH_BITS * e + t) + 1]));
       }
-      wr = fp_mul(wr, w512);
     }
   }
   Fp acc = fp_zero();

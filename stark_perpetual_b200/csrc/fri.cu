@@ -225,3 +225,45 @@ int spg_poly_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* const* h_cols, 
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
 }
+
+// ------------------------------------------------------------------ last FRI layer (host)
+// in-place radix-2 inverse NTT on the host (natural order in and out), n = 2^log_n
+static void host_intt(std::vector<Fp>& a, int log_n) {
+  const size_t n = a.size();
+  for (size_t i = 0; i < n; i++) { size_t r = spg_bitrev((unsigned)i, log_n); if (r > i) std::swap(a[i], a[r]); }
+  const Fp w = fp_inv(spg_host_root_of_unity(log_n));
+  for (size_t h = 1; h < n; h *= 2) {
+    const Fp wh = fp_pow_u64(w, n / (2 * h));
+    for (size_t b = 0; b < n; b += 2 * h) {
+      Fp t = fp_one();
+      for (size_t k = 0; k < h; k++) {
+        const Fp u = a[b + k], v = fp_mul(a[b + k + h], t);
+        a[b + k] = fp_add(u, v); a[b + k + h] = fp_sub(u, v);
+        t = fp_mul(t, wh);
+      }
+    }
+  }
+  uint64_t nn[4] = {(uint64_t)n, 0, 0, 0};
+  const Fp ninv = fp_inv(spg_host_from_u64(nn));
+  for (auto& x : a) x = fp_mul(x, ninv);
+}
+
+// vals: the last layer [8 cosets][n_last] (Montgomery) on the domain g_l * <w_{8 n_last}>, g_l = 3^(8^n_folds).
+// Interpolates it; returns false unless the upper 7/8 of the coefficients vanish; coeffs receives the n_last
+// low ones (what the proof carries).
+bool spg_fri_last_layer_host(const std::vector<Fp>& vals, unsigned log_rows_last, int n_folds, std::vector<Fp>& coeffs) {
+  const size_t n_last = (size_t)1 << log_rows_last;
+  std::vector<Fp> flat(8 * n_last);
+  for (size_t j = 0; j < 8; j++) for (size_t i = 0; i < n_last; i++) flat[j + 8 * i] = vals[j * n_last + i];
+  host_intt(flat, (int)log_rows_last + 3);
+  uint64_t three[4] = {3, 0, 0, 0};
+  Fp g_l = spg_host_from_u64(three);
+  for (int k = 0; k < 3 * n_folds; k++) g_l = fp_sqr(g_l);
+  const Fp gli = fp_inv(g_l);
+  Fp s = fp_one();
+  for (size_t k = 0; k < flat.size(); k++) { flat[k] = fp_mul(flat[k], s); s = fp_mul(s, gli); }
+  for (size_t k = n_last; k < flat.size(); k++)
+    if (!fp_is_zero(flat[k])) return false;
+  coeffs.assign(flat.begin(), flat.begin() + n_last);
+  return true;
+}

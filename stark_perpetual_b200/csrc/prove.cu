@@ -72,27 +72,6 @@ struct Arena {
   }
 };
 
-// in-place radix-2 inverse NTT on the host (natural order in and out), n = 2^log_n
-static void host_intt(std::vector<Fp>& a, int log_n) {
-  const size_t n = a.size();
-  for (size_t i = 0; i < n; i++) { size_t r = spg_bitrev((unsigned)i, log_n); if (r > i) std::swap(a[i], a[r]); }
-  const Fp w = fp_inv(spg_host_root_of_unity(log_n));
-  for (size_t h = 1; h < n; h *= 2) {
-    const Fp wh = fp_pow_u64(w, n / (2 * h));
-    for (size_t b = 0; b < n; b += 2 * h) {
-      Fp t = fp_one();
-      for (size_t k = 0; k < h; k++) {
-        const Fp u = a[b + k], v = fp_mul(a[b + k + h], t);
-        a[b + k] = fp_add(u, v); a[b + k + h] = fp_sub(u, v);
-        t = fp_mul(t, wh);
-      }
-    }
-  }
-  uint64_t nn[4] = {(uint64_t)n, 0, 0, 0};
-  const Fp ninv = fp_inv(spg_host_from_u64(nn));
-  for (auto& x : a) x = fp_mul(x, ninv);
-}
-
 enum { ST_LDE = 0, ST_MERKLE_T, ST_AIR, ST_HLDE, ST_MERKLE_H, ST_OODS, ST_DEEP, ST_FRI, ST_QUERY, ST_H2D };
 
 // d_trace: [25][N] canonical felts on the device.  Appends the proof to `proof`.
@@ -255,21 +234,18 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
     }
     spg_stage_end(ctx, ST_FRI);
     put_bytes(proof, fri_roots.data(), fri_roots.size());
-    // last layer -> coefficients
+    // last layer -> coefficients (host: at most 512 values)
     const unsigned lr = log_rows[n_folds];
     const size_t n_last = (size_t)1 << lr;
-    std::vector<Fp> vals(8 * n_last), flat(8 * n_last);
+    std::vector<Fp> vals(8 * n_last), coeffs;
     SPG_CUDA(cudaMemcpyAsync(vals.data(), layers[n_folds], vals.size() * sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (size_t j = 0; j < 8; j++) for (size_t i = 0; i < n_last; i++) flat[j + 8 * i] = vals[j * n_last + i];
-    host_intt(flat, (int)lr + 3);
-    const Fp gli = fp_inv(g_l);
-    Fp s = fp_one();
-    for (size_t k = 0; k < flat.size(); k++) { flat[k] = fp_mul(flat[k], s); s = fp_mul(s, gli); }
-    for (size_t k = n_last; k < flat.size(); k++)
-      if (!fp_is_zero(flat[k])) { ctx->err = "trace does not satisfy the AIR (FRI last layer is not of low degree)"; return SPG_E_PROOF; }
+    if (!spg_fri_last_layer_host(vals, lr, n_folds, coeffs)) {
+      ctx->err = "trace does not satisfy the AIR (FRI last layer is not of low degree)";
+      return SPG_E_PROOF;
+    }
     std::vector<uint8_t> b;
-    for (size_t k = 0; k < n_last; k++) put_fp(b, flat[k]);
+    for (size_t k = 0; k < n_last; k++) put_fp(b, coeffs[k]);
     ch.absorb(b.data(), b.size());
     put_bytes(proof, b.data(), b.size());
   }

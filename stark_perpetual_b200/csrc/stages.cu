@@ -113,3 +113,45 @@ extern "C" int spg_stage_open(spg_ctx* ctx, const uint64_t* table, size_t n_cols
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
 }
+
+// Prover self-check at the out-of-domain point (host arithmetic, the same routine spg_prove uses): recompute the
+// composition from the 25 + 25 trace values at z and z*w and compare with sum z^m H_m(z^4).  oods: [54][4]
+// canonical.  SPG_E_PROOF when the trace does not satisfy the AIR.
+extern "C" int spg_stage_check_oods(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* x0, const uint64_t* outs,
+                                    const uint64_t* alpha, const uint64_t* z, const uint64_t* oods) {
+  SPG_ARG(ctx && x0 && outs && alpha && z && oods, "spg_stage_check_oods: null");
+  const int C = SPG_AIR_COLS;
+  AirPublic pub;
+  for (int l = 0; l < SPG_AIR_LANES; l++) { pub.x0[l] = spg_host_from_u64(x0 + 4 * l); pub.outs[l] = spg_host_from_u64(outs + 4 * l); }
+  Fp apows[SPG_AIR_LANES * SPG_AIR_NCONSTR], o[SPG_N_OODS];
+  const Fp a = spg_host_from_u64(alpha), zz = spg_host_from_u64(z);
+  apows[0] = fp_one();
+  for (int k = 1; k < SPG_AIR_LANES * SPG_AIR_NCONSTR; k++) apows[k] = fp_mul(apows[k - 1], a);
+  for (int k = 0; k < SPG_N_OODS; k++) o[k] = spg_host_from_u64(oods + 4 * k);
+  const Fp lhs = spg_air_composition_at_host(log_n, chain_log, pub, apows, zz, o, o + C, ctx->h_const_points);
+  Fp rhs = fp_zero(), zp = fp_one();
+  for (int m = 0; m < 4; m++) { rhs = fp_add(rhs, fp_mul(zp, o[2 * C + m])); zp = fp_mul(zp, zz); }
+  if (!fp_eq(lhs, rhs)) { ctx->err = "trace does not satisfy the AIR (composition mismatch at the out-of-domain point)"; return SPG_E_PROOF; }
+  return SPG_OK;
+}
+
+// Last FRI layer: vals = [8][2^log_rows_last][4] raw device representation (Montgomery) gathered from all ranks,
+// coset-major.  Writes the 2^log_rows_last proof coefficients (32 bytes each, proof serialisation) to coeffs_out;
+// SPG_E_PROOF when the layer is not of low degree.
+extern "C" int spg_stage_last_layer(spg_ctx* ctx, const uint64_t* vals, unsigned log_rows_last, int n_folds, uint8_t* coeffs_out) {
+  SPG_ARG(ctx && vals && coeffs_out && log_rows_last <= 6 && n_folds >= 0 && n_folds < 16, "spg_stage_last_layer");
+  const size_t n_last = (size_t)1 << log_rows_last;
+  std::vector<Fp> v(8 * n_last), coeffs;
+  memcpy(v.data(), vals, v.size() * sizeof(Fp));
+  if (!spg_fri_last_layer_host(v, log_rows_last, n_folds, coeffs)) {
+    ctx->err = "trace does not satisfy the AIR (FRI last layer is not of low degree)";
+    return SPG_E_PROOF;
+  }
+  for (size_t k = 0; k < n_last; k++)
+    for (int w = 0; w < 8; w++) {
+      const uint32_t x = coeffs[k].v[7 - w];
+      coeffs_out[32 * k + 4 * w] = (uint8_t)(x >> 24); coeffs_out[32 * k + 4 * w + 1] = (uint8_t)(x >> 16);
+      coeffs_out[32 * k + 4 * w + 2] = (uint8_t)(x >> 8); coeffs_out[32 * k + 4 * w + 3] = (uint8_t)x;
+    }
+  return SPG_OK;
+}

@@ -44,6 +44,9 @@ int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp
 int spg_poly_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* const* h_cols, const int* h_pt_idx, int n_items,
                          const Fp* h_pts, int n_pts, Fp* h_out);
 
+// last FRI layer on the host: see fri.cu
+bool spg_fri_last_layer_host(const std::vector<Fp>& vals, unsigned log_rows_last, int n_folds, std::vector<Fp>& coeffs);
+
 // ---- air.cu
 struct AirPublic {
   Fp x0[SPG_AIR_LANES], outs[SPG_AIR_LANES];   // Montgomery

@@ -19,7 +19,7 @@ import hashlib
 
 import numpy as np
 
-from ._lib import FIELD_PRIME as P, SPG_DEVICE_PTRS, ints_to_limbs, limbs_to_ints
+from ._lib import FIELD_PRIME as P, SPG_DEVICE_PTRS, SPG_NO_SYNC, ints_to_limbs, limbs_to_ints
 
 R_MOD_P = (1 << 256) % P
 LANES, N_COLS, N_CONSTR, BLOWUP, LOG_BLOWUP, GEN = 5, 25, 13, 8, 3, 3
@@ -162,6 +162,7 @@ class GpuBackend:
         import torch
         self.torch, self.ctx, self.lib, self.h = torch, ctx, ctx._lib, ctx._h
         self.dev = torch.device("cuda", ctx.device)
+        self._ticks = []
         # stage kernels and torch's collectives must be ordered on one stream
         with torch.cuda.device(self.dev):
             ctx.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -176,12 +177,33 @@ class GpuBackend:
             "spg_stage_fri_fold": [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
             "spg_stage_open": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                C.c_void_p, C.c_void_p],
+            "spg_stage_check_oods": [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+            "spg_stage_last_layer": [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_void_p],
         }.items():
             fn = getattr(self.lib, name)
             fn.restype, fn.argtypes = C.c_int, args
 
     def _chk(self, rc):
         self.ctx._check(rc)
+
+    # ---- optional stage timing (device events on the shared stream + host clock), read by bench.py
+    def tick(self, name):
+        import time
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.torch.cuda.current_stream())
+        self._ticks.append((name, ev, time.perf_counter()))
+
+    def reset_ticks(self):
+        self._ticks = []
+
+    def stage_times(self):
+        """{stage: (device ms, host wall ms)} between consecutive ticks of the last proof"""
+        self.torch.cuda.synchronize()
+        out = {}
+        for (n0, e0, t0), (_n1, e1, t1) in zip(self._ticks, self._ticks[1:]):
+            d, w = out.get(n0, (0.0, 0.0))
+            out[n0] = (d + e0.elapsed_time(e1), w + 1e3 * (t1 - t0))
+        return out
 
     @staticmethod
     def _felts(values):
@@ -196,12 +218,12 @@ class GpuBackend:
 
     def lde_coeffs(self, cols, log_n, n_cols, out, offset=None, mont=False):
         keep, op = self._felts([offset]) if offset is not None else (None, None)
-        flags = SPG_DEVICE_PTRS | (SPG_MONT_OUT if mont else 0)
+        flags = SPG_DEVICE_PTRS | SPG_NO_SYNC | (SPG_MONT_OUT if mont else 0)      # stream-ordered with what follows
         self._chk(self.lib.spg_lde_coeffs(self.h, C.c_void_p(cols.data_ptr()), log_n, n_cols, op, C.c_void_p(out.data_ptr()), flags))
 
     def lde_cosets(self, coeffs, log_n, n_cols, first, count, out):
         self._chk(self.lib.spg_lde_cosets(self.h, C.c_void_p(coeffs.data_ptr()), log_n, n_cols, LOG_BLOWUP, first, count,
-                                          C.c_void_p(out.data_ptr()), SPG_DEVICE_PTRS))
+                                          C.c_void_p(out.data_ptr()), SPG_DEVICE_PTRS | SPG_NO_SYNC))
 
     def merkle(self, table, n_cols, rows, n_cosets):
         n_leaves = rows // 8 * n_cosets
@@ -210,7 +232,35 @@ class GpuBackend:
         return tree
 
     def root(self, tree):
-        return tree[-32:].cpu().numpy().tobytes()
+        """The sub-tree root as a 32-byte tensor on the backend's device (gathered with one small collective)."""
+        return tree[-32:]
+
+    def check_oods(self, log_n, chain_log, x0, outs, alpha, z, oods):
+        """Prover self-check CP(z) == sum z^m H_m(z^4), host arithmetic inside libspg."""
+        k1, p1 = self._felts(x0); k2, p2 = self._felts(outs); k3, p3 = self._felts([alpha]); k4, p4 = self._felts([z])
+        k5, p5 = self._felts(oods)
+        rc = self.lib.spg_stage_check_oods(self.h, log_n, chain_log, p1, p2, p3, p4, p5)
+        if rc == -5:
+            raise ProofError(self.lib.spg_last_error(self.h).decode())
+        self._chk(rc)
+
+    def table_bytes(self, t):
+        """raw device representation of a small table (the last FRI layer), for the cross-rank gather"""
+        return t.reshape(-1).cpu().numpy().tobytes()
+
+    def last_layer(self, parts, log_rows_last, n_folds):
+        """parts: table_bytes of every rank in rank order (= coset-major [8][n_last]).  Returns the serialised
+        low coefficients; raises ProofError when the layer is not of low degree."""
+        raw = np.frombuffer(b"".join(parts), dtype=np.uint64).copy()
+        n_last = 1 << log_rows_last
+        assert raw.size == 8 * n_last * 4
+        out = np.empty(n_last * 32, dtype=np.uint8)
+        rc = self.lib.spg_stage_last_layer(self.h, raw.ctypes.data_as(C.c_void_p), log_rows_last, n_folds,
+                                           out.ctypes.data_as(C.c_void_p))
+        if rc == -5:
+            raise ProofError(self.lib.spg_last_error(self.h).decode())
+        self._chk(rc)
+        return out.tobytes()
 
     def air(self, t_lde, log_n, chain_log, first, jj0, n_even, x0, outs, alpha, cp):
         k1, p1 = self._felts(x0); k2, p2 = self._felts(outs); k3, p3 = self._felts([alpha])
@@ -298,6 +348,18 @@ class TorchComm:
             import torch.distributed as dist
             dist.broadcast(t, src)
 
+    def all_gather_bytes(self, t):
+        """t: a small uint8 tensor on the collective's device (same length on every rank) -> list of bytes per rank"""
+        if self.world == 1:
+            return [t.cpu().numpy().tobytes()]
+        import torch
+        import torch.distributed as dist
+        out = torch.empty(self.world * t.numel(), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        raw = out.cpu().numpy().tobytes()
+        k = t.numel()
+        return [raw[r * k:(r + 1) * k] for r in range(self.world)]
+
     def all_gather_obj(self, obj):
         if self.world == 1:
             return [obj]
@@ -324,29 +386,36 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
     seed = (log_n.to_bytes(4, "little") + chain_log.to_bytes(4, "little") + n_queries.to_bytes(4, "little")
             + b"".join(ser(v) for v in x0) + b"".join(ser(v) for v in outs))
     ch = Channel(seed)
+    tick = getattr(be, "tick", lambda name: None)
+    if hasattr(be, "reset_ticks"):
+        be.reset_ticks()
     proof = [b"SPGP", (1).to_bytes(4, "little"), log_n.to_bytes(4, "little"), chain_log.to_bytes(4, "little"),
              n_queries.to_bytes(4, "little"), n_folds.to_bytes(4, "little")] + [ser(v) for v in x0] + [ser(v) for v in outs]
 
     def commit(table, n_cols, rows):
         tree = be.merkle(table, n_cols, rows, cs)
-        roots = comm.all_gather_obj(be.root(tree))
+        roots = comm.all_gather_bytes(be.root(tree))
         top = top_levels(roots)
         return tree, top
 
     # 1. interpolation (column-sharded) -> ONE all-gather -> coset evaluation (coset-sharded) + commitment
+    tick("interpolate")
     mine = be.felts(per, n)
     if my_cols:
         be.lde_coeffs(trace_cols_local, log_n, my_cols, mine, mont=True)
     coefs = be.felts(per * world, n)
+    tick("all_gather_coeffs")
     comm.all_gather_into(coefs, mine)
+    tick("lde_trace")
     t_lde = be.felts(cs, N_COLS, n)
     be.lde_cosets(coefs, log_n, N_COLS, first, cs, t_lde)
+    tick("merkle_trace")
     tree_t, top_t = commit(t_lde, N_COLS, n)
     root_t = top_t[-1][0]
     ch.absorb(root_t)
     # 2. composition on the even cosets this rank owns; chunk split; chunk exchange; chunk LDE + commitment
+    tick("air_composition")
     alpha = ch.draw_felt()
-    apows = [pow(alpha, k, P) for k in range(LANES * N_CONSTR)]
     even = [jj for jj in range(4) if first <= 2 * jj < first + cs]
     hev = be.felts(4, n)
     if even:
@@ -354,36 +423,39 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
         be.air(t_lde, log_n, chain_log, first, even[0], len(even), x0, outs, alpha, cp)
         be.cp_split(cp, log_n, even[0], len(even), hev)
     hv = hev.view(4, n // 4, 4, 4)
+    tick("chunk_exchange")
     if world > 1:
         for jj in range(4):
             piece = hv[:, :, jj, :].contiguous()
             comm.broadcast(piece, (2 * jj) // cs)
             hv[:, :, jj, :] = piece
+    tick("lde_chunks")
     h_coef = be.felts(4, n)
     be.lde_coeffs(hev, log_n, 4, h_coef, offset=pow(GEN, -3, P), mont=False)
     h_lde = be.felts(cs, 4, n)
     be.lde_cosets(h_coef, log_n, 4, first, cs, h_lde)
+    tick("merkle_chunks")
     tree_h, top_h = commit(h_lde, 4, n)
     root_h = top_h[-1][0]
     ch.absorb(root_h)
     # 3. out-of-domain values (every rank holds all coefficient columns)
+    tick("oods_eval")
     z = ch.draw_felt()
     wn = root_of_unity(log_n)
     zw, z4 = z * wn % P, pow(z, 4, P)
     cols = [coefs[c] for c in range(N_COLS)] * 2 + [h_coef[m] for m in range(4)]
     oods = be.poly_eval(cols, [0] * N_COLS + [1] * N_COLS + [2] * 4, [z, zw, z4], log_n)
     if check:
-        cpts = be.const_points()
-        lhs = composition_at(log_n, chain_log, x0, outs, apows, z, oods[:25], oods[25:50], cpts, cpts[0])
-        if lhs != sum(pow(z, m, P) * oods[50 + m] for m in range(4)) % P:
-            raise ProofError("trace does not satisfy the AIR (composition mismatch at the out-of-domain point)")
+        be.check_oods(log_n, chain_log, x0, outs, alpha, z, oods)
     ob = b"".join(ser(v) for v in oods)
     ch.absorb(ob)
     # 4. DEEP quotient on the local cosets
+    tick("deep_quotient")
     gamma = ch.draw_felt()
     layers, trees, tops = [be.felts(cs, n)], [None], [None]
     be.deep(t_lde, h_lde, log_n, first, cs, z, gamma, oods, layers[0])
     # 5. FRI
+    tick("fri")
     fri_roots = []
     for l in range(1, n_folds + 1):
         beta = ch.draw_felt()
@@ -393,22 +465,12 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
         layers.append(nxt); trees.append(tree); tops.append(top)
         fri_roots.append(top[-1][0])
         ch.absorb(top[-1][0])
-    n_last = 1 << log_rows[-1]
-    parts = comm.all_gather_obj(be.download_ints(layers[-1]))          # [cs * n_last] per rank, coset-major
-    flat = [0] * (8 * n_last)
-    for r, part in enumerate(parts):
-        for jl in range(cs):
-            for i in range(n_last):
-                flat[(r * cs + jl) + 8 * i] = part[jl * n_last + i]
-    lc = host_intt(flat, log_rows[-1] + 3)
-    gli = pow(pow(GEN, 8 ** n_folds, P), -1, P)
-    lc = [c * pow(gli, k, P) % P for k, c in enumerate(lc)]
-    if any(lc[n_last:]):
-        raise ProofError("trace does not satisfy the AIR (FRI last layer is not of low degree)")
-    lb = b"".join(ser(v) for v in lc[:n_last])
+    parts = comm.all_gather_obj(be.table_bytes(layers[-1]))             # <= 16 KB per rank, coset-major
+    lb = be.last_layer(parts, log_rows[-1], n_folds)
     ch.absorb(lb)
     proof += [root_t, root_h, ob] + fri_roots + [lb]
     # 6. queries: every rank opens the leaves that live in its cosets
+    tick("queries")
     tables = [(t_lde, N_COLS, n, tree_t, top_t), (h_lde, 4, n, tree_h, top_h)]
     tables += [(layers[l], 1, 1 << log_rows[l], trees[l], tops[l]) for l in range(1, n_folds + 1)]
     qidx = []                              # per query, per table: (j, i')
@@ -435,6 +497,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
             leaf, path = all_open[(q, t)]
             owner = qidx[q][t][0] // cs
             proof += [leaf, path] + top_path(top, owner)
+    tick("end")
     return b"".join(proof)
 
 

@@ -64,7 +64,34 @@ class CpuBackend:
         return {"levels": levels, "leaves": leaves}
 
     def root(self, tree):
-        return tree["levels"][-1][0]
+        return torch.from_numpy(np.frombuffer(tree["levels"][-1][0], dtype=np.uint8).copy())
+
+    def check_oods(self, log_n, chain_log, x0, outs, alpha, z, oods):
+        from stark_perpetual_b200 import prover
+        apows = [pow(alpha, k, P) for k in range(65)]
+        lhs = prover.composition_at(log_n, chain_log, x0, outs, apows, z, oods[:25], oods[25:50], CONSTANT_POINTS,
+                                    CONSTANT_POINTS[0])
+        if lhs != sum(pow(z, m, P) * oods[50 + m] for m in range(4)) % P:
+            raise prover.ProofError("trace does not satisfy the AIR (composition mismatch at the out-of-domain point)")
+
+    def table_bytes(self, t):
+        return b"".join(v.to_bytes(32, "little") for v in self._get(t))
+
+    def last_layer(self, parts, log_rows_last, n_folds):
+        from stark_perpetual_b200 import prover
+        n_last = 1 << log_rows_last
+        raw = b"".join(parts)
+        vals = [int.from_bytes(raw[32 * k:32 * k + 32], "little") for k in range(8 * n_last)]     # [8][n_last]
+        flat = [0] * (8 * n_last)
+        for j in range(8):
+            for i in range(n_last):
+                flat[j + 8 * i] = vals[j * n_last + i]
+        lc = prover.host_intt(flat, log_rows_last + 3)
+        gli = pow(pow(GEN, 8 ** n_folds, P), -1, P)
+        lc = [c * pow(gli, k, P) % P for k, c in enumerate(lc)]
+        if any(lc[n_last:]):
+            raise prover.ProofError("trace does not satisfy the AIR (FRI last layer is not of low degree)")
+        return b"".join(stark.ser(v) for v in lc[:n_last])
 
     def air(self, t_lde, log_n, chain_log, first, jj0, n_even, x0, outs, alpha, cp):
         n = 1 << log_n
