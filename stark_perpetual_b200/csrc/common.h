@@ -14,6 +14,10 @@ struct spg_ctx {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host-trace upload pipelined against the LDE (spg_prove with host buffers): copy stream + per-chunk events
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[8] = {nullptr};
+  cudaEvent_t copy_gate = nullptr;
   double last_ms = 0.0;
   uint64_t launches = 0;
   std::string err;
@@ -164,5 +168,6 @@ int spg_lde_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, unsi
 // the two phases; mont != 0 additionally multiplies by R = 2^256 (canonical input -> Montgomery output)
 int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, const uint64_t* offset_canon,
                           Fp* coeffs, int mont = 0);
+// out_C / col0: the given columns are columns [col0, col0 + C) of a table with out_C columns per coset (0 = C)
 int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t C, unsigned log_blowup, size_t j0,
-                          size_t nj, Fp* out);
+                          size_t nj, Fp* out, size_t out_C = 0, size_t col0 = 0);

@@ -95,6 +95,9 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
   for (void* p : ctx->owned) cudaFree(p);
   for (void* p : ctx->scratch_p) cudaFree(p);
   for (auto& b : ctx->pool) cudaFree(b.p);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
+  if (ctx->copy_gate) cudaEventDestroy(ctx->copy_gate);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (auto& e : ctx->stage_ev) { if (e[0]) cudaEventDestroy(e[0]); if (e[1]) cudaEventDestroy(e[1]); }

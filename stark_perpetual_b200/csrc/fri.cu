@@ -61,17 +61,21 @@ __global__ void __launch_bounds__(256) k_deep(unsigned log_n, const Fp* __restri
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n_cosets * n) return;
   const size_t j = idx >> log_n, i = idx & (n - 1);
-  Fp a = fp_zero(), b = fp_zero(), c = fp_zero();
+  // sum_c gamma^(25+c) T_c = gamma^25 * sum_c gamma^c T_c: one pass over the 25 columns serves both quotients.
+  // Lazy accumulation (fp.cuh): products are below 2p, twelve of them are summed before a partial reduction.
+  Fp a = fp_zero(), c = fp_zero();
   const Fp* tp = t_lde + (j * SPG_AIR_COLS << log_n) + i;
 #pragma unroll 5
   for (int col = 0; col < SPG_AIR_COLS; col++) {
-    const Fp v = tp[(size_t)col << log_n];
-    a = fp_add(a, fp_mul(v, gamma[col]));
-    b = fp_add(b, fp_mul(v, gamma[SPG_AIR_COLS + col]));
+    a = fp_add_raw(a, fp_mul_lazy(tp[(size_t)col << log_n], gamma[col]));
+    if (col % 12 == 11) a = fp_partial(a);
   }
+  a = fp_partial(a);
+  Fp b = fp_mul(a, gamma[SPG_AIR_COLS]);
   const Fp* hp = h_lde + (j * 4 << log_n) + i;
 #pragma unroll
-  for (int m = 0; m < 4; m++) c = fp_add(c, fp_mul(hp[(size_t)m << log_n], gamma[2 * SPG_AIR_COLS + m]));
+  for (int m = 0; m < 4; m++) c = fp_add_raw(c, fp_mul_lazy(hp[(size_t)m << log_n], gamma[2 * SPG_AIR_COLS + m]));
+  c = fp_partial(c);
   a = fp_sub(a, K[0]); b = fp_sub(b, K[1]); c = fp_sub(c, K[2]);
   const Fp i1 = inv3[idx], i2 = inv3[idx + (size_t)n_cosets * n], i3 = inv3[idx + 2 * (size_t)n_cosets * n];
   Fp q = fp_add(fp_add(fp_mul(a, i1), fp_mul(b, i2)), fp_mul(c, i3));

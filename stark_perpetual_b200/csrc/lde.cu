@@ -60,7 +60,8 @@ int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t 
 // phase B: scaled coefficients -> evaluations on cosets [j0, j0 + nj) of the 2^log_blowup cosets;
 // out[(j - j0)][c][i]
 int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t C, unsigned log_blowup, size_t j0,
-                          size_t nj, Fp* out) {
+                          size_t nj, Fp* out, size_t out_C, size_t col0) {
+  if (out_C == 0) out_C = C;     // the columns given are the whole table
   SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG, "spg_lde: log_n + log_blowup above 26");
   SPG_ARG(j0 + nj <= ((size_t)1 << log_blowup), "spg_lde: coset range");
   const size_t n = (size_t)1 << log_n;
@@ -68,7 +69,7 @@ int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t
     const unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
     for (size_t c0 = 0; c0 < C; c0 += 32768) {
       const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
-      int rc = spg_ntt_device(ctx, coeffs + c0 * n, out + ((j - j0) * C + c0) * n, log_n, nc, n, n, /*inverse=*/0,
+      int rc = spg_ntt_device(ctx, coeffs + c0 * n, out + ((j - j0) * out_C + col0 + c0) * n, log_n, nc, n, n, /*inverse=*/0,
                               /*dit=*/1, coset_exp, nullptr, nullptr);
       if (rc) return rc;
     }

@@ -75,8 +75,11 @@ struct Arena {
 enum { ST_LDE = 0, ST_MERKLE_T, ST_AIR, ST_HLDE, ST_MERKLE_H, ST_OODS, ST_DEEP, ST_FRI, ST_QUERY, ST_H2D };
 
 // d_trace: [25][N] canonical felts on the device.  Appends the proof to `proof`.
+// h_trace (optional): the same trace in HOST memory; it is then uploaded into d_trace in column chunks on a
+// second stream while the LDE of the chunks already on the device runs (every column's transforms depend on that
+// column only), so the host->device copy of the end-to-end path hides behind the first stage.
 static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigned chain_log, const uint64_t* x0_canon,
-                        unsigned n_queries, std::vector<uint8_t>& proof) {
+                        unsigned n_queries, std::vector<uint8_t>& proof, const Fp* h_trace = nullptr) {
   SPG_ARG(log_n >= 9 && log_n + SPG_LOG_BLOWUP <= SPG_UNI_LOG, "spg_prove: log_n must be in [9, 23]");
   SPG_ARG(9 + chain_log <= log_n, "spg_prove: chain_log");
   SPG_ARG(n_queries >= 1 && n_queries <= 1024, "spg_prove: n_queries");
@@ -112,9 +115,28 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
 
   // ---- public input, channel
   Fp h_last[SPG_AIR_LANES];
-  for (int l = 0; l < SPG_AIR_LANES; l++)
-    SPG_CUDA(cudaMemcpyAsync(&h_last[l], d_trace + ((size_t)(5 * l) << log_n) + (n - 1), sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int n_chunks = 5, chunk_cols = C / n_chunks;
+  if (h_trace) {
+    for (int l = 0; l < SPG_AIR_LANES; l++) h_last[l] = h_trace[((size_t)(5 * l) << log_n) + (n - 1)];
+    if (!ctx->copy_stream) {
+      SPG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (auto& e : ctx->copy_ev) SPG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      SPG_CUDA(cudaEventCreateWithFlags(&ctx->copy_gate, cudaEventDisableTiming));
+    }
+    // the upload buffer may still be read by the previous call's kernels
+    SPG_CUDA(cudaEventRecord(ctx->copy_gate, ctx->stream));
+    SPG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
+    for (int k = 0; k < n_chunks; k++) {
+      const size_t off = ((size_t)k * chunk_cols) << log_n;
+      SPG_CUDA(cudaMemcpyAsync((Fp*)d_trace + off, h_trace + off, ((size_t)chunk_cols << log_n) * sizeof(Fp),
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+      SPG_CUDA(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
+    }
+  } else {
+    for (int l = 0; l < SPG_AIR_LANES; l++)
+      SPG_CUDA(cudaMemcpyAsync(&h_last[l], d_trace + ((size_t)(5 * l) << log_n) + (n - 1), sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   AirPublic pub;
   for (int l = 0; l < SPG_AIR_LANES; l++) {
     pub.x0[l] = spg_host_from_u64(x0_canon + 4 * l);
@@ -135,7 +157,16 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
   uint8_t root[32];
   // ---- 1. trace LDE (canonical in, Montgomery out) + commitment
   spg_stage_begin(ctx, ST_LDE);
-  if ((rc = spg_lde_device(ctx, d_trace, log_n, C, SPG_LOG_BLOWUP, nullptr, t_lde, t_coef, /*mont=*/1))) return rc;
+  if (h_trace) {
+    for (int k = 0; k < n_chunks; k++) {
+      const size_t c0 = (size_t)k * chunk_cols, off = c0 << log_n;
+      SPG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
+      if ((rc = spg_lde_coeffs_device(ctx, d_trace + off, log_n, chunk_cols, nullptr, t_coef + off, /*mont=*/1))) return rc;
+      if ((rc = spg_lde_cosets_device(ctx, t_coef + off, log_n, chunk_cols, SPG_LOG_BLOWUP, 0, SPG_BLOWUP, t_lde, C, c0))) return rc;
+    }
+  } else {
+    if ((rc = spg_lde_device(ctx, d_trace, log_n, C, SPG_LOG_BLOWUP, nullptr, t_lde, t_coef, /*mont=*/1))) return rc;
+  }
   spg_stage_end(ctx, ST_LDE);
   spg_stage_begin(ctx, ST_MERKLE_T);
   if ((rc = spg_merkle_build_device(ctx, t_lde, C, n, tree_t))) return rc;
@@ -311,14 +342,15 @@ extern "C" int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, un
   const size_t n = (size_t)1 << log_n, bytes = (size_t)SPG_AIR_COLS * n * 32;
   const Fp* d_trace = (const Fp*)trace;
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  const Fp* h_trace = nullptr;
   if (!(flags & SPG_DEVICE_PTRS)) {
     void* p;
     SPG_CUDA(spg_scratch(ctx, 2, bytes, &p));
-    SPG_CUDA(cudaMemcpyAsync(p, trace, bytes, cudaMemcpyHostToDevice, ctx->stream));
     d_trace = (const Fp*)p;
+    h_trace = (const Fp*)trace;       // uploaded chunk by chunk inside prove_device, overlapped with the LDE
   }
   std::vector<uint8_t> proof;
-  int rc = prove_device(ctx, d_trace, log_n, chain_log, x0, n_queries, proof);
+  int rc = prove_device(ctx, d_trace, log_n, chain_log, x0, n_queries, proof, h_trace);
   if (rc) return rc;
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
