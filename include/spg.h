@@ -94,6 +94,33 @@ int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r,
 int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv, uint64_t* pub_x, uint64_t* pub_y_or_null,
                                    uint8_t* status, size_t n, int flags);
 
+/* ---- perpetual limit orders (BASELINE.json configs[4]) ------------------------------
+ * Replaces src/services/perpetual/public/perpetual_messages.py:212-286 get_limit_order_msg: field packing and the 4-deep
+ * Pedersen chain run on the device (Cairo twin: src/services/exchange/cairo/signature_message_hashes.cairo:56-91).
+ * Struct of arrays, n entries each; asset ids are canonical felts ([n][4] u64), the other fields have exactly the
+ * widths the reference asserts (perpetual_messages.py:231-236), so only the three id bounds (:226-230) can fail. */
+typedef struct spg_limit_orders {
+  const uint64_t* asset_id_synthetic;    /* [n][4], must be < 2^128 */
+  const uint64_t* asset_id_collateral;   /* [n][4], must be < 2^250 */
+  const uint64_t* asset_id_fee;          /* [n][4], must be < 2^250 */
+  const uint8_t* is_buying_synthetic;    /* [n] */
+  const uint64_t* amount_synthetic;      /* [n] */
+  const uint64_t* amount_collateral;     /* [n] */
+  const uint64_t* max_amount_fee;        /* [n] */
+  const uint64_t* position_id;           /* [n] */
+  const uint32_t* nonce;                 /* [n] */
+  const uint32_t* expiration_timestamp;  /* [n] */
+} spg_limit_orders;
+/* msg_out[i] = get_limit_order_msg(order i).  status[i]: 0 ok; 1 a bound of perpetual_messages.py:226-230 is violated
+ * (the reference raises AssertionError); 2 "Unhashable input." (signature.py:313). */
+int spg_limit_order_msg_batch(spg_ctx* ctx, const spg_limit_orders* orders, uint64_t* msg_out, uint8_t* status, size_t n,
+                              int flags);
+/* verify(get_limit_order_msg(order i), r[i], s[i], pub_x[i]) with x-only keys, the check
+ * src/services/perpetual/cairo/order/order.cairo:132-166 performs per order.  status as spg_ecdsa_verify_batch
+ * (1 valid, 0 invalid, 2 the reference raises -- including a failed order bound or an unhashable message). */
+int spg_limit_order_verify_batch(spg_ctx* ctx, const spg_limit_orders* orders, const uint64_t* r, const uint64_t* s,
+                                 const uint64_t* pub_x, uint8_t* status, size_t n, int flags);
+
 /* ---- NTT over the STARK prime (no reference symbol, field from signature.py:41-42) */
 /* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
  * inverse != 0 uses omega^-1 and scales by 2^-log_n. */

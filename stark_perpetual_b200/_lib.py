@@ -57,6 +57,8 @@ def _load():
             "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_ecdsa_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_private_to_stark_key_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_limit_order_msg_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_limit_order_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_set_stream": (C.c_int, [vp, vp]),
             "spg_stage_ms": (C.c_double, [vp, C.c_int]),
             "spg_lde": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, vp, vp, C.c_int]),
@@ -211,6 +213,39 @@ class Context:
         self._check(self._lib.spg_private_to_stark_key_batch(self._h, _ptr(p), _ptr(out), _ptr(outy) if want_y else None,
                                                              _ptr(st), p.shape[0], 0))
         return (out, outy, st) if want_y else (out, st)
+
+    # ---- perpetual limit orders ----
+    _ORDER_LAYOUT = (("asset_id_synthetic", np.uint64, 4), ("asset_id_collateral", np.uint64, 4), ("asset_id_fee", np.uint64, 4),
+                     ("is_buying_synthetic", np.uint8, 1), ("amount_synthetic", np.uint64, 1), ("amount_collateral", np.uint64, 1),
+                     ("max_amount_fee", np.uint64, 1), ("position_id", np.uint64, 1), ("nonce", np.uint32, 1),
+                     ("expiration_timestamp", np.uint32, 1))
+
+    def _orders_struct(self, arr):
+        """dict of numpy arrays -> (spg_limit_orders as a ctypes pointer array, n, keep-alive list)"""
+        keep, n = [], None
+        for name, dt, width in self._ORDER_LAYOUT:
+            a = np.ascontiguousarray(arr[name], dtype=dt).reshape(-1, width)
+            n = a.shape[0] if n is None else n
+            assert a.shape[0] == n, name
+            keep.append(a)
+        ptrs = (C.c_void_p * len(keep))(*[a.ctypes.data for a in keep])
+        return ptrs, n, keep
+
+    def limit_order_msg(self, arr):
+        """arr: dict of numpy arrays in the spg_limit_orders layout -> (msg (n, 4) uint64, status (n,) uint8)."""
+        ptrs, n, keep = self._orders_struct(arr)
+        out = np.empty((n, 4), dtype=np.uint64)
+        st = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.spg_limit_order_msg_batch(self._h, ptrs, _ptr(out), _ptr(st), n, 0))
+        return out, st
+
+    def limit_order_verify(self, arr, r, s, pub_x):
+        ptrs, n, keep = self._orders_struct(arr)
+        sig = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in (r, s, pub_x)]
+        assert all(a.shape[0] == n for a in sig)
+        st = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.spg_limit_order_verify_batch(self._h, ptrs, _ptr(sig[0]), _ptr(sig[1]), _ptr(sig[2]), _ptr(st), n, 0))
+        return st
 
     # ---- NTT ----
     def ntt(self, data, log_n, inverse=False, order=NTT_NAT_TO_NAT):

@@ -96,6 +96,16 @@ __global__ void __launch_bounds__(128) k_private_to_public(const uint64_t* __res
   status[i] = st;
 }
 
+// device-pointer building block (orders.cu): enqueue the verification kernel on the context stream
+int spg_ecdsa_verify_device(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* px,
+                            const uint64_t* py, uint8_t* status, size_t n) {
+  int rc = ensure_ecdsa_tables(ctx);
+  if (rc) return rc;
+  k_ecdsa_verify<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(msg, r, s, px, py, status, n, make_tables(ctx, true));
+  SPG_LAUNCH_CHECK();
+  return SPG_OK;
+}
+
 extern "C" int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
                                       const uint64_t* pub_x, const uint64_t* pub_y_or_null, uint8_t* status, size_t n,
                                       int flags) {

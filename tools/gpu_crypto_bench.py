@@ -22,7 +22,7 @@ def main():
     out = {}
     for n in (1024, 65536, 1 << 20):
         x, y = rand_felts(n, 21), rand_felts(n, 22)
-        ctx.pedersen_hash2(x[:256], y[:256])
+        ctx.pedersen_hash2(x, y)             # warm-up at this size (pooled device temporaries)
         t0 = time.perf_counter()
         _, st = ctx.pedersen_hash2(x, y)
         wall = time.perf_counter() - t0
@@ -46,7 +46,7 @@ def main():
             a[:, 3] &= np.uint64(0x07ffffffffffffff)       # < 2^251
         px = np.tile(pubs, (n // n_valid, 1))
         msg[:n_valid], r[:n_valid], s[:n_valid] = vm, vr, vs
-        ctx.ecdsa_verify(msg[:256], r[:256], s[:256], px[:256])
+        ctx.ecdsa_verify(msg, r, s, px)      # warm-up at this size
         t0 = time.perf_counter()
         st = ctx.ecdsa_verify(msg, r, s, px)
         wall = time.perf_counter() - t0
@@ -55,6 +55,31 @@ def main():
                                        "verify_per_s_e2e": n / wall, "valid": int((st == 1).sum()),
                                        "invalid": int((st == 0).sum()), "raises": int((st == 2).sum()),
                                        "first_valid_ok": bool((st[:n_valid] == 1).all())}
+    # BASELINE.json configs[4]: 65536 limit orders, packing + 4-deep hash chain + ECDSA in one device pipeline
+    n = 65536
+    g = np.random.Generator(np.random.PCG64(1005))
+    orders = {"asset_id_synthetic": rand_felts(n, 41), "asset_id_collateral": rand_felts(n, 42), "asset_id_fee": rand_felts(n, 43),
+              "is_buying_synthetic": g.integers(0, 2, n, dtype=np.uint8)}
+    orders["asset_id_synthetic"][:, 2:] = 0
+    for f in ("asset_id_collateral", "asset_id_fee"):
+        orders[f][:, 3] &= np.uint64((1 << 58) - 1)
+    for f in ("amount_synthetic", "amount_collateral", "max_amount_fee", "position_id"):
+        orders[f] = g.integers(0, 2**64, n, dtype=np.uint64)
+    for f in ("nonce", "expiration_timestamp"):
+        orders[f] = g.integers(0, 2**32, n, dtype=np.uint32)
+    r, s = rand_felts(n, 32), rand_felts(n, 33)
+    for a in (r, s):
+        a[:, 3] &= np.uint64(0x07ffffffffffffff)
+    px = np.tile(pubs, (n // n_valid, 1))
+    for fn, label, args in ((ctx.limit_order_msg, "limit_order_msg_n65536", (orders,)),
+                            (ctx.limit_order_verify, "limit_order_verify_n65536", (orders, r, s, px))):
+        fn(*args)
+        t0 = time.perf_counter()
+        res = fn(*args)
+        wall = time.perf_counter() - t0
+        st = res[1] if isinstance(res, tuple) else res
+        out[label] = {"kernel_ms": ctx.last_kernel_ms, "wall_ms": wall * 1e3, "orders_per_s_kernel": n / (ctx.last_kernel_ms * 1e-3),
+                      "orders_per_s_e2e": n / wall, "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))}}
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "crypto_bench.json"), "w"), indent=1)
