@@ -21,7 +21,7 @@
         "+r"(acc[7]), "+r"(acc[8])                                                                   \
       : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b))
 
-// MODE 0: two rows, shared multiplier q (reference, measured 2.1 cycles / IMAD.WIDE)
+// MODE 0: two rows, shared multiplier q  (each row is 4 IMAD.WIDE: ptxas fuses every mad.lo.cc / madc.hi.cc pair)
 // MODE 1: multiplier = a limb of the other row (changes every iteration)
 // MODE 2: four rows in flight (more ILP), multiplier from the other row
 // MODE 3: as 1 but 128 registers forced via a big dummy array? (occupancy) -- done through launch bounds instead
@@ -123,7 +123,7 @@ int main() {
   const int sms = prop.multiProcessorCount, threads = 256;
   const double clk = khz * 1e3;
   void* buf; cudaMalloc(&buf, (size_t)sms * 8 * threads * 8);
-  printf("{\"unit\": \"SMSP cycles per warp instruction (IMAD.WIDE rows count 8 per row)\",\n");
+  printf("{\"unit\": \"SMSP cycles per warp instruction; a carry row = 4 mad.lo.cc/madc.hi.cc pairs = 4 IMAD.WIDE[.X] + 1 IADD3.X, counted as 4\",\n");
   for (int bps = 8; bps >= 2; bps /= 2) {      // blocks per SM: 16, 8, 4 warps per SMSP
     const int blocks = sms * bps;
     const double thr = (double)blocks * threads * ITERS;
@@ -131,11 +131,11 @@ int main() {
     float ms;
     printf(" \"warps_per_smsp_%d\": {", bps * 2);
     ms = time_it([&] { k_rows<0><<<blocks, threads>>>((unsigned*)buf, 777u); });
-    printf("\"rows_shared_q\": %.2f, ", cyc(ms, 16));
+    printf("\"rows_shared_q\": %.2f, ", cyc(ms, 8));
     ms = time_it([&] { k_rows<1><<<blocks, threads>>>((unsigned*)buf, 777u); });
-    printf("\"rows_var_mult\": %.2f, ", cyc(ms, 16));
+    printf("\"rows_var_mult\": %.2f, ", cyc(ms, 8));
     ms = time_it([&] { k_rows<2><<<blocks, threads>>>((unsigned*)buf, 777u); });
-    printf("\"rows4_var_mult\": %.2f, ", cyc(ms, 32));
+    printf("\"rows4_var_mult\": %.2f, ", cyc(ms, 16));
     ms = time_it([&] { k_wide_ring<<<blocks, threads>>>((unsigned long long*)buf, 777u); });
     printf("\"mul_wide_ring\": %.2f, ", cyc(ms, 8));
     ms = time_it([&] { k_wide_acc_ring<<<blocks, threads>>>((unsigned long long*)buf, 777u); });
