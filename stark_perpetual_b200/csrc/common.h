@@ -44,6 +44,9 @@ struct spg_ctx {
   // milliseconds, so temporaries of the entry points are kept and reused (all work is ordered on ctx->stream)
   struct PoolBlock { void* p; size_t size; bool in_use; };
   std::vector<PoolBlock> pool;
+  // direct diagonal-twiddle tables of the coset transforms, per (log_n, log_blowup): [2^log_blowup][S][R] (see lde.cu)
+  struct DiagTables { int log_n, log_blowup; Fp* t; };
+  std::vector<DiagTables> diag_tables;
   // LDE scale tables cached per (log_n, offset, mont): lo[R] , hi[B]
   struct LdeTables { int log_n; uint64_t offset[4]; int mont; Fp* lo; Fp* hi; };
   std::vector<LdeTables> lde_tables;
@@ -159,7 +162,9 @@ int spg_from_mont_device(spg_ctx* ctx, Fp* data, size_t n);
 // ntt.cu
 int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
-                   const Fp* scale_lo, const Fp* scale_hi);
+                   const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table = nullptr);
+// ntt.cu: fill a direct diagonal table for the second pass of a two-pass forward DIT with coset exponent coset_exp
+int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, unsigned long long coset_exp, Fp* table);
 int spg_bitrev_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols);
 // lde.cu: device-resident LDE, trace [C][N] -> out [B][C][N]; coeffs (optional) receives the scaled
 // coefficient columns g^k c_k (bit-reversed order)

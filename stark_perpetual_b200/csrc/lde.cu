@@ -57,6 +57,33 @@ int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t 
   return SPG_OK;
 }
 
+// Direct diagonal-twiddle tables for the coset transforms of a two-pass LDE: one N-entry table per coset, built once
+// per (log_n, log_blowup) and kept in the context (8 x 32 MB at 2^20).  A coset's table is re-read by every column of
+// the launch and stays L2-resident; it replaces the two-level lookup's multiplication in the load phase of pass 2.
+static int ensure_diag_tables(spg_ctx* ctx, unsigned log_n, unsigned log_blowup, const Fp** out) {
+  *out = nullptr;
+  if (log_n < 11 || log_n > 20 || log_blowup > 3) return SPG_OK;      // single-pass or three-pass sizes: two-level lookup
+  for (auto& t : ctx->diag_tables)
+    if (t.log_n == (int)log_n && t.log_blowup == (int)log_blowup) { *out = t.t; return SPG_OK; }
+  const size_t n = (size_t)1 << log_n, nb = (size_t)1 << log_blowup;
+  if (ctx->diag_tables.size() >= 2) {
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->diag_tables[0].t);
+    ctx->diag_tables.erase(ctx->diag_tables.begin());
+  }
+  spg_ctx::DiagTables t;
+  t.log_n = (int)log_n; t.log_blowup = (int)log_blowup; t.t = nullptr;
+  if (cudaMalloc((void**)&t.t, nb * n * sizeof(Fp)) != cudaSuccess) { cudaGetLastError(); return SPG_OK; }   // optional
+  for (size_t j = 0; j < nb; j++) {
+    const unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
+    int rc = spg_ntt_build_diag_table(ctx, log_n, coset_exp, t.t + j * n);
+    if (rc) { cudaFree(t.t); return rc; }
+  }
+  ctx->diag_tables.push_back(t);
+  *out = t.t;
+  return SPG_OK;
+}
+
 // phase B: scaled coefficients -> evaluations on cosets [j0, j0 + nj) of the 2^log_blowup cosets;
 // out[(j - j0)][c][i]
 int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t C, unsigned log_blowup, size_t j0,
@@ -65,12 +92,15 @@ int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t
   SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG, "spg_lde: log_n + log_blowup above 26");
   SPG_ARG(j0 + nj <= ((size_t)1 << log_blowup), "spg_lde: coset range");
   const size_t n = (size_t)1 << log_n;
+  const Fp* diag = nullptr;
+  int rc0 = ensure_diag_tables(ctx, log_n, log_blowup, &diag);
+  if (rc0) return rc0;
   for (size_t j = j0; j < j0 + nj; j++) {
     const unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
     for (size_t c0 = 0; c0 < C; c0 += 32768) {
       const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
       int rc = spg_ntt_device(ctx, coeffs + c0 * n, out + ((j - j0) * out_C + col0 + c0) * n, log_n, nc, n, n, /*inverse=*/0,
-                              /*dit=*/1, coset_exp, nullptr, nullptr);
+                              /*dit=*/1, coset_exp, nullptr, nullptr, diag ? diag + j * n : nullptr);
       if (rc) return rc;
     }
   }

@@ -45,9 +45,29 @@ __global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
   out[col * n + spg_bitrev((unsigned)r, (int)log_n)] = in[i];
 }
 
+// diag_table[(c << log_r) | k] = omega_{2^26}^(k * (c * ec + e0)) for the pass P (k = bit-reversed row)
+__global__ void k_build_diag_table(NttPass P, Fp* __restrict__ table) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ((size_t)1 << (P.log_r + P.log_s))) return;
+  const unsigned long long k = idx & ((1ull << P.log_r) - 1), c = idx >> P.log_r;
+  table[idx] = fp_reduce(Tile::uni_pow(P, k * (c * P.ec + P.e0)));
+}
+
+int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, unsigned long long coset_exp, Fp* table) {
+  NttPass passes[8];
+  const int np = spg_ntt_make_passes(passes, NTT_LOG_WS, nullptr, nullptr, log_n, 0, 0, 0, /*dit=*/1, coset_exp, nullptr, nullptr,
+                                     ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
+  SPG_ARG(np == 2, "diag table: two-pass transforms only");
+  const NttPass& P = passes[1];
+  const size_t total = (size_t)1 << (P.log_r + P.log_s);
+  k_build_diag_table<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(P, table);
+  SPG_LAUNCH_CHECK();
+  return SPG_OK;
+}
+
 int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
-                   const Fp* scale_lo, const Fp* scale_hi) {
+                   const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table) {
   SPG_ARG(log_n <= 26, "NTT size above 2^26 not supported by the universal twiddle table");
   SPG_ARG(ncols < 65536, "too many columns in one NTT batch");
   if (ncols == 0) return SPG_OK;
@@ -62,6 +82,7 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
   if (!dit && coset_exp != 0) { ctx->err = "coset shift only supported for DIT"; return SPG_E_ARG; }
   const int np = spg_ntt_make_passes(passes, NTT_LOG_WS, in, out, log_n, in_stride, out_stride, inverse, dit,
                                      coset_exp, scale_lo, scale_hi, ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
+  if (diag_table && np == 2 && dit && !inverse) passes[1].diag_table = diag_table;
   for (int pi = 0; pi < np; pi++) {
     const NttPass& P = passes[pi];
     const size_t ctas = ((size_t)1 << log_n) >> (P.log_r + P.log_g);

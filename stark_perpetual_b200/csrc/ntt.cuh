@@ -44,6 +44,9 @@ struct NttPass {
   const Fp* scale_lo;          // R entries
   const Fp* scale_hi;          // B entries
   int final_pass;              // last pass of the transform: store canonical values (otherwise any lazy representative)
+  // optional direct table of the diagonal factor (forward DIT passes of an LDE): diag_table[(c << log_r) | bitrev_R(r)]
+  // = omega_{2^26}^(bitrev_R(r) * (c * ec + e0)); saves the two-level lookup's multiplication (null: use uniA/uniB)
+  const Fp* diag_table;
 };
 
 // One half (16 bytes) of a field element in the shared-memory workspace.  The workspace is PLANAR -- low halves
@@ -128,9 +131,13 @@ struct NttTile {
   static SPG_HD Fp apply_factors(const NttPass& P, Fp x, unsigned b, int r, unsigned c) {
     if (P.use_diag) {
       unsigned long long k = spg_bitrev((unsigned)r, P.log_r);
-      unsigned long long E = k * ((unsigned long long)c * P.ec + P.e0);
-      if (P.inverse) E = (0ull - E);
-      x = fp_mul_lazy(x, uni_pow(P, E));
+      if (P.diag_table) {
+        x = fp_mul_lazy(x, P.diag_table[((unsigned long long)c << P.log_r) | k]);
+      } else {
+        unsigned long long E = k * ((unsigned long long)c * P.ec + P.e0);
+        if (P.inverse) E = (0ull - E);
+        x = fp_mul_lazy(x, uni_pow(P, E));
+      }
     }
     if (P.scale_lo) x = fp_mul_lazy(x, P.scale_lo[r]);
     if (P.scale_hi) x = fp_mul_lazy(x, P.scale_hi[b]);
@@ -336,6 +343,7 @@ static inline int spg_ntt_make_passes(NttPass* passes, int log_ws, const Fp* in,
     P.scale_lo = nullptr; P.scale_hi = nullptr;
     if (log_s == 0) { P.scale_lo = scale_lo; P.scale_hi = scale_hi; }
     P.final_pass = (pi == np - 1);
+    P.diag_table = nullptr;
   }
   return np;
 }
