@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_sharded_driver_gloo(tmp_path, world):
     out = tmp_path / "result.txt"
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), WORLD_SIZE=str(world),
