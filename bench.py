@@ -148,6 +148,75 @@ def reference_arm(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------- orders workload
+def orders_arm(args):
+    """BASELINE.json configs[4]: batch-verify synthetic perpetual limit orders (packing + 4 Pedersen hashes + STARK-curve
+    ECDSA per order), sharded across the ranks as independent units: no collective on the data path (weak in the
+    sense of SURVEY.md section 8e: fixed total of --orders, contiguous n/G split)."""
+    import torch
+    import torch.distributed as dist
+    import stark_perpetual_b200 as spg
+    from conftest import rand_felts
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = spg.Context(local)
+    n_total = args.orders
+    n = n_total // world
+    g = np.random.Generator(np.random.PCG64(1005 + rank))
+    orders = {"asset_id_synthetic": rand_felts(n, 41 + rank), "asset_id_collateral": rand_felts(n, 142 + rank),
+              "asset_id_fee": rand_felts(n, 243 + rank), "is_buying_synthetic": g.integers(0, 2, n, dtype=np.uint8)}
+    orders["asset_id_synthetic"][:, 2:] = 0
+    for f in ("asset_id_collateral", "asset_id_fee"):
+        orders[f][:, 3] &= np.uint64((1 << 58) - 1)
+    for f in ("amount_synthetic", "amount_collateral", "max_amount_fee", "position_id"):
+        orders[f] = g.integers(0, 2**64, n, dtype=np.uint64)
+    for f in ("nonce", "expiration_timestamp"):
+        orders[f] = g.integers(0, 2**32, n, dtype=np.uint32)
+    r, s_ = rand_felts(n, 32 + rank), rand_felts(n, 33 + rank)
+    for a in (r, s_):
+        a[:, 3] &= np.uint64(0x07ffffffffffffff)
+    keys, _st = ctx.private_to_stark_key(rand_felts(64, 7))
+    px = np.tile(keys, (n // 64 + 1, 1))[:n]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        ctx.limit_order_verify(orders, r, s_, px)
+    launches_before = ctx.launch_count
+    barrier()
+    t0 = time.perf_counter()
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        st = ctx.limit_order_verify(orders, r, s_, px)       # host buffers in, statuses out: the e2e call
+        kernel_ms += ctx.last_kernel_ms
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([kernel_ms / args.steps, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    k_ms, w_ms = float(t[0].item()), float(t[1].item())
+    if rank == 0:
+        per_order_in = 3 * 32 + 1 + 4 * 8 + 2 * 4 + 3 * 32
+        line = {"metric": "limit_orders_verified_per_s", "value": n * world / (k_ms * 1e-3), "unit": "orders/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": k_ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u256 (8x u32 limbs, Montgomery)", "data": "synthetic",
+                "config": {"workload": "limit_order_verify_batch", "orders": n * world, "per_gpu": n,
+                           "parallelism": "independent units, contiguous n/G split, no collective"},
+                "gpu_launches": (ctx.launch_count - launches_before),
+                "e2e": {"value": n * world / (w_ms * 1e-3), "unit": "orders/s", "ms_per_step": w_ms,
+                        "h2d_bytes_per_step": n * world * per_order_in, "d2h_bytes_per_step": n * world},
+                "status_counts": {int(k): int(v) for k, v in zip(*np.unique(st, return_counts=True))}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -158,12 +227,17 @@ def main():
     ap.add_argument("--log-n", dest="log_n", type=int, default=20)
     ap.add_argument("--chain-log", dest="chain_log", type=int, default=2)
     ap.add_argument("--queries", type=int, default=30)
+    ap.add_argument("--workload", default="proof", choices=["proof", "orders"],
+                    help="proof: the headline 2^20-row proof (default); orders: BASELINE configs[4] batch verification")
+    ap.add_argument("--orders", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle verification of one proof")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload == "orders":
+        return orders_arm(args)
     args.warmup = max(args.warmup, 3)
 
     import torch

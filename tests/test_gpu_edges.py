@@ -1,0 +1,75 @@
+"""GPU: empty, minimal and extreme inputs through every batched entry point (the domain's edge cases: empty batches,
+single elements, field-boundary values, collisions), plus size-independent properties at full size."""
+import numpy as np
+import pytest
+
+from conftest import rand_felts
+from oracle import clib
+from oracle.params import FIELD_PRIME as P
+from oracle.pedersen import pedersen_hash as opedersen
+from stark_perpetual_b200._lib import NTT_NAT_TO_REV, NTT_REV_TO_NAT, ints_to_limbs, limbs_to_ints
+
+pytestmark = pytest.mark.gpu
+E4 = np.empty((0, 4), dtype=np.uint64)
+
+
+def test_empty_batches(ctx):
+    out, st = ctx.pedersen_hash2(E4, E4)
+    assert out.shape == (0, 4) and st.shape == (0,)
+    out, st = ctx.pedersen_chain(E4, 3)
+    assert out.shape == (0, 4)
+    assert ctx.ecdsa_verify(E4, E4, E4, E4).shape == (0,)
+    out, st = ctx.private_to_stark_key(E4)
+    assert out.shape == (0, 4)
+    assert ctx.field_op("mul", E4, E4).shape == (0, 4)
+    assert ctx.ntt(E4, 5).shape == (0, 4)
+    empty_orders = {"asset_id_synthetic": E4, "asset_id_collateral": E4, "asset_id_fee": E4,
+                    "is_buying_synthetic": np.empty(0, np.uint8), "amount_synthetic": np.empty(0, np.uint64),
+                    "amount_collateral": np.empty(0, np.uint64), "max_amount_fee": np.empty(0, np.uint64),
+                    "position_id": np.empty(0, np.uint64), "nonce": np.empty(0, np.uint32),
+                    "expiration_timestamp": np.empty(0, np.uint32)}
+    out, st = ctx.limit_order_msg(empty_orders)
+    assert out.shape == (0, 4) and st.shape == (0,)
+
+
+def test_single_element_and_size_one_transforms(ctx):
+    x = ints_to_limbs([P - 1])
+    assert limbs_to_ints(ctx.ntt(x, 0)) == [P - 1]                       # size-1 transform is the identity
+    assert limbs_to_ints(ctx.ntt(x, 0, inverse=True)) == [P - 1]
+    pair = ints_to_limbs([5, P - 1])
+    assert limbs_to_ints(ctx.ntt(pair, 1, order=2)) == [(5 + P - 1) % P, (5 - (P - 1)) % P]
+    out, st = ctx.pedersen_hash2(ints_to_limbs([0]), ints_to_limbs([0]))
+    assert st[0] == 0 and limbs_to_ints(out)[0] == opedersen(0, 0)
+    lde = ctx.lde(ints_to_limbs([7] * 8), 3, 1, 3)                        # a constant column extends to the constant
+    assert limbs_to_ints(lde) == [7] * 64
+
+
+def test_pedersen_boundary_values(ctx):
+    vals = [0, 1, P - 1, P - 2, 2**248 - 1, 2**248, 2**251, 2**251 + 17 * 2**192]
+    xs = [a for a in vals for _b in vals]
+    ys = [b for _a in vals for b in vals]
+    out, st = ctx.pedersen_hash2(ints_to_limbs(xs), ints_to_limbs(ys))
+    assert not st.any()
+    assert limbs_to_ints(out) == [opedersen(a, b) for a, b in zip(xs, ys)]
+    # out of range in either position, and ragged validity inside one batch
+    out, st = ctx.pedersen_hash2(ints_to_limbs([1, P, 2, 2**256 - 1]), ints_to_limbs([P, 1, 3, 1]))
+    assert list(st) == [1, 1, 0, 1] and limbs_to_ints(out)[2] == opedersen(2, 3)
+    assert limbs_to_ints(out)[0] == 0 and limbs_to_ints(out)[1] == 0       # failed elements are zeroed
+
+
+def test_ntt_full_size_round_trip_and_dc_term(ctx):
+    """2^22 points: inverse(forward) is the identity, and output 0 (frequency 0) is the sum of the inputs."""
+    log_n = 22
+    x = rand_felts(1 << log_n, 91)
+    f = ctx.ntt(x, log_n, False, NTT_NAT_TO_REV)
+    assert np.array_equal(ctx.ntt(f, log_n, True, NTT_REV_TO_NAT), x)
+    assert limbs_to_ints(f[:1])[0] == sum(limbs_to_ints(x)) % P           # bit-reversed position 0 = frequency 0
+
+
+def test_lde_interpolates_trace_on_coset_zero_shift(ctx):
+    """LDE with offset 1: coset 0 reproduces the column itself (size-independent property, 2^16 x 3)."""
+    log_n, C = 16, 3
+    tr = rand_felts(C << log_n, 17)
+    out = ctx.lde(tr, log_n, C, 3, offset=1).reshape(8, C, 1 << log_n, 4)
+    assert np.array_equal(out[0].reshape(-1, 4), tr)
+    assert np.array_equal(out.reshape(-1, 4), clib.lde(tr, log_n, C, 3, offset=1))
