@@ -4,37 +4,63 @@
 #include "stark_kernels.cuh"
 
 // ------------------------------------------------------------------ 1 / (x - A) over cosets
-// Montgomery batch inversion: each thread owns `ch` points strided by the block size (coalesced), keeps the
-// running prefix products in the output buffer itself, inverts once (Fermat chain), and unwinds.
+// Montgomery batch inversion: each thread owns `ch` points strided by the block size (coalesced) and handles up to
+// three shifts A[a] at once -- the domain point x is stepped once per point for all of them, the running prefix
+// products live in the output buffers themselves, and ONE Fermat inversion (of the product of the three running
+// products) serves all chains of the thread.  Per output: (1 + 2/3) multiplications forward, (2 + 2/3) backward,
+// plus 271 / (3 ch) for the inversion.
+template <int NA>
 __global__ void __launch_bounds__(256) k_inv_x_minus(unsigned log_n, int j0, int jstep, int nj, const Fp* __restrict__ A,
                                                      Fp* __restrict__ out, int ch, Fp g, const Fp* __restrict__ uniA,
                                                      const Fp* __restrict__ uniB) {
   const size_t n = (size_t)1 << log_n;
-  const int jj = blockIdx.y, a = blockIdx.z, j = j0 + jstep * jj;
+  const int jj = blockIdx.y, a0 = blockIdx.z * NA, j = j0 + jstep * jj;
   const size_t i0 = (size_t)blockIdx.x * 256 * ch + threadIdx.x;
   const int sh = SPG_UNI_LOG - (int)log_n - SPG_LOG_BLOWUP;
   Fp x = fp_mul(g, spg_uni_pow(uniA, uniB, ((unsigned long long)j + 8ull * i0) << sh));
   const unsigned long long step_e = (256ull << (SPG_UNI_LOG - log_n));
   const Fp step = spg_uni_pow(uniA, uniB, step_e), stepinv = spg_uni_pow(uniA, uniB, 0ull - step_e);
-  const Fp av = A[a];
-  Fp* o = out + (((size_t)a * nj + jj) << log_n);
-  Fp acc = fp_one();
+  Fp av[NA], acc[NA];
+  Fp* o[NA];
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    av[a] = A[a0 + a];
+    acc[a] = fp_one();
+    o[a] = out + (((size_t)(a0 + a) * nj + jj) << log_n);
+  }
   for (int k = 0; k < ch; k++) {
     const size_t i = i0 + 256ull * k;
     if (i < n) {
-      o[i] = acc;
-      acc = fp_mul(acc, fp_sub(x, av));
+#pragma unroll
+      for (int a = 0; a < NA; a++) { o[a][i] = acc[a]; acc[a] = fp_mul(acc[a], fp_sub(x, av[a])); }
     }
     x = fp_mul(x, step);
   }
-  Fp inv = fp_inv_chain(acc);
+  // one inversion for the NA chains: inv[a] = (prod of all) ^-1 * prod of the others
+  Fp inv[NA];
+  {
+    Fp all = acc[0];
+#pragma unroll
+    for (int a = 1; a < NA; a++) all = fp_mul(all, acc[a]);
+    const Fp ia = fp_inv_chain(all);
+    if (NA == 1) inv[0] = ia;
+    else if (NA == 2) { inv[0] = fp_mul(ia, acc[1]); inv[1] = fp_mul(ia, acc[0]); }
+    else {
+      inv[0] = fp_mul(ia, fp_mul(acc[1], acc[2 % NA]));
+      inv[1] = fp_mul(ia, fp_mul(acc[0], acc[2 % NA]));
+      inv[2 % NA] = fp_mul(ia, fp_mul(acc[0], acc[1]));
+    }
+  }
   for (int k = ch - 1; k >= 0; k--) {
     x = fp_mul(x, stepinv);
     const size_t i = i0 + 256ull * k;
     if (i < n) {
-      const Fp pre = o[i];
-      o[i] = fp_reduce(fp_mul(inv, pre));
-      inv = fp_mul(inv, fp_sub(x, av));
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        const Fp pre = o[a][i];
+        o[a][i] = fp_reduce(fp_mul(inv[a], pre));
+        inv[a] = fp_mul(inv[a], fp_sub(x, av[a]));
+      }
     }
   }
 }
@@ -47,8 +73,13 @@ int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int 
   if (ch < 1) ch = 1;
   if (ch > 64) ch = 64;
   const unsigned tiles = (unsigned)((n + 256ull * ch - 1) / (256ull * ch));
-  dim3 grid(tiles, (unsigned)nj, (unsigned)n_a);
-  k_inv_x_minus<<<grid, 256, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
+  if (n_a % 3 == 0) {
+    dim3 grid(tiles, (unsigned)nj, (unsigned)(n_a / 3));
+    k_inv_x_minus<3><<<grid, 256, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
+  } else {
+    dim3 grid(tiles, (unsigned)nj, (unsigned)n_a);
+    k_inv_x_minus<1><<<grid, 256, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
+  }
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
