@@ -54,7 +54,10 @@ __device__ __forceinline__ void load_canon(const uint64_t* src, uint32_t (&x)[8]
 
 // chain_len elements per hash unit: h = H(e0, e1); h = H(h, e2); ... (chain_len >= 1; a single element
 // hashes alone like the reference's variadic pedersen_hash(x)).  elems: [n][chain_len] canonical felts.
-__global__ void __launch_bounds__(128) k_pedersen_chain(const uint64_t* __restrict__ elems, int chain_len,
+#ifndef PEDERSEN_MIN_CTAS
+#define PEDERSEN_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, PEDERSEN_MIN_CTAS) k_pedersen_chain(const uint64_t* __restrict__ elems, int chain_len,
                                                         uint64_t* __restrict__ out, uint8_t* __restrict__ status,
                                                         size_t n, const APoint* __restrict__ cp) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -61,7 +61,10 @@ __device__ __forceinline__ void load8(const uint64_t* src, uint32_t (&x)[8]) {
   x[0] = lo.x; x[1] = lo.y; x[2] = lo.z; x[3] = lo.w; x[4] = hi.x; x[5] = hi.y; x[6] = hi.z; x[7] = hi.w;
 }
 
-__global__ void __launch_bounds__(64) k_ecdsa_verify(const uint64_t* __restrict__ msg, const uint64_t* __restrict__ r,
+#ifndef ECDSA_MIN_CTAS
+#define ECDSA_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(64, ECDSA_MIN_CTAS) k_ecdsa_verify(const uint64_t* __restrict__ msg, const uint64_t* __restrict__ r,
                                                      const uint64_t* __restrict__ s, const uint64_t* __restrict__ px,
                                                      const uint64_t* __restrict__ py, uint8_t* __restrict__ status,
                                                      size_t n, EcdsaTables T) {

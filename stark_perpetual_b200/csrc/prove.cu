@@ -115,7 +115,9 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
 
   // ---- public input, channel
   Fp h_last[SPG_AIR_LANES];
-  const int n_chunks = 5, chunk_cols = C / n_chunks;
+  // upload chunks (columns): a small first chunk so that the LDE starts after 1/25 of the copy
+  const int n_chunks = 6, chunk_begin[7] = {0, 1, 5, 10, 15, 20, 25};
+  static_assert(SPG_AIR_COLS == 25, "chunk table");
   if (h_trace) {
     for (int l = 0; l < SPG_AIR_LANES; l++) h_last[l] = h_trace[((size_t)(5 * l) << log_n) + (n - 1)];
     if (!ctx->copy_stream) {
@@ -127,8 +129,8 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
     SPG_CUDA(cudaEventRecord(ctx->copy_gate, ctx->stream));
     SPG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_gate, 0));
     for (int k = 0; k < n_chunks; k++) {
-      const size_t off = ((size_t)k * chunk_cols) << log_n;
-      SPG_CUDA(cudaMemcpyAsync((Fp*)d_trace + off, h_trace + off, ((size_t)chunk_cols << log_n) * sizeof(Fp),
+      const size_t off = (size_t)chunk_begin[k] << log_n, cols = (size_t)(chunk_begin[k + 1] - chunk_begin[k]);
+      SPG_CUDA(cudaMemcpyAsync((Fp*)d_trace + off, h_trace + off, (cols << log_n) * sizeof(Fp),
                                cudaMemcpyHostToDevice, ctx->copy_stream));
       SPG_CUDA(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
     }
@@ -159,10 +161,10 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
   spg_stage_begin(ctx, ST_LDE);
   if (h_trace) {
     for (int k = 0; k < n_chunks; k++) {
-      const size_t c0 = (size_t)k * chunk_cols, off = c0 << log_n;
+      const size_t c0 = (size_t)chunk_begin[k], off = c0 << log_n, cols = (size_t)(chunk_begin[k + 1] - chunk_begin[k]);
       SPG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->copy_ev[k], 0));
-      if ((rc = spg_lde_coeffs_device(ctx, d_trace + off, log_n, chunk_cols, nullptr, t_coef + off, /*mont=*/1))) return rc;
-      if ((rc = spg_lde_cosets_device(ctx, t_coef + off, log_n, chunk_cols, SPG_LOG_BLOWUP, 0, SPG_BLOWUP, t_lde, C, c0))) return rc;
+      if ((rc = spg_lde_coeffs_device(ctx, d_trace + off, log_n, cols, nullptr, t_coef + off, /*mont=*/1))) return rc;
+      if ((rc = spg_lde_cosets_device(ctx, t_coef + off, log_n, cols, SPG_LOG_BLOWUP, 0, SPG_BLOWUP, t_lde, C, c0))) return rc;
     }
   } else {
     if ((rc = spg_lde_device(ctx, d_trace, log_n, C, SPG_LOG_BLOWUP, nullptr, t_lde, t_coef, /*mont=*/1))) return rc;
