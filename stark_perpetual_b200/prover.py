@@ -454,25 +454,39 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
     gamma = ch.draw_felt()
     layers, trees, tops = [be.felts(cs, n)], [None], [None]
     be.deep(t_lde, h_lde, log_n, first, cs, z, gamma, oods, layers[0])
-    # 5. FRI
+    # 5. FRI.  Only the first fold works on sharded data: its output (N/8 rows per coset, 32 MB at 2^20) is
+    # all-gathered once, and every rank then folds and commits the remaining, geometrically shrinking layers
+    # locally -- no further collective or root exchange on the latency-bound tail of the protocol.
     tick("fri")
     fri_roots = []
+    full_tops = [None]
     for l in range(1, n_folds + 1):
         beta = ch.draw_felt()
-        nxt = be.felts(cs, 1 << log_rows[l])
-        be.fri_fold(layers[l - 1], log_rows[l - 1], first, cs, beta, l - 1, nxt)
-        tree, top = commit(nxt, 1, 1 << log_rows[l])
-        layers.append(nxt); trees.append(tree); tops.append(top)
-        fri_roots.append(top[-1][0])
-        ch.absorb(top[-1][0])
-    parts = comm.all_gather_obj(be.table_bytes(layers[-1]))             # <= 16 KB per rank, coset-major
-    lb = be.last_layer(parts, log_rows[-1], n_folds)
+        rows_l = 1 << log_rows[l]
+        if l == 1:
+            part = be.felts(cs, rows_l)
+            be.fri_fold(layers[0], log_rows[0], first, cs, beta, 0, part)
+            if world > 1:
+                nxt = be.felts(BLOWUP, rows_l)
+                comm.all_gather_into(nxt, part)                   # rank r holds cosets [r cs, (r+1) cs): coset-major
+            else:
+                nxt = part
+        else:
+            nxt = be.felts(BLOWUP, rows_l)
+            be.fri_fold(layers[l - 1], log_rows[l - 1], 0, BLOWUP, beta, l - 1, nxt)
+        tree = be.merkle(nxt, 1, rows_l, BLOWUP)
+        root = be.root(tree).cpu().numpy().tobytes()
+        layers.append(nxt); trees.append(tree); full_tops.append([[root]])
+        fri_roots.append(root)
+        ch.absorb(root)
+    lb = be.last_layer([be.table_bytes(layers[-1])], log_rows[-1], n_folds)
     ch.absorb(lb)
     proof += [root_t, root_h, ob] + fri_roots + [lb]
     # 6. queries: every rank opens the leaves that live in its cosets
     tick("queries")
-    tables = [(t_lde, N_COLS, n, tree_t, top_t), (h_lde, 4, n, tree_h, top_h)]
-    tables += [(layers[l], 1, 1 << log_rows[l], trees[l], tops[l]) for l in range(1, n_folds + 1)]
+    # (table, columns, rows, tree, top levels, first coset held, cosets held); FRI layers are replicated (opened by rank 0)
+    tables = [(t_lde, N_COLS, n, tree_t, top_t, first, cs), (h_lde, 4, n, tree_h, top_h, first, cs)]
+    tables += [(layers[l], 1, 1 << log_rows[l], trees[l], full_tops[l], 0, BLOWUP) for l in range(1, n_folds + 1)]
     qidx = []                              # per query, per table: (j, i')
     for _ in range(n_queries):
         idx = ch.draw_index(n)
@@ -483,19 +497,21 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
             row.append((j, ip))
         qidx.append(row)
     mine_open = {}
-    for t, (table, n_cols, rows, tree, _top) in enumerate(tables):
-        want = [(q, (j - first) * (rows // 8) + ip) for q, rowq in enumerate(qidx) for (j, ip) in [rowq[t]]
-                if first <= j < first + cs]
-        res = be.open(table, n_cols, rows, cs, tree, [w[1] for w in want])
+    for t, (table, n_cols, rows, tree, _top, tfirst, tcs) in enumerate(tables):
+        if tcs == BLOWUP and world > 1 and rank != 0:
+            continue                       # replicated table: one opener is enough
+        want = [(q, (j - tfirst) * (rows // 8) + ip) for q, rowq in enumerate(qidx) for (j, ip) in [rowq[t]]
+                if tfirst <= j < tfirst + tcs]
+        res = be.open(table, n_cols, rows, tcs, tree, [w[1] for w in want])
         for (q, _li), r in zip(want, res):
             mine_open[(q, t)] = r
     all_open = {}
     for part in comm.all_gather_obj(mine_open):
         all_open.update(part)
     for q in range(n_queries):
-        for t, (_table, _nc, _rows, _tree, top) in enumerate(tables):
+        for t, (_table, _nc, _rows, _tree, top, _tf, tcs) in enumerate(tables):
             leaf, path = all_open[(q, t)]
-            owner = qidx[q][t][0] // cs
+            owner = qidx[q][t][0] // tcs
             proof += [leaf, path] + top_path(top, owner)
     tick("end")
     return b"".join(proof)
