@@ -248,6 +248,10 @@ class GpuBackend:
         """raw device representation of a small table (the last FRI layer), for the cross-rank gather"""
         return t.reshape(-1).cpu().numpy().tobytes()
 
+    def bytes_tensor(self, b):
+        """bytes -> uint8 tensor on the device the collectives run on"""
+        return self.torch.frombuffer(bytearray(b), dtype=self.torch.uint8).to(self.dev)
+
     def last_layer(self, parts, log_rows_last, n_folds):
         """parts: table_bytes of every rank in rank order (= coset-major [8][n_last]).  Returns the serialised
         low coefficients; raises ProofError when the layer is not of low degree."""
@@ -360,6 +364,13 @@ class TorchComm:
         k = t.numel()
         return [raw[r * k:(r + 1) * k] for r in range(self.world)]
 
+    def sum_bytes(self, t):
+        """element-wise sum over ranks of a uint8 tensor (used with disjoint non-zero regions: a scatter-free gather)"""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy().tobytes()
+
     def all_gather_obj(self, obj):
         if self.world == 1:
             return [obj]
@@ -444,7 +455,17 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
     wn = root_of_unity(log_n)
     zw, z4 = z * wn % P, pow(z, 4, P)
     cols = [coefs[c] for c in range(N_COLS)] * 2 + [h_coef[m] for m in range(4)]
-    oods = be.poly_eval(cols, [0] * N_COLS + [1] * N_COLS + [2] * 4, [z, zw, z4], log_n)
+    pidx = [0] * N_COLS + [1] * N_COLS + [2] * 4
+    # the 54 evaluations are dealt round-robin to the ranks (every rank holds every coefficient column) and the
+    # 32-byte results gathered
+    mine_items = list(range(rank, len(cols), world))
+    vals = be.poly_eval([cols[k] for k in mine_items], [pidx[k] for k in mine_items], [z, zw, z4], log_n) if mine_items else []
+    per_rank = -(-len(cols) // world)
+    buf = b"".join(v.to_bytes(32, "little") for v in vals).ljust(32 * per_rank, b"\0")
+    oods = [0] * len(cols)
+    for r, part in enumerate(comm.all_gather_bytes(be.bytes_tensor(buf))):
+        for i, k in enumerate(range(r, len(cols), world)):
+            oods[k] = int.from_bytes(part[32 * i:32 * i + 32], "little")
     if check:
         be.check_oods(log_n, chain_log, x0, outs, alpha, z, oods)
     ob = b"".join(ser(v) for v in oods)
@@ -496,23 +517,31 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
             ip %= (1 << log_rows[l]) // 8
             row.append((j, ip))
         qidx.append(row)
-    mine_open = {}
+    # every (query, table) opening has one owner and a size known to all ranks: each rank writes its openings into a
+    # zeroed buffer with a fixed layout and the buffers are summed (one small all-reduce instead of pickled objects)
+    sizes = []
+    for (_table, n_cols, rows, _tree, _top, _tf, tcs) in tables:
+        levels = (rows // 8 * tcs).bit_length() - 1
+        sizes.append((8 * n_cols * 32, levels * 32))
+    per_query = sum(a + b for a, b in sizes)
+    t_off = [sum(a + b for a, b in sizes[:t]) for t in range(len(tables))]
+    buf = bytearray(per_query * n_queries)
     for t, (table, n_cols, rows, tree, _top, tfirst, tcs) in enumerate(tables):
         if tcs == BLOWUP and world > 1 and rank != 0:
             continue                       # replicated table: one opener is enough
         want = [(q, (j - tfirst) * (rows // 8) + ip) for q, rowq in enumerate(qidx) for (j, ip) in [rowq[t]]
                 if tfirst <= j < tfirst + tcs]
         res = be.open(table, n_cols, rows, tcs, tree, [w[1] for w in want])
-        for (q, _li), r in zip(want, res):
-            mine_open[(q, t)] = r
-    all_open = {}
-    for part in comm.all_gather_obj(mine_open):
-        all_open.update(part)
+        for (q, _li), (leaf, path) in zip(want, res):
+            o = q * per_query + t_off[t]
+            buf[o:o + len(leaf)] = leaf
+            buf[o + sizes[t][0]:o + sizes[t][0] + len(path)] = path
+    allb = comm.sum_bytes(be.bytes_tensor(bytes(buf)))
     for q in range(n_queries):
         for t, (_table, _nc, _rows, _tree, top, _tf, tcs) in enumerate(tables):
-            leaf, path = all_open[(q, t)]
+            o = q * per_query + t_off[t]
             owner = qidx[q][t][0] // tcs
-            proof += [leaf, path] + top_path(top, owner)
+            proof += [allb[o:o + sizes[t][0]], allb[o + sizes[t][0]:o + sizes[t][0] + sizes[t][1]]] + top_path(top, owner)
     tick("end")
     return b"".join(proof)
 

@@ -77,6 +77,9 @@ class CpuBackend:
     def table_bytes(self, t):
         return b"".join(v.to_bytes(32, "little") for v in self._get(t))
 
+    def bytes_tensor(self, b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8)
+
     def last_layer(self, parts, log_rows_last, n_folds):
         from stark_perpetual_b200 import prover
         n_last = 1 << log_rows_last
