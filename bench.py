@@ -72,7 +72,10 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.marks = [], None, gpu_index, []
+
+    def mark(self):
+        self.marks.append(len(self.rows))
 
     def start(self):
         try:
@@ -96,10 +99,13 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows
+        if len(self.marks) >= 2 and self.marks[1] > self.marks[0]:
+            rows = self.rows[self.marks[0]:self.marks[1] + 1]      # the timed region only
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -221,7 +227,7 @@ def orders_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log-n", dest="log_n", type=int, default=20)
@@ -296,22 +302,24 @@ def main():
         torch.cuda.synchronize()
 
     proof = None
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi takes a moment to deliver its first row: started before the warm-up,
+    for _ in range(args.warmup):  # only the rows of the timed region are kept (mark / stop below)
         proof = step()
     barrier()
     launches_per_step = (ctx.launch_count - launches_before) // args.warmup
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = np.zeros(len(STAGES))
     barrier()
+    sampler.mark()
     e0.record(stream)
     for _ in range(args.steps):
         proof = step()
         stage_ms += np.array([ctx.stage_ms(i) for i in range(len(STAGES))])
     e1.record(stream)
     barrier()
+    sampler.mark()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -2,7 +2,7 @@
  * TEST INFRASTRUCTURE ONLY: used by tests/ as a faster checker than the Python oracle and by
  * bench.py's cpu_baseline / --impl reference legs.  PARITY UNPINNED for these stages: the
  * reference repository contains no prover; the field p and generator 3 are the
- * reference's (signature.py:41-42).  Validated against oracle/ntt.py in tests/test_oracle.py.
+ * reference's (signature.py:41-42).  Validated against oracle/ntt.py in tests/test_oracle_ntt.py.
  *
  * Build: oracle/Makefile  ->  oracle/_build/libspg_oracle.so   (gcc -O3 -fopenmp)
  */
