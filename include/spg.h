@@ -80,6 +80,14 @@ int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, const uint8_t*
 int spg_pedersen_chain_batch(spg_ctx* ctx, const uint64_t* elems, size_t chain_len, uint64_t* out, uint8_t* status,
                              size_t n, int flags);
 
+/* Merkle tree whose node function is pedersen_hash(left, right): the StarkEx state trees (positions / orders) that
+ * src/services/perpetual/cairo/state/state.cairo:155-173 updates with merkle_multi_update, and for which
+ * src/starkware/python/merkle_tree.py:4-44 builds the update hints.  leaves: [n_leaves][4] canonical felts, n_leaves a
+ * power of two >= 2.  root_out: [4]; nodes_out (optional): the n_leaves - 1 internal nodes, level by level from the
+ * bottom (n/2, n/4, ..., 1).  *status_out (host): 0 ok, 1 a leaf >= p, 2 "Unhashable input." somewhere in the tree. */
+int spg_pedersen_merkle_tree(spg_ctx* ctx, const uint64_t* leaves, size_t n_leaves, uint64_t* root_out, uint64_t* nodes_out,
+                             uint8_t* status_out, int flags);
+
 /* ---- STARK-curve ECDSA (BASELINE.json configs[4]) ---------------------------------
  * Replaces signature.py:217-260 verify(msg_hash, r, s, public_key).  All operands are 256-bit values as 4 x u64
  * LE limbs.  pub_y_or_null = NULL: x-only keys (signature.py:229-238: y = smaller root, then -y).

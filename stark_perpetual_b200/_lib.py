@@ -57,6 +57,7 @@ def _load():
             "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_ecdsa_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_private_to_stark_key_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_pedersen_merkle_tree": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_int]),
             "spg_limit_order_msg_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_limit_order_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_set_stream": (C.c_int, [vp, vp]),
@@ -188,6 +189,17 @@ class Context:
         st = np.empty(n, dtype=np.uint8)
         self._check(self._lib.spg_pedersen_chain_batch(self._h, _ptr(e), chain_len, _ptr(out), _ptr(st), n, 0))
         return out, st
+
+    def pedersen_merkle_tree(self, leaves, want_nodes=False):
+        """leaves: (n, 4) canonical felts, n a power of two -> (root (4,), nodes (n - 1, 4) or None, status)."""
+        lv = np.ascontiguousarray(leaves, dtype=np.uint64).reshape(-1, 4)
+        n = lv.shape[0]
+        root = np.empty(4, dtype=np.uint64)
+        nodes = np.empty((n - 1, 4), dtype=np.uint64) if want_nodes else None
+        st = np.zeros(1, dtype=np.uint8)
+        self._check(self._lib.spg_pedersen_merkle_tree(self._h, _ptr(lv), n, _ptr(root), _ptr(nodes) if want_nodes else None,
+                                                       _ptr(st), 0))
+        return root, nodes, int(st[0])
 
     # ---- ECDSA ----
     def ecdsa_verify(self, msg, r, s, pub_x, pub_y=None):

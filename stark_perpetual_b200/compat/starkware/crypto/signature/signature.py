@@ -181,6 +181,47 @@ def sign(msg_hash: int, priv_key: int, seed: Optional[int] = None) -> ECSignatur
         return r, inv_mod_curve_size(w)
 
 
+def sign_batch(msg_hashes, priv_keys, seeds=None):
+    """[sign(m, k, seed) for ...]: the nonces are derived on the host (RFC 6979, signature.py:117-134), the curve
+    multiplications k*G of the whole batch run in one launch, and only the signatures that hit one of the reference's
+    three rejection rules (signature.py:158-170) go round again with the bumped seed."""
+    n = len(msg_hashes)
+    seeds = list(seeds) if seeds is not None else [None] * n
+    for m in msg_hashes:
+        assert 0 <= m < 2**N_ELEMENT_BITS_ECDSA, "Message not signable."
+    out = [None] * n
+    todo = list(range(n))
+    while todo:
+        ks = [generate_k_rfc6979(msg_hashes[i], priv_keys[i], seeds[i]) for i in todo]
+        for i in todo:
+            seeds[i] = 1 if seeds[i] is None else seeds[i] + 1
+        rs = private_to_stark_key_batch(ks)
+        again = []
+        for i, k, r in zip(todo, ks, rs):
+            z = msg_hashes[i] + r * priv_keys[i]
+            if not (1 <= r < 2**N_ELEMENT_BITS_ECDSA) or z % EC_ORDER == 0:
+                again.append(i)
+                continue
+            w = k * pow(z, -1, EC_ORDER) % EC_ORDER
+            if not (1 <= w < 2**N_ELEMENT_BITS_ECDSA):
+                again.append(i)
+                continue
+            out[i] = (r, inv_mod_curve_size(w))
+        todo = again
+    return out
+
+
+def pedersen_merkle_root(leaves):
+    """Root of the Merkle tree with pedersen_hash nodes over a power-of-two number of leaves (the StarkEx state-tree
+    node function, src/services/perpetual/cairo/state/state.cairo:155-173), computed level by level on the GPU."""
+    for v in leaves:
+        assert 0 <= v < FIELD_PRIME
+    root, _nodes, st = _ctx().pedersen_merkle_tree(ints_to_limbs(leaves))
+    assert st != 1
+    assert st != 2, "Unhashable input."
+    return limbs_to_ints(root.reshape(1, 4))[0]
+
+
 def grind_key(key_seed: int, key_value_limit: int) -> int:
     # signature.py:263-288 (host-side hashing only)
     max_allowed = 2**256 - (2**256 % key_value_limit)

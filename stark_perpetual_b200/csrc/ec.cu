@@ -207,3 +207,50 @@ extern "C" int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, con
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
 }
+
+// ------------------------------------------------------------------ Merkle tree with Pedersen nodes
+// node = pedersen_hash(left, right) (signature.py:296-318), the node function of the StarkEx state trees that
+// src/services/perpetual/cairo/state/state.cairo:155-173 updates through merkle_multi_update; the reference's
+// starkware/python/merkle_tree.py:4-44 builds the update-tree hints for exactly these trees.  A level is the chain
+// kernel with chain_len = 2 applied to the previous level in place of a pair list (children are adjacent).
+extern "C" int spg_pedersen_merkle_tree(spg_ctx* ctx, const uint64_t* leaves, size_t n_leaves, uint64_t* root_out,
+                                        uint64_t* nodes_out, uint8_t* status_out, int flags) {
+  SPG_ARG(ctx && leaves && root_out && status_out, "spg_pedersen_merkle_tree: null");
+  SPG_ARG(n_leaves >= 2 && (n_leaves & (n_leaves - 1)) == 0, "spg_pedersen_merkle_tree: n_leaves must be a power of two >= 2");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  // nodes: n/2 + n/4 + ... + 1 = n - 1 internal nodes, level by level from the bottom; status per node
+  DevBuf bl, bn, bs;
+  const uint64_t* dl = leaves;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(bl.alloc(ctx, n_leaves * 32));
+    SPG_CUDA(cudaMemcpyAsync(bl.p, leaves, n_leaves * 32, cudaMemcpyHostToDevice, ctx->stream));
+    dl = bl.as<uint64_t>();
+  }
+  SPG_CUDA(bn.alloc(ctx, (n_leaves - 1) * 32)); SPG_CUDA(bs.alloc(ctx, n_leaves - 1));
+  uint64_t* dn = bn.as<uint64_t>();
+  uint8_t* ds = bs.as<uint8_t>();
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  const uint64_t* prev = dl;
+  size_t off = 0;
+  for (size_t m = n_leaves / 2; m >= 1; m /= 2) {
+    int rc = spg_pedersen_chain_device(ctx, prev, 2, dn + 4 * off, ds + off, m);
+    if (rc) return rc;
+    prev = dn + 4 * off;
+    off += m;
+    if (m == 1) break;
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  std::vector<uint8_t> st(n_leaves - 1);
+  SPG_CUDA(cudaMemcpyAsync(st.data(), ds, n_leaves - 1, cudaMemcpyDeviceToHost, ctx->stream));
+  const cudaMemcpyKind back = (flags & SPG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  SPG_CUDA(cudaMemcpyAsync(root_out, dn + 4 * (n_leaves - 2), 32, back, ctx->stream));
+  if (nodes_out) SPG_CUDA(cudaMemcpyAsync(nodes_out, dn, (n_leaves - 1) * 32, back, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  // a failed node (input >= p can only happen at the leaves; "Unhashable input." anywhere) poisons its ancestors:
+  // report the worst status seen
+  uint8_t worst = 0;
+  for (uint8_t v : st) if (v > worst) worst = v;
+  *status_out = worst;
+  return SPG_OK;
+}

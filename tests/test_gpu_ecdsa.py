@@ -124,3 +124,45 @@ def test_compat_signature_module(ctx, golden):
                 sig.verify(int(msg, 16), int(r, 16), int(s, 16), pk)
         else:
             assert sig.verify(int(msg, 16), int(r, 16), int(s, 16), pk) == bool(res), tag
+
+
+def test_sign_batch_matches_reference_vectors_and_scalar_sign(ctx, golden):
+    """sign_batch (host RFC 6979 nonces, one GPU launch for all k*G) against the 4 JS KATs (signature.spec.js:96-137),
+    the reference-generated sign vectors and the oracle's sign."""
+    sig = compat()
+    kat = golden["sign_js_kat"]
+    vec = golden["sign"]
+    msgs = [int(v[0], 16) for v in kat] + [int(v[0], 16) for v in vec]
+    privs = [int(v[1], 16) for v in kat] + [int(v[1], 16) for v in vec]
+    want = [(int(v[2], 16), int(v[3], 16)) for v in kat] + [(int(v[2], 16), int(v[3], 16)) for v in vec]
+    assert sig.sign_batch(msgs, privs) == want
+    rng = random.Random(31)
+    m2 = [rng.randrange(2**251) for _ in range(64)]
+    k2 = [rng.randrange(1, EC_ORDER) for _ in range(64)]
+    got = sig.sign_batch(m2, k2)
+    assert got[:8] == [oecdsa.sign(m, k) for m, k in zip(m2[:8], k2[:8])]
+    pubs = sig.private_to_stark_key_batch(k2)
+    assert sig.verify_batch(m2, [g[0] for g in got], [g[1] for g in got], pubs) == [True] * 64
+    assert sig.sign_batch(m2[:3], k2[:3], seeds=[5, None, 7])[0] == oecdsa.sign(m2[0], k2[0], 5)
+
+
+def test_pedersen_merkle_tree(ctx):
+    """Merkle tree with pedersen_hash nodes (StarkEx state-tree node function) against the oracle's hash, node by node."""
+    from oracle.pedersen import pedersen_hash as oph
+    sig = compat()
+    rng = random.Random(99)
+    leaves = [rng.randrange(P) for _ in range(32)]
+    leaves[0], leaves[1], leaves[2] = 0, P - 1, 1
+    root, nodes, st = ctx.pedersen_merkle_tree(ints_to_limbs(leaves), want_nodes=True)
+    assert st == 0
+    level, want_nodes = leaves, []
+    while len(level) > 1:
+        level = [oph(level[2 * i], level[2 * i + 1]) for i in range(len(level) // 2)]
+        want_nodes += level
+    assert limbs_to_ints(nodes) == want_nodes
+    assert limbs_to_ints(root.reshape(1, 4))[0] == want_nodes[-1] == sig.pedersen_merkle_root(leaves)
+    # two leaves: the tree is one hash; a leaf >= p is reported
+    r2, _n, st = ctx.pedersen_merkle_tree(ints_to_limbs([3, 4]))
+    assert st == 0 and limbs_to_ints(r2.reshape(1, 4))[0] == oph(3, 4)
+    _r, _n, st = ctx.pedersen_merkle_tree(ints_to_limbs([3, P, 5, 6]))
+    assert st == 1
