@@ -17,24 +17,47 @@ typedef NttTile<NTT_LOG_WS, NTT_LOG_EPT> Tile;
 #ifndef NTT_MIN_CTAS
 #define NTT_MIN_CTAS 4
 #endif
+// Synchronisation between the phases of a pass.  When the pass uses the whole workspace for one column (log_g = 0,
+// log_r = LOG_WS) and every thread owns exactly one butterfly group per step, a step with sh + w <= 5 + LOG_EPT only
+// touches rows inside the 2^(5 + LOG_EPT)-row window [warp * 128, warp * 128 + 128): warp w of the CTA reads and writes
+// that window and nothing else.  Consecutive such phases therefore need a warp barrier only -- three of the six
+// CTA-wide barriers of a 10-bit pass (the load / store phase is mapped onto the same windows).
 template <bool DIT>
 __global__ void __launch_bounds__(Tile::NT, NTT_MIN_CTAS) k_ntt_pass(NttPass P) {
   extern __shared__ uint4 smem_raw[];
   FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
   const int tid = threadIdx.x;
   const unsigned cta = blockIdx.x, col = blockIdx.y;
-#pragma unroll
-  for (int j = 0; j < Tile::EPT; j++) Tile::load_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
-  __syncthreads();
+  constexpr int LW = 5 + NTT_LOG_EPT;                       // log2 rows per warp window
+  const bool windowed = (P.log_g == 0 && P.log_r == NTT_LOG_WS);
   const int ns = Tile::n_steps(P);
+  auto local = [&](int k) {                                 // phase k: -1 = load, ns = store, else butterfly step k
+    if (!windowed) return false;
+    if (k < 0 || k >= ns) return true;
+    int w, sh;
+    Tile::step_geom<DIT>(P, k, &w, &sh);
+    return w == NTT_LOG_EPT && sh + w <= LW;
+  };
+  auto sync_between = [&](int a, int b) {
+    if (local(a) && local(b)) __syncwarp(); else __syncthreads();
+  };
+#pragma unroll
+  for (int j = 0; j < Tile::EPT; j++) {
+    const int idx = windowed ? (((tid >> 5) << LW) | (j << 5) | (tid & 31)) : (j * Tile::NT + tid);
+    Tile::load_one<DIT>(P, ws, cta, col, idx);
+  }
+  sync_between(-1, 0);
   for (int k = 0; k < ns; k++) {
     int w, sh;
     Tile::step_geom<DIT>(P, k, &w, &sh);
     Tile::step_w<DIT>(P, ws, tid, w, sh);
-    __syncthreads();
+    sync_between(k, k + 1);
   }
 #pragma unroll
-  for (int j = 0; j < Tile::EPT; j++) Tile::store_one<DIT>(P, ws, cta, col, j * Tile::NT + tid);
+  for (int j = 0; j < Tile::EPT; j++) {
+    const int idx = windowed ? (((tid >> 5) << LW) | (j << 5) | (tid & 31)) : (j * Tile::NT + tid);
+    Tile::store_one<DIT>(P, ws, cta, col, idx);
+  }
 }
 
 __global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
