@@ -80,6 +80,11 @@ int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, const uint8_t*
 int spg_pedersen_chain_batch(spg_ctx* ctx, const uint64_t* elems, size_t chain_len, uint64_t* out, uint8_t* status,
                              size_t n, int flags);
 
+/* signature.py:300-318 pedersen_hash_as_point: both coordinates of the hash point.  elems: [n][n_elems] canonical felts,
+ * n_elems = 1 or 2 (host pointers); status as spg_pedersen_hash2_batch. */
+int spg_pedersen_hash_point_batch(spg_ctx* ctx, const uint64_t* elems, size_t n_elems, uint64_t* out_x, uint64_t* out_y,
+                                  uint8_t* status, size_t n, int flags);
+
 /* Merkle tree whose node function is pedersen_hash(left, right): the StarkEx state trees (positions / orders) that
  * src/services/perpetual/cairo/state/state.cairo:155-173 updates with merkle_multi_update, and for which
  * src/starkware/python/merkle_tree.py:4-44 builds the update hints.  leaves: [n_leaves][4] canonical felts, n_leaves a
@@ -101,6 +106,17 @@ int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r,
  * priv[i] * G (pub_y_or_null may be NULL); status 1 if priv is outside (0, n). */
 int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv, uint64_t* pub_x, uint64_t* pub_y_or_null,
                                    uint8_t* status, size_t n, int flags);
+
+/* signature.py:84-96 get_y_coordinate: y[i] = the smaller square root of x^3 + x + beta (math_utils.py:43-47).
+ * status[i]: 0 ok; 1 InvalidPublicKeyError (no point with this x; is_valid_stark_key, signature.py:204-214, is
+ * status == 0); 2 x is not a field element. */
+int spg_get_y_coordinate_batch(spg_ctx* ctx, const uint64_t* x, uint64_t* y, uint8_t* status, size_t n, int flags);
+/* signature.py:176-190 mimic_ec_mult_air: out = m * point + shift_point computed with the AIR's steps.  m: [n][4];
+ * point_xy, shift_xy, out_xy: [n][8] (x then y, canonical).  status[i]: 0 ok; 1 the reference raises AssertionError
+ * (m outside (0, 2^251), partial_sum.x == point.x on some step, doubling of a point with y = 0); 2 a coordinate is not
+ * a field element. */
+int spg_mimic_ec_mult_air_batch(spg_ctx* ctx, const uint64_t* m, const uint64_t* point_xy, const uint64_t* shift_xy,
+                                uint64_t* out_xy, uint8_t* status, size_t n, int flags);
 
 /* ---- perpetual limit orders (BASELINE.json configs[4]) ------------------------------
  * Replaces src/services/perpetual/public/perpetual_messages.py:212-286 get_limit_order_msg: field packing and the 4-deep

@@ -57,6 +57,9 @@ def _load():
             "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_ecdsa_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_private_to_stark_key_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_pedersen_hash_point_batch": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_get_y_coordinate_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_mimic_ec_mult_air_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_pedersen_merkle_tree": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_int]),
             "spg_limit_order_msg_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_limit_order_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
@@ -188,6 +191,29 @@ class Context:
         out = np.empty((n, 4), dtype=np.uint64)
         st = np.empty(n, dtype=np.uint8)
         self._check(self._lib.spg_pedersen_chain_batch(self._h, _ptr(e), chain_len, _ptr(out), _ptr(st), n, 0))
+        return out, st
+
+    def pedersen_hash_point(self, elems, n_elems):
+        """elems: (n * n_elems, 4) canonical felts -> (x (n, 4), y (n, 4), status)."""
+        e = np.ascontiguousarray(elems, dtype=np.uint64).reshape(-1, 4)
+        n = e.shape[0] // n_elems
+        x, y, st = np.empty((n, 4), np.uint64), np.empty((n, 4), np.uint64), np.empty(n, np.uint8)
+        self._check(self._lib.spg_pedersen_hash_point_batch(self._h, _ptr(e), n_elems, _ptr(x), _ptr(y), _ptr(st), n, 0))
+        return x, y, st
+
+    def get_y_coordinate(self, xs):
+        x = np.ascontiguousarray(xs, dtype=np.uint64).reshape(-1, 4)
+        y, st = np.empty_like(x), np.empty(x.shape[0], np.uint8)
+        self._check(self._lib.spg_get_y_coordinate_batch(self._h, _ptr(x), _ptr(y), _ptr(st), x.shape[0], 0))
+        return y, st
+
+    def mimic_ec_mult_air(self, m, point_xy, shift_xy):
+        """m: (n, 4); point_xy, shift_xy: (n, 8) -> (out_xy (n, 8), status)."""
+        m = np.ascontiguousarray(m, dtype=np.uint64).reshape(-1, 4)
+        p = np.ascontiguousarray(point_xy, dtype=np.uint64).reshape(-1, 8)
+        s = np.ascontiguousarray(shift_xy, dtype=np.uint64).reshape(-1, 8)
+        out, st = np.empty_like(p), np.empty(m.shape[0], np.uint8)
+        self._check(self._lib.spg_mimic_ec_mult_air_batch(self._h, _ptr(m), _ptr(p), _ptr(s), _ptr(out), _ptr(st), m.shape[0], 0))
         return out, st
 
     def pedersen_merkle_tree(self, leaves, want_nodes=False):

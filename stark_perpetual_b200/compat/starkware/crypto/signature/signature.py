@@ -67,7 +67,59 @@ def pedersen_hash(*elements: int) -> int:
     return limbs_to_ints(out)[0]
 
 
+def pedersen_hash_as_point(*elements: int) -> ECPoint:
+    # signature.py:300-318
+    assert 1 <= len(elements) <= 2, "pedersen_params.json holds constant points for two elements only"
+    for x in elements:
+        assert 0 <= x < FIELD_PRIME
+    px, py, st = _ctx().pedersen_hash_point(ints_to_limbs(list(elements)), len(elements))
+    assert st[0] != 1
+    assert st[0] != 2, "Unhashable input."
+    return limbs_to_ints(px)[0], limbs_to_ints(py)[0]
+
+
 # ---------------------------------------------------------------------------------- keys
+def get_y_coordinate(stark_key_x_coordinate: int) -> int:
+    # signature.py:84-96 (Python ints reduce mod p silently; so does this wrapper)
+    y, st = _ctx().get_y_coordinate(ints_to_limbs([stark_key_x_coordinate % FIELD_PRIME]))
+    if st[0] == 1:
+        raise InvalidPublicKeyError()
+    return limbs_to_ints(y)[0]
+
+
+def get_random_private_key() -> int:
+    import secrets
+    return secrets.randbelow(EC_ORDER - 1) + 1                        # signature.py:99-101
+
+
+def is_point_on_curve(x: int, y: int) -> bool:
+    return pow(y, 2, FIELD_PRIME) == (pow(x, 3, FIELD_PRIME) + ALPHA * x + BETA) % FIELD_PRIME   # signature.py:193-194
+
+
+def is_valid_stark_private_key(private_key: int) -> bool:
+    return 0 < private_key < EC_ORDER                                 # signature.py:197-201
+
+
+def is_valid_stark_key(stark_key: int) -> bool:
+    # signature.py:204-214
+    try:
+        get_y_coordinate(stark_key_x_coordinate=stark_key)
+    except InvalidPublicKeyError:
+        return False
+    return True
+
+
+def mimic_ec_mult_air(m: int, point: ECPoint, shift_point: ECPoint) -> ECPoint:
+    # signature.py:176-190; every assertion of the reference surfaces as AssertionError
+    assert 0 < m < 2**N_ELEMENT_BITS_ECDSA
+    out, st = _ctx().mimic_ec_mult_air(ints_to_limbs([m]),
+                                       ints_to_limbs([point[0] % FIELD_PRIME, point[1] % FIELD_PRIME]).reshape(1, 8),
+                                       ints_to_limbs([shift_point[0] % FIELD_PRIME, shift_point[1] % FIELD_PRIME]).reshape(1, 8))
+    assert st[0] == 0
+    o = limbs_to_ints(out.reshape(2, 4))
+    return o[0], o[1]
+
+
 def private_key_to_ec_point_on_stark_curve(priv_key: int) -> ECPoint:
     assert 0 < priv_key < EC_ORDER                                    # signature.py:105
     x, y, st = _ctx().private_to_stark_key(ints_to_limbs([priv_key]), want_y=True)

@@ -59,7 +59,8 @@ __device__ __forceinline__ void load_canon(const uint64_t* src, uint32_t (&x)[8]
 #endif
 __global__ void __launch_bounds__(128, PEDERSEN_MIN_CTAS) k_pedersen_chain(const uint64_t* __restrict__ elems, int chain_len,
                                                         uint64_t* __restrict__ out, uint8_t* __restrict__ status,
-                                                        size_t n, const APoint* __restrict__ cp) {
+                                                        size_t n, const APoint* __restrict__ cp,
+                                                        uint64_t* __restrict__ out_y = nullptr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t* e = elems + i * (size_t)chain_len * 4;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(128, PEDERSEN_MIN_CTAS) k_pedersen_chain(const
     load_canon(e + 4 * k, x);
     if (spg_canon_geq_p(x)) st = 1;
   }
-  Fp res = fp_zero();
+  Fp res = fp_zero(), res_y = fp_zero();
   if (!st) {
     load_canon(e, x);
     int k = 1;
@@ -84,17 +85,23 @@ __global__ void __launch_bounds__(128, PEDERSEN_MIN_CTAS) k_pedersen_chain(const
         ok = pedersen_absorb(a, y, cp + 2 + SPG_HASH_BITS) && ok;
       }
       if (!ok) { st = 2; break; }
-      const Fp zi = fp_inv_chain(a.p.Z);
-      res = fp_from_mont(fp_mul(a.p.X, fp_sqr(zi)));
+      const Fp zi = fp_inv_chain(a.p.Z), zi2 = fp_sqr(zi);
+      res = fp_from_mont(fp_mul(a.p.X, zi2));
+      if (out_y) res_y = fp_from_mont(fp_mul(a.p.Y, fp_mul(zi2, zi)));     // pedersen_hash_as_point (signature.py:300)
 #pragma unroll
       for (int q = 0; q < 8; q++) x[q] = res.v[q];
       k++;
     } while (k < chain_len);
-    if (st) res = fp_zero();
+    if (st) { res = fp_zero(); res_y = fp_zero(); }
   }
   uint4* o = reinterpret_cast<uint4*>(out + 4 * i);
   o[0] = make_uint4(res.v[0], res.v[1], res.v[2], res.v[3]);
   o[1] = make_uint4(res.v[4], res.v[5], res.v[6], res.v[7]);
+  if (out_y) {
+    o = reinterpret_cast<uint4*>(out_y + 4 * i);
+    o[0] = make_uint4(res_y.v[0], res_y.v[1], res_y.v[2], res_y.v[3]);
+    o[1] = make_uint4(res_y.v[4], res_y.v[5], res_y.v[6], res_y.v[7]);
+  }
   status[i] = st;
 }
 
@@ -118,11 +125,11 @@ __global__ void k_limbs_to_be32(const uint64_t* __restrict__ in, uint8_t* __rest
 }
 
 int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len, uint64_t* out, uint8_t* status,
-                              size_t n) {
+                              size_t n, uint64_t* out_y = nullptr) {
   if (n == 0) return SPG_OK;
   const int threads = 128;
   k_pedersen_chain<<<(unsigned)((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
-      elems, chain_len, out, status, n, (const APoint*)ctx->const_points);
+      elems, chain_len, out, status, n, (const APoint*)ctx->const_points, out_y);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
@@ -252,5 +259,25 @@ extern "C" int spg_pedersen_merkle_tree(spg_ctx* ctx, const uint64_t* leaves, si
   uint8_t worst = 0;
   for (uint8_t v : st) if (v > worst) worst = v;
   *status_out = worst;
+  return SPG_OK;
+}
+
+// pedersen_hash_as_point (signature.py:300-318): both coordinates of the hash point of 1 or 2 elements per item.
+extern "C" int spg_pedersen_hash_point_batch(spg_ctx* ctx, const uint64_t* elems, size_t n_elems, uint64_t* out_x, uint64_t* out_y,
+                                             uint8_t* status, size_t n, int flags) {
+  SPG_ARG(ctx && elems && out_x && out_y && status, "spg_pedersen_hash_point_batch: null");
+  SPG_ARG(n_elems == 1 || n_elems == 2, "spg_pedersen_hash_point_batch: the constant-point table covers one or two elements");
+  SPG_ARG(!(flags & SPG_DEVICE_PTRS), "spg_pedersen_hash_point_batch: host pointers only");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  DevBuf be, bx, by, bs;
+  SPG_CUDA(be.alloc(ctx, n * n_elems * 32)); SPG_CUDA(bx.alloc(ctx, n * 32)); SPG_CUDA(by.alloc(ctx, n * 32)); SPG_CUDA(bs.alloc(ctx, n));
+  SPG_CUDA(cudaMemcpyAsync(be.p, elems, n * n_elems * 32, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = spg_pedersen_chain_device(ctx, be.as<uint64_t>(), (int)n_elems, bx.as<uint64_t>(), bs.as<uint8_t>(), n, by.as<uint64_t>());
+  if (rc) return rc;
+  SPG_CUDA(cudaMemcpyAsync(out_x, bx.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(out_y, by.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(status, bs.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
 }

@@ -171,3 +171,118 @@ extern "C" int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
   return SPG_OK;
 }
+
+// ------------------------------------------------------------------ the remaining building blocks of signature.py
+// get_y_coordinate (signature.py:84-96): y = the smaller square root of x^3 + x + beta.
+// status: 0 ok, 1 InvalidPublicKeyError (not a quadratic residue), 2 x is not a field element.
+__global__ void __launch_bounds__(128) k_get_y(const uint64_t* __restrict__ x, uint64_t* __restrict__ y,
+                                               uint8_t* __restrict__ status, size_t n, EcdsaTables T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t xl[8];
+  load8(x + 4 * i, xl);
+  Fp res = fp_zero();
+  uint8_t st = 0;
+  if (spg_canon_geq_p(xl)) st = 2;
+  else {
+    Fp xc; for (int k = 0; k < 8; k++) xc.v[k] = xl[k];
+    const Fp xm = fp_to_mont(xc);
+    const Fp rhs = fp_add(fp_add(fp_mul(fp_sqr(xm), xm), xm), T.beta);
+    Fp ym;
+    if (fp_sqrt_min(rhs, T, &ym)) res = fp_from_mont(ym); else st = 1;
+  }
+  uint4* o = reinterpret_cast<uint4*>(y + 4 * i);
+  o[0] = make_uint4(res.v[0], res.v[1], res.v[2], res.v[3]);
+  o[1] = make_uint4(res.v[4], res.v[5], res.v[6], res.v[7]);
+  status[i] = st;
+}
+
+// mimic_ec_mult_air (signature.py:176-190): m * point + shift_point with the AIR's steps.
+// status: 0 ok, 1 the reference raises AssertionError (m out of (0, 2^251), an x-collision, a doubling of y = 0),
+// 2 a coordinate is not a field element.
+__global__ void __launch_bounds__(64) k_mimic_mult(const uint64_t* __restrict__ m, const uint64_t* __restrict__ pt,
+                                                   const uint64_t* __restrict__ shift, uint64_t* __restrict__ out,
+                                                   uint8_t* __restrict__ status, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t ml[8], c[4][8];
+  load8(m + 4 * i, ml);
+  load8(pt + 8 * i, c[0]); load8(pt + 8 * i + 4, c[1]); load8(shift + 8 * i, c[2]); load8(shift + 8 * i + 4, c[3]);
+  uint8_t st = 0;
+  for (int k = 0; k < 4; k++) if (spg_canon_geq_p(c[k])) st = 2;
+  Fp ox = fp_zero(), oy = fp_zero();
+  if (!st) {
+    if (u256_is_zero(ml) || !u256_lt_2_251(ml)) st = 1;
+    else {
+      Fp f[4];
+      for (int k = 0; k < 4; k++) { Fp t; for (int q = 0; q < 8; q++) t.v[q] = c[k][q]; f[k] = fp_to_mont(t); }
+      JPoint p; p.X = f[0]; p.Y = f[1]; p.Z = fp_one();
+      APoint s; s.x = f[2]; s.y = f[3];
+      JPoint r;
+      if (!mimic_mult_var(ml, p, s, &r)) st = 1;
+      else {
+        const Fp zi = fp_inv_chain(r.Z), zi2 = fp_sqr(zi);
+        ox = fp_from_mont(fp_mul(r.X, zi2));
+        oy = fp_from_mont(fp_mul(r.Y, fp_mul(zi2, zi)));
+      }
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(out + 8 * i);
+  o[0] = make_uint4(ox.v[0], ox.v[1], ox.v[2], ox.v[3]); o[1] = make_uint4(ox.v[4], ox.v[5], ox.v[6], ox.v[7]);
+  o[2] = make_uint4(oy.v[0], oy.v[1], oy.v[2], oy.v[3]); o[3] = make_uint4(oy.v[4], oy.v[5], oy.v[6], oy.v[7]);
+  status[i] = st;
+}
+
+// host-buffer helper shared by the two entry points below: n items of `in_words` / `out_words` u64 words
+template <class Launch>
+static int run_simple(spg_ctx* ctx, const uint64_t* const* ins, const size_t* in_words, int n_in, uint64_t* out, size_t out_words,
+                      uint8_t* status, size_t n, int flags, Launch launch) {
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_ecdsa_tables(ctx);
+  if (rc) return rc;
+  const uint64_t* din[4] = {nullptr, nullptr, nullptr, nullptr};
+  uint64_t* dout = out; uint8_t* dst = status;
+  DevBuf bi[4], bo, bs;
+  for (int k = 0; k < n_in; k++) din[k] = ins[k];
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    for (int k = 0; k < n_in; k++) {
+      SPG_CUDA(bi[k].alloc(ctx, n * in_words[k] * 8));
+      SPG_CUDA(cudaMemcpyAsync(bi[k].p, ins[k], n * in_words[k] * 8, cudaMemcpyHostToDevice, ctx->stream));
+      din[k] = bi[k].as<uint64_t>();
+    }
+    SPG_CUDA(bo.alloc(ctx, n * out_words * 8)); SPG_CUDA(bs.alloc(ctx, n));
+    dout = bo.as<uint64_t>(); dst = bs.as<uint8_t>();
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  launch(din, dout, dst);
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(cudaMemcpyAsync(out, dout, n * out_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}
+
+extern "C" int spg_get_y_coordinate_batch(spg_ctx* ctx, const uint64_t* x, uint64_t* y, uint8_t* status, size_t n, int flags) {
+  SPG_ARG(ctx && x && y && status, "spg_get_y_coordinate_batch: null");
+  if (n == 0) return SPG_OK;
+  const uint64_t* ins[1] = {x};
+  const size_t words[1] = {4};
+  return run_simple(ctx, ins, words, 1, y, 4, status, n, flags, [&](const uint64_t* const* d, uint64_t* o, uint8_t* st) {
+    k_get_y<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d[0], o, st, n, make_tables(ctx, true));
+  });
+}
+
+extern "C" int spg_mimic_ec_mult_air_batch(spg_ctx* ctx, const uint64_t* m, const uint64_t* point_xy, const uint64_t* shift_xy,
+                                           uint64_t* out_xy, uint8_t* status, size_t n, int flags) {
+  SPG_ARG(ctx && m && point_xy && shift_xy && out_xy && status, "spg_mimic_ec_mult_air_batch: null");
+  if (n == 0) return SPG_OK;
+  const uint64_t* ins[3] = {m, point_xy, shift_xy};
+  const size_t words[3] = {4, 8, 8};
+  return run_simple(ctx, ins, words, 3, out_xy, 8, status, n, flags, [&](const uint64_t* const* d, uint64_t* o, uint8_t* st) {
+    k_mimic_mult<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(d[0], d[1], d[2], o, st, n);
+  });
+}

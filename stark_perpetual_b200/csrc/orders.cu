@@ -13,7 +13,8 @@
 #include "common.h"
 #include "../../include/spg.h"
 
-int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len, uint64_t* out, uint8_t* status, size_t n);
+int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len, uint64_t* out, uint8_t* status, size_t n,
+                              uint64_t* out_y = nullptr);
 int spg_ecdsa_verify_device(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* px,
                             const uint64_t* py, uint8_t* status, size_t n);
 

@@ -166,3 +166,51 @@ def test_pedersen_merkle_tree(ctx):
     assert st == 0 and limbs_to_ints(r2.reshape(1, 4))[0] == oph(3, 4)
     _r, _n, st = ctx.pedersen_merkle_tree(ints_to_limbs([3, P, 5, 6]))
     assert st == 1
+
+
+def test_remaining_signature_module_functions(ctx, golden):
+    """get_y_coordinate / is_valid_stark_key (reference-generated vectors), pedersen_hash_as_point, mimic_ec_mult_air and
+    the fast_pedersen_hash byte ABI, through the compat module, against the oracle."""
+    from oracle import pedersen as opedersen
+    from oracle.params import EC_GEN, SHIFT_POINT
+    sig = compat()
+    from starkware.crypto.signature import fast_pedersen_hash as fph
+    for x, y in golden["get_y"]:
+        if y is None:
+            with pytest.raises(sig.InvalidPublicKeyError):
+                sig.get_y_coordinate(int(x, 16))
+            assert not sig.is_valid_stark_key(int(x, 16))
+        else:
+            assert sig.get_y_coordinate(int(x, 16)) == int(y, 16)
+            assert sig.is_valid_stark_key(int(x, 16))
+    xs = [int(x, 16) for x, _y in golden["get_y"]] + [0, 1, P - 1]
+    ys, st = ctx.get_y_coordinate(ints_to_limbs(xs))
+    for x, y, s in zip(xs, limbs_to_ints(ys), st):
+        try:
+            assert (int(s), y) == (0, oecdsa.get_y_coordinate(x))
+        except oecdsa.InvalidPublicKeyError:
+            assert int(s) == 1
+    assert ctx.get_y_coordinate(ints_to_limbs([P]))[1][0] == 2
+    # hash as point
+    for a, b, _o, _t in golden["pedersen"][:6]:
+        assert sig.pedersen_hash_as_point(int(a, 16), int(b, 16)) == opedersen.pedersen_hash_as_point(int(a, 16), int(b, 16))
+    assert sig.pedersen_hash_as_point(5) == opedersen.pedersen_hash_as_point(5)
+    # mimic_ec_mult_air: values and the assertion cases
+    rng = random.Random(5)
+    q = oecdsa.private_key_to_ec_point_on_stark_curve(rng.randrange(1, EC_ORDER))
+    for m in (1, 2, 3, rng.randrange(1, 2**251), 2**251 - 1):
+        assert sig.mimic_ec_mult_air(m, q, SHIFT_POINT) == oecdsa.mimic_ec_mult_air(m, q, SHIFT_POINT)
+    assert sig.mimic_ec_mult_air(7, EC_GEN, q) == oecdsa.mimic_ec_mult_air(7, EC_GEN, q)
+    for bad in ((0, q, SHIFT_POINT), (2**251, q, SHIFT_POINT), (5, q, q), (5, q, (q[0], P - q[1]))):
+        with pytest.raises(AssertionError):
+            sig.mimic_ec_mult_air(*bad)
+        with pytest.raises(AssertionError):
+            oecdsa.mimic_ec_mult_air(*bad)
+    assert sig.is_point_on_curve(*q) and not sig.is_point_on_curve(q[0], q[1] + 1)
+    assert sig.is_valid_stark_private_key(1) and not sig.is_valid_stark_private_key(EC_ORDER)
+    assert sig.is_valid_stark_private_key(sig.get_random_private_key())
+    # byte ABI of fast_pedersen_hash
+    a, b = int(golden["pedersen"][0][0], 16), int(golden["pedersen"][0][1], 16)
+    assert fph.pedersen_hash(a, b) == int(golden["pedersen"][0][2], 16)
+    assert fph.pedersen_hash_func(a.to_bytes(32, "big"), b.to_bytes(32, "big")) == int(golden["pedersen"][0][2], 16).to_bytes(32, "big")
+    assert fph.pedersen_hash_func_batch(a.to_bytes(32, "big") * 3, b.to_bytes(32, "big") * 3) == int(golden["pedersen"][0][2], 16).to_bytes(32, "big") * 3
