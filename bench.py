@@ -115,7 +115,7 @@ def cpu_sample(cfg):
     """Time the C oracle (OpenMP) on a bounded sample of the proof's dominant stage: the blowup-8 LDE of as
     many 2^log_n columns as there are host threads (one per thread).  Returns (mul/s, cores, text, seconds)."""
     from oracle import clib
-    cores = clib.num_threads()
+    cores = clib.use_all_cores()
     sample_cols = max(1, min(25, cores))
     tr = host_trace_random(sample_cols, cfg["log_n"], 4242)
     t0 = time.perf_counter()

@@ -182,6 +182,15 @@ void spgo_lde(const uint64_t* trace, unsigned log_n, size_t C, unsigned log_blow
   free(twi); free(twf);
 }
 
+/* use `n` OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1, which would starve the CPU baseline) */
+void spgo_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int spgo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -32,6 +32,12 @@ def num_threads():
     return lib().spgo_num_threads()
 
 
+def use_all_cores():
+    """All host cores for the OpenMP loops, whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    lib().spgo_set_threads(C.c_int(os.cpu_count() or 1))
+    return num_threads()
+
+
 def mul_batch(a, b):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     b = np.ascontiguousarray(b, dtype=np.uint64)
