@@ -22,8 +22,8 @@ struct spg_ctx {
   uint64_t launches = 0;
   std::string err;
   // NTT tables (device, Montgomery form)
-  Fp* tw_fwd = nullptr;   // omega_1024^e, 512
-  Fp* tw_inv = nullptr;   // omega_1024^-e, 512
+  Fp* tw_fwd = nullptr;   // omega_2048^e, 1024 (SPG_TW_LOG in ntt.cuh)
+  Fp* tw_inv = nullptr;   // omega_2048^-e, 1024
   Fp* uniA = nullptr;     // omega_{2^26}^(i << 13), 8192
   Fp* uniB = nullptr;     // omega_{2^26}^i, 8192
   // curve tables
@@ -163,6 +163,8 @@ int spg_from_mont_device(spg_ctx* ctx, Fp* data, size_t n);
 int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
                    const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table = nullptr);
+// ntt.cu: log2 of the shared-memory workspace (= the largest pass) the NTT kernels use for a 2^log_n transform
+int spg_ntt_tile_log_ws(unsigned log_n);
 // ntt.cu: fill a direct diagonal table for the second pass of a two-pass forward DIT with coset exponent coset_exp
 int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, unsigned long long coset_exp, Fp* table);
 int spg_bitrev_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols);

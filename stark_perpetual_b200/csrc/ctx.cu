@@ -2,6 +2,7 @@
 #include <string.h>
 
 #include "common.h"
+#include "ntt.cuh"
 
 // ------------------------------------------------------------------ host helpers
 static void exp_root(int log_n, uint32_t e[8]) {
@@ -34,12 +35,13 @@ static int upload(spg_ctx* ctx, const std::vector<Fp>& h, Fp** d) {
 int spg_curve_tables_init(spg_ctx* ctx);   // ec.cu
 
 static int build_tables(spg_ctx* ctx) {
-  // intra-tile twiddles omega_1024^(+-e)
-  Fp w = spg_host_root_of_unity(10);
+  // intra-tile twiddles omega_{2^SPG_TW_LOG}^(+-e), e < 2^(SPG_TW_LOG - 1)
+  Fp w = spg_host_root_of_unity(SPG_TW_LOG);
   Fp wi = fp_inv(w);
-  std::vector<Fp> f(512), b(512);
+  const int ntw = 1 << (SPG_TW_LOG - 1);
+  std::vector<Fp> f(ntw), b(ntw);
   f[0] = b[0] = fp_one();
-  for (int i = 1; i < 512; i++) { f[i] = fp_mul(f[i - 1], w); b[i] = fp_mul(b[i - 1], wi); }
+  for (int i = 1; i < ntw; i++) { f[i] = fp_mul(f[i - 1], w); b[i] = fp_mul(b[i - 1], wi); }
   int rc;
   if ((rc = upload(ctx, f, &ctx->tw_fwd))) return rc;
   if ((rc = upload(ctx, b, &ctx->tw_inv))) return rc;

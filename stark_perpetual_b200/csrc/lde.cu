@@ -20,7 +20,7 @@ static int ensure_scale_tables(spg_ctx* ctx, unsigned log_n, const uint64_t* off
       return SPG_OK;
     }
   std::vector<Fp> lo, hi;
-  spg_lde_scale_tables(log_n, spg_host_from_u64(offset), lo, hi);
+  spg_lde_scale_tables(log_n, spg_ntt_tile_log_ws(log_n), spg_host_from_u64(offset), lo, hi);
   if (mont) for (auto& v : lo) v = fp_mul(v, fp_r2());     // extra factor R: canonical in -> Montgomery out
   const size_t R = lo.size(), B = hi.size();
   if (ctx->lde_tables.size() >= 8) {   // tiny cache: drop the oldest entry
@@ -62,7 +62,8 @@ int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t 
 // the launch and stays L2-resident; it replaces the two-level lookup's multiplication in the load phase of pass 2.
 static int ensure_diag_tables(spg_ctx* ctx, unsigned log_n, unsigned log_blowup, const Fp** out) {
   *out = nullptr;
-  if (log_n < 11 || log_n > 20 || log_blowup > 3) return SPG_OK;      // single-pass or three-pass sizes: two-level lookup
+  if (log_n <= (unsigned)spg_ntt_tile_log_ws(log_n) || log_n > 2 * (unsigned)spg_ntt_tile_log_ws(log_n) || log_blowup > 3)
+    return SPG_OK;      // single-pass or three-pass sizes: two-level lookup
   for (auto& t : ctx->diag_tables)
     if (t.log_n == (int)log_n && t.log_blowup == (int)log_blowup) { *out = t.t; return SPG_OK; }
   const size_t n = (size_t)1 << log_n, nb = (size_t)1 << log_blowup;

@@ -3,33 +3,33 @@
 #include "common.h"
 #include "ntt.cuh"
 
-// Tile shape, chosen by measurement on B200 (profiles/r1e_ntt_variants.md): a 2^10-element workspace (32 KB), radix-4
-// steps (4 elements per thread, 256 threads), 64 registers -> 4 CTAs = 32 warps per SM.  The radix-8 / 2^11 shape
-// needs 128 registers (16 warps per SM) and is 7-9 % slower at 2^20 and above.
+// Tile shapes, chosen by measurement on B200: radix-4 steps (4 elements per thread, 64 registers).  The default
+// workspace is 2^10 elements (32 KB, 256 threads, 4 CTAs = 32 warps per SM); transforms of 2^21 and 2^22 points use a
+// 2^11 workspace (64 KB, 512 threads, 2 CTAs per SM) so that they stay at two passes.  The radix-8 / 128-register
+// shape of the first version is 7-9 % slower at 2^20 and above.
 #ifndef NTT_LOG_WS
 #define NTT_LOG_WS 10
 #endif
 #ifndef NTT_LOG_EPT
 #define NTT_LOG_EPT 2
 #endif
-typedef NttTile<NTT_LOG_WS, NTT_LOG_EPT> Tile;
 
-#ifndef NTT_MIN_CTAS
-#define NTT_MIN_CTAS 4
-#endif
+int spg_ntt_tile_log_ws(unsigned log_n) { return (log_n == 21 || log_n == 22) ? 11 : NTT_LOG_WS; }
+
 // Synchronisation between the phases of a pass.  When the pass uses the whole workspace for one column (log_g = 0,
 // log_r = LOG_WS) and every thread owns exactly one butterfly group per step, a step with sh + w <= 5 + LOG_EPT only
 // touches rows inside the 2^(5 + LOG_EPT)-row window [warp * 128, warp * 128 + 128): warp w of the CTA reads and writes
 // that window and nothing else.  Consecutive such phases therefore need a warp barrier only -- three of the six
 // CTA-wide barriers of a 10-bit pass (the load / store phase is mapped onto the same windows).
-template <bool DIT>
-__global__ void __launch_bounds__(Tile::NT, NTT_MIN_CTAS) k_ntt_pass(NttPass P) {
+template <bool DIT, int LOG_WS>
+__global__ void __launch_bounds__((1 << LOG_WS) >> NTT_LOG_EPT, LOG_WS == 10 ? 4 : 2) k_ntt_pass(NttPass P) {
+  typedef NttTile<LOG_WS, NTT_LOG_EPT> Tile;
   extern __shared__ uint4 smem_raw[];
   FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
   const int tid = threadIdx.x;
   const unsigned cta = blockIdx.x, col = blockIdx.y;
   constexpr int LW = 5 + NTT_LOG_EPT;                       // log2 rows per warp window
-  const bool windowed = (P.log_g == 0 && P.log_r == NTT_LOG_WS);
+  const bool windowed = (P.log_g == 0 && P.log_r == LOG_WS);
   const int ns = Tile::n_steps(P);
   auto local = [&](int k) {                                 // phase k: -1 = load, ns = store, else butterfly step k
     if (!windowed) return false;
@@ -73,12 +73,12 @@ __global__ void k_build_diag_table(NttPass P, Fp* __restrict__ table) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ((size_t)1 << (P.log_r + P.log_s))) return;
   const unsigned long long k = idx & ((1ull << P.log_r) - 1), c = idx >> P.log_r;
-  table[idx] = fp_reduce(Tile::uni_pow(P, k * (c * P.ec + P.e0)));
+  table[idx] = fp_reduce(NttTile<NTT_LOG_WS, NTT_LOG_EPT>::uni_pow(P, k * (c * P.ec + P.e0)));
 }
 
 int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, unsigned long long coset_exp, Fp* table) {
   NttPass passes[8];
-  const int np = spg_ntt_make_passes(passes, NTT_LOG_WS, nullptr, nullptr, log_n, 0, 0, 0, /*dit=*/1, coset_exp, nullptr, nullptr,
+  const int np = spg_ntt_make_passes(passes, spg_ntt_tile_log_ws(log_n), nullptr, nullptr, log_n, 0, 0, 0, /*dit=*/1, coset_exp, nullptr, nullptr,
                                      ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
   SPG_ARG(np == 2, "diag table: two-pass transforms only");
   const NttPass& P = passes[1];
@@ -94,24 +94,32 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
   SPG_ARG(log_n <= 26, "NTT size above 2^26 not supported by the universal twiddle table");
   SPG_ARG(ncols < 65536, "too many columns in one NTT batch");
   if (ncols == 0) return SPG_OK;
-  const int smem = Tile::WS * (int)sizeof(Fp);
+  const int log_ws = spg_ntt_tile_log_ws(log_n);
   bool& attr_set = ctx->ntt_attr_set;
   if (!attr_set) {
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false, NTT_LOG_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_LOG_WS) * 32));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, NTT_LOG_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_LOG_WS) * 32));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
     attr_set = true;
   }
   NttPass passes[8];
   if (!dit && coset_exp != 0) { ctx->err = "coset shift only supported for DIT"; return SPG_E_ARG; }
-  const int np = spg_ntt_make_passes(passes, NTT_LOG_WS, in, out, log_n, in_stride, out_stride, inverse, dit,
+  const int np = spg_ntt_make_passes(passes, log_ws, in, out, log_n, in_stride, out_stride, inverse, dit,
                                      coset_exp, scale_lo, scale_hi, ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
   if (diag_table && np == 2 && dit && !inverse) passes[1].diag_table = diag_table;
+  const int smem = (1 << log_ws) * (int)sizeof(Fp), threads = (1 << log_ws) >> NTT_LOG_EPT;
   for (int pi = 0; pi < np; pi++) {
     const NttPass& P = passes[pi];
     const size_t ctas = ((size_t)1 << log_n) >> (P.log_r + P.log_g);
     dim3 grid((unsigned)ctas, (unsigned)ncols);
-    if (dit) k_ntt_pass<true><<<grid, Tile::NT, smem, ctx->stream>>>(P);
-    else k_ntt_pass<false><<<grid, Tile::NT, smem, ctx->stream>>>(P);
+    if (log_ws == 11) {
+      if (dit) k_ntt_pass<true, 11><<<grid, threads, smem, ctx->stream>>>(P);
+      else k_ntt_pass<false, 11><<<grid, threads, smem, ctx->stream>>>(P);
+    } else {
+      if (dit) k_ntt_pass<true, NTT_LOG_WS><<<grid, threads, smem, ctx->stream>>>(P);
+      else k_ntt_pass<false, NTT_LOG_WS><<<grid, threads, smem, ctx->stream>>>(P);
+    }
     SPG_LAUNCH_CHECK();
   }
   return SPG_OK;
@@ -148,7 +156,7 @@ extern "C" int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batc
   const Fp* scale_hi = nullptr;
   if (inverse) {
     int lr, lb;
-    spg_ntt_last_pass_geometry(log_n, &lr, &lb);
+    spg_ntt_last_pass_geometry(log_n, spg_ntt_tile_log_ws(log_n), &lr, &lb);
     uint64_t nn[4] = {(uint64_t)n, 0, 0, 0};
     Fp ninv = fp_inv(spg_host_from_u64(nn));
     SPG_CUDA(sc.alloc(ctx, ((size_t)1 << lb) * 32));

@@ -20,7 +20,7 @@
 #pragma once
 #include "fp.cuh"
 
-#define SPG_TW_LOG 10          // intra-tile twiddle table: omega_1024^e, e < 512
+#define SPG_TW_LOG 11          // intra-tile twiddle table: omega_2048^e, e < 1024 (passes of up to 11 bits)
 #define SPG_UNI_LOG 26         // universal two-level table: omega_{2^26}^e = uniA[e >> 13] * uniB[e & 8191]
 #define SPG_UNI_HALF 13
 
@@ -32,7 +32,7 @@ struct NttPass {
   int log_r, log_s;            // this pass: rows R, row stride S   (B = N / (R S))
   int log_g;                   // S > 1: columns per CTA;  S == 1: tiles per CTA
   int inverse;                 // use omega^-1
-  const Fp* tw;                // omega_1024^e  (forward) or omega_1024^-e (inverse), 512 entries
+  const Fp* tw;                // omega_2048^e  (forward) or omega_2048^-e (inverse), 1024 entries
   const Fp* uniA;              // universal table, high part (8192 entries)
   const Fp* uniB;              // universal table, low part (8192 entries)
   // diagonal twiddle  omega_{2^26}^( +- bitrev_R(r) * (c * ec + e0) )  applied AFTER a DIF pass /
@@ -286,10 +286,10 @@ struct NttTile {
 };
 
 // ------------------------------------------------------------------ pass planner (host)
-// Split log_n into per-pass tile sizes (each <= 10 bits, as even as possible, larger first).
-static inline int spg_ntt_plan_bits(unsigned log_n, int bits[8]) {
+// Split log_n into per-pass tile sizes (each <= max_bits = log2 of the workspace, as even as possible, larger first).
+static inline int spg_ntt_plan_bits(unsigned log_n, int bits[8], int max_bits) {
   if (log_n == 0) { bits[0] = 0; return 1; }
-  int np = (log_n + 9) / 10;
+  int np = ((int)log_n + max_bits - 1) / max_bits;
   int base = log_n / np, extra = log_n % np;
   for (int i = 0; i < np; i++) bits[i] = base + (i < extra ? 1 : 0);
   return np;
@@ -297,9 +297,9 @@ static inline int spg_ntt_plan_bits(unsigned log_n, int bits[8]) {
 
 // geometry of the pass that touches contiguous tiles (last for DIF, first for DIT):
 // it sees the column as [2^log_b_hi blocks][2^log_r_lo rows]
-static inline void spg_ntt_last_pass_geometry(unsigned log_n, int* log_r_lo, int* log_b_hi) {
+static inline void spg_ntt_last_pass_geometry(unsigned log_n, int max_bits, int* log_r_lo, int* log_b_hi) {
   int bits[8];
-  int np = spg_ntt_plan_bits(log_n, bits);
+  int np = spg_ntt_plan_bits(log_n, bits, max_bits);
   *log_r_lo = bits[np - 1];
   *log_b_hi = (int)log_n - bits[np - 1];
 }
@@ -314,7 +314,7 @@ static inline int spg_ntt_make_passes(NttPass* passes, int log_ws, const Fp* in,
                                       const Fp* scale_hi, const Fp* tw_fwd, const Fp* tw_inv, const Fp* uniA,
                                       const Fp* uniB) {
   int bits[8];
-  const int np = spg_ntt_plan_bits(log_n, bits);
+  const int np = spg_ntt_plan_bits(log_n, bits, log_ws);
   for (int pi = 0; pi < np; pi++) {
     const int i = dit ? np - 1 - pi : pi;
     int log_s = 0;
@@ -351,9 +351,9 @@ static inline int spg_ntt_make_passes(NttPass* passes, int log_ws, const Fp* in,
 #include <vector>
 // LDE scale tables for the store phase of the inverse DIF: output position b*R + r holds coefficient
 // k = bitrev_R(r) * B + bitrev_B(b), which gets  g^k / N = lo[r] * hi[b].
-static inline void spg_lde_scale_tables(unsigned log_n, const Fp& g_mont, std::vector<Fp>& lo, std::vector<Fp>& hi) {
+static inline void spg_lde_scale_tables(unsigned log_n, int max_bits, const Fp& g_mont, std::vector<Fp>& lo, std::vector<Fp>& hi) {
   int lr, lb;
-  spg_ntt_last_pass_geometry(log_n, &lr, &lb);
+  spg_ntt_last_pass_geometry(log_n, max_bits, &lr, &lb);
   const size_t R = (size_t)1 << lr, B = (size_t)1 << lb;
   lo.resize(R); hi.resize(B);
   uint64_t nn[4] = {(uint64_t)1 << log_n, 0, 0, 0};

@@ -48,10 +48,11 @@ int main(int argc, char** argv) {
   int log_blowup = argc > 2 ? atoi(argv[2]) : 3;
   const size_t n = (size_t)1 << log_n, nb = (size_t)1 << log_blowup;
   const unsigned C = 2;
-  Fp w1024 = root(10), w1024i = fp_inv(w1024);
-  std::vector<Fp> twf(512), twi(512), A(8192), B(8192);
+  Fp w1024 = root(SPG_TW_LOG), w1024i = fp_inv(w1024);
+  const int ntw = 1 << (SPG_TW_LOG - 1);
+  std::vector<Fp> twf(ntw), twi(ntw), A(8192), B(8192);
   twf[0] = twi[0] = fp_one();
-  for (int i = 1; i < 512; i++) { twf[i] = fp_mul(twf[i - 1], w1024); twi[i] = fp_mul(twi[i - 1], w1024i); }
+  for (int i = 1; i < ntw; i++) { twf[i] = fp_mul(twf[i - 1], w1024); twi[i] = fp_mul(twi[i - 1], w1024i); }
   Fp u = root(26);
   B[0] = fp_one();
   for (int i = 1; i < 8192; i++) B[i] = fp_mul(B[i - 1], u);
@@ -68,7 +69,7 @@ int main(int argc, char** argv) {
   }
   const Fp g = from_u64(3);
   std::vector<Fp> lo, hi;
-  spg_lde_scale_tables(log_n, g, lo, hi);
+  spg_lde_scale_tables(log_n, EMUL_LOG_WS, g, lo, hi);
   NttPass passes[8];
   int np = spg_ntt_make_passes(passes, EMUL_LOG_WS, x.data(), coef.data(), log_n, n, n, 1, 0, 0, lo.data(), hi.data(),
                                twf.data(), twi.data(), A.data(), B.data());

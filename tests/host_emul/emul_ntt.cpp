@@ -52,10 +52,11 @@ int main(int argc, char** argv) {
   const size_t n = (size_t)1 << log_n;
   const unsigned ncols = 2;
   // tables
-  Fp w1024 = root(10), w1024i = fp_inv(w1024);
-  std::vector<Fp> twf(512), twi(512), A(8192), B(8192);
+  Fp w1024 = root(SPG_TW_LOG), w1024i = fp_inv(w1024);
+  const int ntw = 1 << (SPG_TW_LOG - 1);
+  std::vector<Fp> twf(ntw), twi(ntw), A(8192), B(8192);
   twf[0] = twi[0] = fp_one();
-  for (int i = 1; i < 512; i++) { twf[i] = fp_mul(twf[i - 1], w1024); twi[i] = fp_mul(twi[i - 1], w1024i); }
+  for (int i = 1; i < ntw; i++) { twf[i] = fp_mul(twf[i - 1], w1024); twi[i] = fp_mul(twi[i - 1], w1024i); }
   Fp u = root(26);
   B[0] = fp_one();
   for (int i = 1; i < 8192; i++) B[i] = fp_mul(B[i - 1], u);
@@ -111,7 +112,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < n; i++) in[c * n + (dit ? spg_bitrev((unsigned)i, log_n) : i)] = x[c * n + i];
   // inverse scaling through scale_hi
   int lr, lb;
-  spg_ntt_last_pass_geometry(log_n, &lr, &lb);
+  spg_ntt_last_pass_geometry(log_n, EMUL_LOG_WS, &lr, &lb);
   std::vector<Fp> sc((size_t)1 << lb, inverse ? fp_inv(from_u64(n)) : fp_one());
   NttPass passes[8];
   int np = spg_ntt_make_passes(passes, EMUL_LOG_WS, in.data(), y.data(), log_n, n, n, inverse, dit, coset_exp, nullptr,
