@@ -108,7 +108,10 @@ struct AirEvalConsts {
   Fp shift_x, shift_y;
 };
 
-__global__ void __launch_bounds__(128) k_air_eval(unsigned log_n, unsigned log_seg, const Fp* __restrict__ t_lde,
+#ifndef AIR_MIN_CTAS
+#define AIR_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(128, AIR_MIN_CTAS) k_air_eval(unsigned log_n, unsigned log_seg, const Fp* __restrict__ t_lde,
                                                   const AirEvalConsts* __restrict__ K, const Fp* __restrict__ izt,
                                                   const Fp* __restrict__ plde, const Fp* __restrict__ ilast,
                                                   Fp* __restrict__ cp, int first_coset, int jj0, int n_even) {
