@@ -78,10 +78,13 @@ struct NttTile {
   static SPG_HD int slot(const NttPass& P, int r, int g) {
     return P.log_s ? ((r << P.log_g) | g) : ((g << P.log_r) | r);
   }
-  // swizzled position of a slot: the low 3 bits are XORed with the fold of all higher 3-bit groups
+  // swizzled position of a slot: the low 3 bits are XORed with the fold of all higher 3-bit groups, plus slot bit 4
+  // into bit 2.  Over GF(2) this makes the 8 slots of a quarter-warp distinct modulo 8 for every access pattern of
+  // the kernel: consecutive slots, any power-of-two stride >= 8, stride 4 (radix-4 step at shift 0) and the mixed
+  // pattern of the radix-4 step at shift 2 (four consecutive slots, then +16), which the plain fold maps 2-way.
   static SPG_HD int swz(int s) {
     int u = s >> 3;
-    return s ^ ((u ^ (u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7);
+    return s ^ ((u ^ (u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7) ^ ((u & 2) << 1);
   }
   static SPG_HD Fp ws_load(const FpHalf* ws, int s) {
     const int i = swz(s);
