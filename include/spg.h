@@ -62,7 +62,8 @@ double spg_stage_ms(spg_ctx* ctx, int stage);
 int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n,
                  int flags);
 /* throughput probe: every thread runs `iters` dependent Montgomery multiplications on `chains`
- * independent accumulators; returns field multiplications per second in *mul_per_s. */
+ * independent accumulators; returns field multiplications per second in *mul_per_s, and the issue rate of
+ * IMAD.WIDE (carry-chained rows, the multiplication's own pattern) in *imad_wide_per_s. */
 int spg_bench_field_mul(spg_ctx* ctx, int iters, int chains, double* mul_per_s, double* imad_wide_per_s);
 
 /* ---- Pedersen hash (BASELINE.json configs[0]) ------------------------------------
