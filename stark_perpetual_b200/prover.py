@@ -473,7 +473,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
     # 4. DEEP quotient on the local cosets
     tick("deep_quotient")
     gamma = ch.draw_felt()
-    layers, trees, tops = [be.felts(cs, n)], [None], [None]
+    layers, trees = [be.felts(cs, n)], [None]
     be.deep(t_lde, h_lde, log_n, first, cs, z, gamma, oods, layers[0])
     # 5. FRI.  Only the first fold works on sharded data: its output (N/8 rows per coset, 32 MB at 2^20) is
     # all-gathered once, and every rank then folds and commits the remaining, geometrically shrinking layers
