@@ -80,3 +80,26 @@ def test_limit_order_elements_layout(pm):
     assert e[4] == (3 << 241) | (0x1234 << 177) | (0x1234 << 113) | (0x1234 << 49) | (0x5678 << 17)
     e = pm.limit_order_elements(7, 9, 1, 11, 0xAAAA, 0xBBBB, 0xCCCC, 0xDDDD, 0x1234, 0x5678)
     assert e[:2] == [9, 7] and e[3] >> 160 == 0xBBBB
+
+
+def test_compat_signature_host_side_pieces(golden):
+    """The host-side parts of the compat signature module (no GPU needed): constants, grind_key (key_derivation.spec.js
+    KAT + reference-generated vectors), the RFC 6979 nonce derivation against the oracle's, and the pure predicates."""
+    sys.path.insert(0, COMPAT)
+    try:
+        from starkware.crypto.signature import signature as sig
+    finally:
+        sys.path.remove(COMPAT)
+    from oracle import ecdsa as oecdsa, params
+    assert (sig.FIELD_PRIME, sig.EC_ORDER, sig.ALPHA, sig.BETA, sig.FIELD_GEN) == (
+        params.FIELD_PRIME, params.EC_ORDER, params.ALPHA, params.BETA, 3)
+    assert sig.SHIFT_POINT == params.SHIFT_POINT and sig.EC_GEN == params.EC_GEN
+    assert sig.N_ELEMENT_BITS_ECDSA == 251 and sig.N_ELEMENT_BITS_HASH == 252
+    for a, b, o in golden["grind_key"]:
+        assert sig.grind_key(int(a, 16), int(b, 16)) == int(o, 16)
+    for mh, priv, _r, _s in golden["sign_js_kat"]:
+        for seed in (None, 1, 77):
+            assert sig.generate_k_rfc6979(int(mh, 16), int(priv, 16), seed) == oecdsa.generate_k_rfc6979(int(mh, 16), int(priv, 16), seed)
+    assert sig.is_valid_stark_private_key(1) and not sig.is_valid_stark_private_key(0)
+    assert sig.is_point_on_curve(*params.EC_GEN) and not sig.is_point_on_curve(1, 1)
+    assert sig.inv_mod_curve_size(7) * 7 % params.EC_ORDER == 1
