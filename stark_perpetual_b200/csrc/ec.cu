@@ -60,15 +60,17 @@ __device__ __forceinline__ void load_canon(const uint64_t* src, uint32_t (&x)[8]
 __global__ void __launch_bounds__(128, PEDERSEN_MIN_CTAS) k_pedersen_chain(const uint64_t* __restrict__ elems, int chain_len,
                                                         uint64_t* __restrict__ out, uint8_t* __restrict__ status,
                                                         size_t n, const APoint* __restrict__ cp,
-                                                        uint64_t* __restrict__ out_y = nullptr) {
+                                                        uint64_t* __restrict__ out_y = nullptr,
+                                                        const uint64_t* __restrict__ second = nullptr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t* e = elems + i * (size_t)chain_len * 4;
+  // `second` != null: pairs given as two separate arrays (x in elems, y in second), chain_len == 2
+  const uint64_t* e = second ? elems + i * 4 : elems + i * (size_t)chain_len * 4;
   uint32_t x[8];
   uint8_t st = 0;
   // range checks first (signature.py:307)
   for (int k = 0; k < chain_len; k++) {
-    load_canon(e + 4 * k, x);
+    load_canon((second && k == 1) ? second + i * 4 : e + 4 * k, x);
     if (spg_canon_geq_p(x)) st = 1;
   }
   Fp res = fp_zero(), res_y = fp_zero();
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(128, PEDERSEN_MIN_CTAS) k_pedersen_chain(const
       bool ok = pedersen_absorb(a, x, cp + 2);
       if (k < chain_len) {
         uint32_t y[8];
-        load_canon(e + 4 * k, y);
+        load_canon((second && k == 1) ? second + i * 4 : e + 4 * k, y);
         ok = pedersen_absorb(a, y, cp + 2 + SPG_HASH_BITS) && ok;
       }
       if (!ok) { st = 2; break; }
@@ -125,11 +127,11 @@ __global__ void k_limbs_to_be32(const uint64_t* __restrict__ in, uint8_t* __rest
 }
 
 int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len, uint64_t* out, uint8_t* status,
-                              size_t n, uint64_t* out_y = nullptr) {
+                              size_t n, uint64_t* out_y = nullptr, const uint64_t* second = nullptr) {
   if (n == 0) return SPG_OK;
   const int threads = 128;
   k_pedersen_chain<<<(unsigned)((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
-      elems, chain_len, out, status, n, (const APoint*)ctx->const_points, out_y);
+      elems, chain_len, out, status, n, (const APoint*)ctx->const_points, out_y, second);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
@@ -167,19 +169,18 @@ extern "C" int spg_pedersen_hash2_batch(spg_ctx* ctx, const uint64_t* x, const u
   SPG_ARG(ctx && x && y && out && status, "spg_pedersen_hash2_batch: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
-  // interleave (x, y) pairs on the device, then run the chain kernel with chain_len = 2
-  DevBuf pairs, bo, bs;
-  SPG_CUDA(pairs.alloc(ctx, n * 64));
-  const cudaMemcpyKind kind = (flags & SPG_DEVICE_PTRS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  SPG_CUDA(cudaMemcpy2DAsync(pairs.p, 64, x, 32, 32, n, kind, ctx->stream));
-  SPG_CUDA(cudaMemcpy2DAsync((char*)pairs.p + 32, 64, y, 32, 32, n, kind, ctx->stream));
+  // the kernel reads x and y from their own arrays (contiguous uploads; no interleaving copy)
+  DevBuf bx, by, bo, bs;
+  const uint64_t *dx = x, *dy = y;
   uint64_t* dout = out; uint8_t* dst = status;
   if (!(flags & SPG_DEVICE_PTRS)) {
-    SPG_CUDA(bo.alloc(ctx, n * 32)); SPG_CUDA(bs.alloc(ctx, n));
-    dout = bo.as<uint64_t>(); dst = bs.as<uint8_t>();
+    SPG_CUDA(bx.alloc(ctx, n * 32)); SPG_CUDA(by.alloc(ctx, n * 32)); SPG_CUDA(bo.alloc(ctx, n * 32)); SPG_CUDA(bs.alloc(ctx, n));
+    SPG_CUDA(cudaMemcpyAsync(bx.p, x, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(by.p, y, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    dx = bx.as<uint64_t>(); dy = by.as<uint64_t>(); dout = bo.as<uint64_t>(); dst = bs.as<uint8_t>();
   }
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  int rc = spg_pedersen_chain_device(ctx, pairs.as<uint64_t>(), 2, dout, dst, n);
+  int rc = spg_pedersen_chain_device(ctx, dx, 2, dout, dst, n, nullptr, dy);
   if (rc) return rc;
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!(flags & SPG_DEVICE_PTRS)) {

@@ -14,7 +14,7 @@
 #include "../../include/spg.h"
 
 int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len, uint64_t* out, uint8_t* status, size_t n,
-                              uint64_t* out_y = nullptr);
+                              uint64_t* out_y = nullptr, const uint64_t* second = nullptr);
 int spg_ecdsa_verify_device(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* px,
                             const uint64_t* py, uint8_t* status, size_t n);
 
