@@ -52,6 +52,33 @@ __global__ void __launch_bounds__(128) k_merkle_nodes(const uint32_t* __restrict
 // tree over L = n_cosets * rows / 8 leaves (the table holds n_cosets consecutive cosets; 8 = the whole table,
 // fewer = the sub-tree one GPU owns): L leaf digests followed by L/2, L/4, ... 1 nodes: 2L - 1 digests of
 // 32 bytes.  Level l (0 = leaves) starts at digest offset  2L - (2L >> l).
+// the top of a tree in ONE launch: from a level of n_in <= 1024 digests up to the root, one CTA, levels separated by
+// CTA barriers (the upper ten levels of every tree are launch-latency, not work)
+__global__ void __launch_bounds__(512) k_merkle_top(uint32_t* __restrict__ tree, size_t off, int n_in) {
+  __shared__ uint32_t lvl[2][1024 * 8 / 2];     // ping-pong: at most 512 digests are ever written
+  const int tid = threadIdx.x;
+  const uint32_t* src = tree + 8 * off;
+  size_t out_off = off + (size_t)n_in;
+  int cur = 0;
+  for (int n = n_in; n > 1; n >>= 1) {
+    const int n_out = n >> 1;
+    if (tid < n_out) {
+      uint32_t m[16];
+#pragma unroll
+      for (int k = 0; k < 16; k++) m[k] = src[16 * tid + k];
+      B2s st;
+      b2s_init(st);
+      b2s_compress(st, m, 64, true);
+#pragma unroll
+      for (int k = 0; k < 8; k++) { lvl[cur][8 * tid + k] = st.h[k]; tree[8 * (out_off + tid) + k] = st.h[k]; }
+    }
+    __syncthreads();
+    src = lvl[cur];
+    cur ^= 1;
+    out_off += n_out;
+  }
+}
+
 int spg_merkle_build_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows, uint32_t* tree, int n_cosets) {
   SPG_ARG(rows >= 8 && (rows & (rows - 1)) == 0, "merkle: rows must be a power of two >= 8");
   SPG_ARG(n_cosets == 1 || n_cosets == 2 || n_cosets == 4 || n_cosets == 8, "merkle: n_cosets");
@@ -60,6 +87,11 @@ int spg_merkle_build_device(spg_ctx* ctx, const Fp* table, int ncols, size_t row
   SPG_LAUNCH_CHECK();
   size_t off = 0, n = n_leaves;
   while (n > 1) {
+    if (n <= 1024) {
+      k_merkle_top<<<1, 512, 0, ctx->stream>>>(tree, off, (int)n);
+      SPG_LAUNCH_CHECK();
+      break;
+    }
     const size_t n_out = n / 2;
     k_merkle_nodes<<<(unsigned)((n_out + 127) / 128), 128, 0, ctx->stream>>>(tree + 8 * off, tree + 8 * (off + n), n_out);
     SPG_LAUNCH_CHECK();
