@@ -73,3 +73,32 @@ def test_lde_interpolates_trace_on_coset_zero_shift(ctx):
     out = ctx.lde(tr, log_n, C, 3, offset=1).reshape(8, C, 1 << log_n, 4)
     assert np.array_equal(out[0].reshape(-1, 4), tr)
     assert np.array_equal(out.reshape(-1, 4), clib.lde(tr, log_n, C, 3, offset=1))
+
+
+def root_dummy():
+    import ctypes as C
+    return np.empty(8, np.uint8).ctypes.data_as(C.c_void_p)
+
+
+def test_argument_errors_are_reported_not_crashed(ctx):
+    """Bad arguments come back as SPG_E_ARG with a message (the Python layer raises SpgError); the context stays usable."""
+    import ctypes as C
+    import stark_perpetual_b200 as spg
+    lib, h = ctx._lib, ctx._h
+    x = rand_felts(8, 1)
+    assert lib.spg_ntt(h, x.ctypes.data_as(C.c_void_p), 27, 1, 0, 0, 0) == -2     # above the 2^26 twiddle table
+    with pytest.raises(spg.SpgError, match="chain_len"):
+        ctx.pedersen_chain(x, 0) if False else ctx._check(lib.spg_pedersen_chain_batch(h, x.ctypes.data_as(C.c_void_p), 0,
+                                                          x.ctypes.data_as(C.c_void_p), root_dummy(), 1, 0))
+    assert lib.spg_ntt(h, None, 3, 1, 0, 0, 0) == -2         # null data
+    assert lib.spg_ntt(h, x.ctypes.data_as(C.c_void_p), 3, 1, 0, 7, 0) == -2      # bad order
+    root = np.empty(32, np.uint8)
+    assert lib.spg_merkle_commit(h, x.ctypes.data_as(C.c_void_p), 1, 6, root.ctypes.data_as(C.c_void_p), None, 0) == -2   # rows not 2^k
+    ln = C.c_size_t(0)
+    assert lib.spg_prove(h, x.ctypes.data_as(C.c_void_p), 8, 0, x.ctypes.data_as(C.c_void_p), 30, None, 0, C.byref(ln), 0) == -2   # log_n < 9
+    st = np.zeros(1, np.uint8)
+    assert lib.spg_pedersen_merkle_tree(h, x.ctypes.data_as(C.c_void_p), 6, root.ctypes.data_as(C.c_void_p), None,
+                                        st.ctypes.data_as(C.c_void_p), 0) == -2                                         # 6 leaves
+    assert b"bad argument" in lib.spg_last_error(h)
+    # still healthy
+    assert np.array_equal(ctx.ntt(ctx.ntt(x, 3, False, NTT_NAT_TO_REV), 3, True, NTT_REV_TO_NAT), x)
