@@ -18,7 +18,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 tail -2 gpurun_out/${TAG}_ncu_bench.log | cut -c1-300
 echo "=== ncu pipes (all kernels of one step)"
 bash tools/ncu_pipes.sh ${TAG} > /dev/null 2>&1
-python tools/ncu_summarize.py gpurun_out/${TAG}_pipes.csv > gpurun_out/${TAG}_pipes_summary.txt 2>&1; head -4 gpurun_out/${TAG}_pipes_summary.txt
+head -4 gpurun_out/${TAG}_pipes_summary.txt
 echo "=== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 60 -c 2 -f -o gpurun_out/${TAG}_prof \
   python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1

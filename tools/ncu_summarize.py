@@ -6,13 +6,16 @@ import csv
 import sys
 
 
-def main(path):
+def main(path, last=None):
     rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
     hdr = rows[0]
     ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
     launches = collections.OrderedDict()
     for r in rows[1:]:
         launches.setdefault(r[iid], {"name": r[ik]})[r[im]] = float(r[iv].replace(",", "") or 0)
+    if last:        # keep only the last `last` launches (one proof)
+        keep = list(launches.keys())[-last:]
+        launches = collections.OrderedDict((k, launches[k]) for k in keep)
     agg = collections.OrderedDict()
     for l in launches.values():
         name = l["name"].split("(")[0]
@@ -52,4 +55,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], int(sys.argv[sys.argv.index("--last") + 1]) if "--last" in sys.argv else None)
