@@ -107,6 +107,14 @@ int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r,
  * priv[i] * G (pub_y_or_null may be NULL); status 1 if priv is outside (0, n). */
 int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv, uint64_t* pub_x, uint64_t* pub_y_or_null,
                                    uint8_t* status, size_t n, int flags);
+/* signature.py:137-173 sign(msg_hash, priv_key, seed): deterministic signatures, nonce by RFC 6979 (HMAC-SHA256) exactly
+ * as signature.py:117-134 derives it through python-ecdsa 0.17.0, the three rejection rules (:158-170) retried on the
+ * device with the bumped seed.  seed_or_null[i] is the reference's `seed` argument (NULL or 0 = None: both give no
+ * extra entropy on the first attempt and 1 on the second).  (r[i], s[i]) canonical.
+ * status[i]: 0 ok; 1 "Message not signable" (msg >= 2^251, the reference's AssertionError :141); 2 private key outside
+ * [1, n) (outside the reference's domain, is_valid_stark_private_key); 3 no signature after 128 attempts (never). */
+int spg_sign_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* priv, const uint64_t* seed_or_null, uint64_t* r,
+                   uint64_t* s, uint8_t* status, size_t n, int flags);
 
 /* signature.py:84-96 get_y_coordinate: y[i] = the smaller square root of x^3 + x + beta (math_utils.py:43-47).
  * status[i]: 0 ok; 1 InvalidPublicKeyError (no point with this x; is_valid_stark_key, signature.py:204-214, is

@@ -57,6 +57,7 @@ def _load():
             "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_ecdsa_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_private_to_stark_key_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_sign_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_pedersen_hash_point_batch": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_get_y_coordinate_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_mimic_ec_mult_air_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
@@ -67,6 +68,16 @@ def _load():
             "spg_stage_ms": (C.c_double, [vp, C.c_int]),
             "spg_lde": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, vp, vp, C.c_int]),
             "spg_lde_coeffs": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, vp, vp, C.c_int]),
+            # stage-level entry points driven by prover.py (multi-GPU)
+            "spg_stage_merkle": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp]),
+            "spg_stage_air": (C.c_int, [vp, C.c_uint, C.c_uint, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]),
+            "spg_stage_cp_split": (C.c_int, [vp, C.c_uint, vp, C.c_int, C.c_int, vp]),
+            "spg_stage_poly_eval": (C.c_int, [vp, C.c_uint, vp, vp, C.c_int, vp, C.c_int, vp]),
+            "spg_stage_deep": (C.c_int, [vp, C.c_uint, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+            "spg_stage_fri_fold": (C.c_int, [vp, vp, C.c_uint, C.c_int, C.c_int, vp, C.c_int, vp]),
+            "spg_stage_open": (C.c_int, [vp, vp, C.c_size_t, C.c_size_t, C.c_int, vp, vp, C.c_int, vp, vp]),
+            "spg_stage_check_oods": (C.c_int, [vp, C.c_uint, C.c_uint, vp, vp, vp, vp, vp]),
+            "spg_stage_last_layer": (C.c_int, [vp, vp, C.c_uint, C.c_int, vp]),
             "spg_lde_cosets": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, C.c_size_t, C.c_size_t, vp, C.c_int]),
         }
         for name, (res, args) in sig.items():
@@ -251,6 +262,18 @@ class Context:
         self._check(self._lib.spg_private_to_stark_key_batch(self._h, _ptr(p), _ptr(out), _ptr(outy) if want_y else None,
                                                              _ptr(st), p.shape[0], 0))
         return (out, outy, st) if want_y else (out, st)
+
+    def sign(self, msg, priv, seeds=None):
+        """msg, priv: (n, 4) canonical; seeds: (n,) uint64 or None -> (r (n, 4), s (n, 4), status)."""
+        m = np.ascontiguousarray(msg, dtype=np.uint64).reshape(-1, 4)
+        d = np.ascontiguousarray(priv, dtype=np.uint64).reshape(-1, 4)
+        assert m.shape == d.shape
+        sd = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64).reshape(-1)
+        assert sd is None or sd.shape[0] == m.shape[0]
+        r, s, st = np.empty_like(m), np.empty_like(m), np.empty(m.shape[0], dtype=np.uint8)
+        self._check(self._lib.spg_sign_batch(self._h, _ptr(m), _ptr(d), _ptr(sd) if sd is not None else None, _ptr(r), _ptr(s),
+                                             _ptr(st), m.shape[0], 0))
+        return r, s, st
 
     # ---- perpetual limit orders ----
     _ORDER_LAYOUT = (("asset_id_synthetic", np.uint64, 4), ("asset_id_collateral", np.uint64, 4), ("asset_id_fee", np.uint64, 4),

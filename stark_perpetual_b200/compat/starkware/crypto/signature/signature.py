@@ -13,6 +13,8 @@ import math
 import os
 from typing import Optional, Tuple, Union
 
+import numpy as np
+
 import stark_perpetual_b200 as _spg
 from stark_perpetual_b200._lib import ints_to_limbs, limbs_to_ints
 
@@ -216,9 +218,16 @@ def generate_k_rfc6979(msg_hash: int, priv_key: int, seed: Optional[int] = None)
                                msg_hash.to_bytes(math.ceil(msg_hash.bit_length() / 8), "big"), extra_entropy=extra)
 
 
+_SEED_LIMIT = 2**64 - 256      # room for the retry counter in the kernel's 64-bit seed
+
+
 def sign(msg_hash: int, priv_key: int, seed: Optional[int] = None) -> ECSignature:
-    # signature.py:137-173; x(k*G) on the GPU
+    # signature.py:137-173
     assert 0 <= msg_hash < 2**N_ELEMENT_BITS_ECDSA, "Message not signable."
+    if 1 <= priv_key < EC_ORDER and (seed is None or 0 <= seed < _SEED_LIMIT):
+        return sign_batch([msg_hash], [priv_key], [seed])[0]
+    # keys outside [1, n) and seeds beyond 64 bits are outside the batch kernel's domain: the reference's loop with
+    # the nonce derived on the host and x(k*G) on the GPU
     while True:
         k = generate_k_rfc6979(msg_hash, priv_key, seed)
         seed = 1 if seed is None else seed + 1
@@ -234,33 +243,25 @@ def sign(msg_hash: int, priv_key: int, seed: Optional[int] = None) -> ECSignatur
 
 
 def sign_batch(msg_hashes, priv_keys, seeds=None):
-    """[sign(m, k, seed) for ...]: the nonces are derived on the host (RFC 6979, signature.py:117-134), the curve
-    multiplications k*G of the whole batch run in one launch, and only the signatures that hit one of the reference's
-    three rejection rules (signature.py:158-170) go round again with the bumped seed."""
+    """[sign(m, k, seed) for ...] in one launch (spg_sign_batch): each GPU thread derives its RFC 6979 nonce
+    (HMAC-SHA256, signature.py:117-134), multiplies the generator, finishes the signature modulo n and retries with
+    the bumped seed on the reference's three rejection rules (signature.py:158-170).  Keys must lie in [1, n)."""
     n = len(msg_hashes)
-    seeds = list(seeds) if seeds is not None else [None] * n
     for m in msg_hashes:
         assert 0 <= m < 2**N_ELEMENT_BITS_ECDSA, "Message not signable."
-    out = [None] * n
-    todo = list(range(n))
-    while todo:
-        ks = [generate_k_rfc6979(msg_hashes[i], priv_keys[i], seeds[i]) for i in todo]
-        for i in todo:
-            seeds[i] = 1 if seeds[i] is None else seeds[i] + 1
-        rs = private_to_stark_key_batch(ks)
-        again = []
-        for i, k, r in zip(todo, ks, rs):
-            z = msg_hashes[i] + r * priv_keys[i]
-            if not (1 <= r < 2**N_ELEMENT_BITS_ECDSA) or z % EC_ORDER == 0:
-                again.append(i)
-                continue
-            w = k * pow(z, -1, EC_ORDER) % EC_ORDER
-            if not (1 <= w < 2**N_ELEMENT_BITS_ECDSA):
-                again.append(i)
-                continue
-            out[i] = (r, inv_mod_curve_size(w))
-        todo = again
-    return out
+    for k in priv_keys:
+        assert 1 <= k < EC_ORDER, "private key outside [1, EC_ORDER)"
+    sd = None
+    if seeds is not None:
+        sd = [0 if x is None else x for x in seeds]      # None and 0 are the same signature (no extra entropy)
+        for x in sd:
+            assert 0 <= x < _SEED_LIMIT
+        sd = np.array(sd, dtype=np.uint64)
+    if n == 0:
+        return []
+    r, s, st = _ctx().sign(ints_to_limbs(msg_hashes), ints_to_limbs(priv_keys), sd)
+    assert not st.any(), "spg_sign_batch status %s" % sorted(set(st.tolist()))
+    return list(zip(limbs_to_ints(r), limbs_to_ints(s)))
 
 
 def pedersen_merkle_root(leaves):

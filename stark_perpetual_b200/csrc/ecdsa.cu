@@ -1,9 +1,10 @@
 // Batched STARK-curve ECDSA verification and key derivation (BASELINE.json
 // configs[4]).  Reference: src/starkware/crypto/signature/signature.py:217-260 (verify), :104-110
-// (private_to_stark_key).  One thread per signature; per-signature code in ecdsa.cuh.
+// (private_to_stark_key), :117-173 (sign).  One thread per signature; per-signature code in ecdsa.cuh / sign.cuh.
 #include "common.h"
 #include "curve_params.inc"
 #include "ecdsa.cuh"
+#include "sign.cuh"
 
 static int ensure_ecdsa_tables(spg_ctx* ctx) {
   if (ctx->sqrt_tables) return SPG_OK;
@@ -285,4 +286,58 @@ extern "C" int spg_mimic_ec_mult_air_batch(spg_ctx* ctx, const uint64_t* m, cons
   return run_simple(ctx, ins, words, 3, out_xy, 8, status, n, flags, [&](const uint64_t* const* d, uint64_t* o, uint8_t* st) {
     k_mimic_mult<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(d[0], d[1], d[2], o, st, n);
   });
+}
+
+// ------------------------------------------------------------------ sign (signature.py:137-173)
+// One thread derives the RFC 6979 nonce (HMAC-SHA256), multiplies the generator, and finishes the signature modulo
+// n; the reference's retry loop (bumped seed) runs inside the thread.
+__global__ void __launch_bounds__(64) k_ecdsa_sign(const uint64_t* __restrict__ msg, const uint64_t* __restrict__ priv,
+                                                   const uint64_t* __restrict__ seed, uint64_t* __restrict__ r,
+                                                   uint64_t* __restrict__ s, uint8_t* __restrict__ status, size_t n,
+                                                   EcdsaTables T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t m[8], d[8], ro[8], so[8];
+  load8(msg + 4 * i, m); load8(priv + 4 * i, d);
+  for (int k = 0; k < 8; k++) ro[k] = so[k] = 0;
+  status[i] = (uint8_t)ecdsa_sign_one(m, d, seed ? seed[i] : 0ull, T, ro, so);
+  uint4* o = reinterpret_cast<uint4*>(r + 4 * i);
+  o[0] = make_uint4(ro[0], ro[1], ro[2], ro[3]); o[1] = make_uint4(ro[4], ro[5], ro[6], ro[7]);
+  o = reinterpret_cast<uint4*>(s + 4 * i);
+  o[0] = make_uint4(so[0], so[1], so[2], so[3]); o[1] = make_uint4(so[4], so[5], so[6], so[7]);
+}
+
+extern "C" int spg_sign_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* priv, const uint64_t* seed_or_null,
+                              uint64_t* r, uint64_t* s, uint8_t* status, size_t n, int flags) {
+  SPG_ARG(ctx && msg && priv && r && s && status, "spg_sign_batch: null");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  int rc = ensure_ecdsa_tables(ctx);
+  if (rc) return rc;
+  const uint64_t *dm = msg, *dp = priv, *dseed = seed_or_null;
+  uint64_t *dr = r, *ds = s; uint8_t* dst = status;
+  DevBuf bm, bp, bseed, bo, bs;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(bm.alloc(ctx, n * 32)); SPG_CUDA(bp.alloc(ctx, n * 32)); SPG_CUDA(bo.alloc(ctx, 2 * n * 32)); SPG_CUDA(bs.alloc(ctx, n));
+    SPG_CUDA(cudaMemcpyAsync(bm.p, msg, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(bp.p, priv, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (seed_or_null) {
+      SPG_CUDA(bseed.alloc(ctx, n * 8));
+      SPG_CUDA(cudaMemcpyAsync(bseed.p, seed_or_null, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      dseed = bseed.as<uint64_t>();
+    }
+    dm = bm.as<uint64_t>(); dp = bp.as<uint64_t>(); dr = bo.as<uint64_t>(); ds = dr + 4 * n; dst = bs.as<uint8_t>();
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_ecdsa_sign<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(dm, dp, dseed, dr, ds, dst, n, make_tables(ctx, true));
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(cudaMemcpyAsync(r, dr, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(s, ds, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
 }

@@ -166,22 +166,6 @@ class GpuBackend:
         # stage kernels and torch's collectives must be ordered on one stream
         with torch.cuda.device(self.dev):
             ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        for name, args in {
-            "spg_stage_merkle": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p],
-            "spg_stage_air": [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                              C.c_void_p, C.c_void_p],
-            "spg_stage_cp_split": [C.c_void_p, C.c_uint, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
-            "spg_stage_poly_eval": [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
-            "spg_stage_deep": [C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_void_p, C.c_void_p],
-            "spg_stage_fri_fold": [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p],
-            "spg_stage_open": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                               C.c_void_p, C.c_void_p],
-            "spg_stage_check_oods": [C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
-            "spg_stage_last_layer": [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_void_p],
-        }.items():
-            fn = getattr(self.lib, name)
-            fn.restype, fn.argtypes = C.c_int, args
 
     def _chk(self, rc):
         self.ctx._check(rc)

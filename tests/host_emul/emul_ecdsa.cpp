@@ -1,12 +1,13 @@
 // CPU emulation of the ECDSA verification kernel's per-thread code (csrc/ecdsa.cuh), compiled with g++.
 // stdin: lines "msg r s pub_x pub_y|-" (hex canonical, no 0x);  "K priv" lines compute the public key x.
-// stdout: status (0 False / 1 True / 2 raises) or the key.
+//        "S msg priv seed" lines (seed decimal) sign: the kernel's sign.cuh code (RFC 6979 nonce, k G, mod-n finish).
+// stdout: status (0 False / 1 True / 2 raises), the key, or "status r s".
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
 
-#include "../../stark_perpetual_b200/csrc/ecdsa.cuh"
+#include "../../stark_perpetual_b200/csrc/sign.cuh"
 #include "../../stark_perpetual_b200/csrc/curve_params.inc"
 
 static Fp from_canon(const uint64_t* w) { return fp_to_mont(fp_from_u64(w)); }
@@ -58,6 +59,18 @@ int main() {
       uint64_t out[4]; fp_to_u64(fp_from_mont(gen_mult(k, T).x), out);
       printf("%016llx%016llx%016llx%016llx\n", (unsigned long long)out[3], (unsigned long long)out[2],
              (unsigned long long)out[1], (unsigned long long)out[0]);
+      continue;
+    }
+    if (a[0][0] == 'S') {
+      for (int k = 1; k < 4; k++) if (scanf("%100s", a[k]) != 1) return 1;
+      uint32_t m[8], d[8], r[8] = {0}, s[8] = {0};
+      parse_hex(a[1], m); parse_hex(a[2], d);
+      const int st = ecdsa_sign_one(m, d, strtoull(a[3], nullptr, 10), T, r, s);
+      printf("%d ", st);
+      for (int k = 7; k >= 0; k--) printf("%08x", r[k]);
+      printf(" ");
+      for (int k = 7; k >= 0; k--) printf("%08x", s[k]);
+      printf("\n");
       continue;
     }
     for (int k = 1; k < 5; k++) if (scanf("%100s", a[k]) != 1) return 1;

@@ -26,6 +26,30 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "missing export: " + name
 
 
+def declared_prototypes():
+    """name -> number of parameters, from include/spg.h"""
+    text = open(os.path.join(ROOT, "include", "spg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(spg_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_python_binding_declares_every_prototype():
+    """Every entry point has ctypes argtypes of the header's arity in the Python binding: an undeclared size_t passed
+    as a Python int is truncated to 32 bits and the upper half of the stack slot is garbage."""
+    from stark_perpetual_b200 import _lib
+    lib = _lib._load()
+    protos = declared_prototypes()
+    assert set(protos) == set(declared_symbols())
+    for name, n_params in protos.items():
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, "no argtypes for " + name
+        assert len(fn.argtypes) == n_params, (name, len(fn.argtypes), n_params)
+
+
 def test_no_cpu_fallback():
     """Without a GPU the product path must refuse to run rather than fall back."""
     import torch

@@ -127,8 +127,8 @@ def test_compat_signature_module(ctx, golden):
 
 
 def test_sign_batch_matches_reference_vectors_and_scalar_sign(ctx, golden):
-    """sign_batch (host RFC 6979 nonces, one GPU launch for all k*G) against the 4 JS KATs (signature.spec.js:96-137),
-    the reference-generated sign vectors and the oracle's sign."""
+    """sign_batch (spg_sign_batch: nonce, k*G and the mod-n finish all in the kernel) against the 4 JS KATs
+    (signature.spec.js:96-137), the reference-generated sign vectors and the oracle's sign."""
     sig = compat()
     kat = golden["sign_js_kat"]
     vec = golden["sign"]
@@ -144,6 +144,16 @@ def test_sign_batch_matches_reference_vectors_and_scalar_sign(ctx, golden):
     pubs = sig.private_to_stark_key_batch(k2)
     assert sig.verify_batch(m2, [g[0] for g in got], [g[1] for g in got], pubs) == [True] * 64
     assert sig.sign_batch(m2[:3], k2[:3], seeds=[5, None, 7])[0] == oecdsa.sign(m2[0], k2[0], 5)
+    # scalar sign: in-domain arguments go through the kernel, a 70-bit seed through the host loop; both the reference's
+    for seed in (None, 0, 1, 2**40 + 3, 2**70 + 1):
+        assert sig.sign(m2[1], k2[1], seed) == oecdsa.sign(m2[1], k2[1], seed)
+    # messages around the nibble rule (signature.py:119-121) and the C-ABI status codes
+    edge = [0, 1, 2**248 - 1, 2**248, 2**249 + 3, 2**251 - 1]
+    assert sig.sign_batch(edge, k2[:6]) == [oecdsa.sign(m, k) for m, k in zip(edge, k2[:6])]
+    _r, _s, st = ctx.sign(ints_to_limbs([2**251, 5, 5, 5]), ints_to_limbs([5, 0, EC_ORDER, 7]))
+    assert st.tolist() == [1, 2, 2, 0]
+    with pytest.raises(AssertionError):
+        sig.sign(2**251, 5)
 
 
 def test_pedersen_merkle_tree(ctx):

@@ -80,3 +80,29 @@ def test_emulated_ecdsa_vs_reference_golden(golden):
         assert int(o) == v[4], v[5]
     for (_priv, pub), o in zip(golden["keys"], out[nv:]):
         assert int(o, 16) == int(pub, 16)
+
+
+def test_emulated_sign_vs_golden_and_oracle(golden):
+    """The per-thread signing code of the CUDA kernel (csrc/sign.cuh: SHA-256 / HMAC / RFC 6979 nonce, k*G, the
+    mod-n finish and the retry rules) run on the host: the reference's four JS deterministic-signature KATs
+    (signature.spec.js:96-137), the 14 signatures the reference's sign produced (tests/golden), and seeded
+    signatures against the oracle."""
+    import random
+    from oracle import ecdsa as oec
+    exe = _build("emul_ecdsa")
+    cases = [(int(m, 16), int(d, 16), 0, int(r, 16), int(s, 16)) for m, d, r, s in golden["sign"] + golden["sign_js_kat"]]
+    rng = random.Random(77)
+    for seed in (0, 1, 255, 256, 2**32 + 5, 2**64 - 2):
+        m, d = rng.randrange(2**251), rng.randrange(1, oec.EC_ORDER)
+        cases.append((m, d, seed) + oec.sign(m, d, seed if seed else None))
+    for m in (0, 1, 2**248 - 1, 2**248, 2**249 + 3, 2**251 - 1):      # bit lengths around the nibble rule (:119-121)
+        d = rng.randrange(1, oec.EC_ORDER)
+        cases.append((m, d, 0) + oec.sign(m, d))
+    lines = ["S %x %x %d" % (m, d, seed) for m, d, seed, _r, _s in cases]
+    lines += ["S %x %x 0" % (2**251, 5), "S %x %x 0" % (5, 0), "S %x %x 0" % (5, oec.EC_ORDER)]
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout.strip().split("\n")
+    assert len(out) == len(lines)
+    for (m, d, seed, r, s), o in zip(cases, out):
+        st, rr, ss = o.split()
+        assert st == "0" and int(rr, 16) == r and int(ss, 16) == s, (hex(m), seed)
+    assert [o.split()[0] for o in out[len(cases):]] == ["1", "2", "2"]

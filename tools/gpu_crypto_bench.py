@@ -55,6 +55,22 @@ def main():
                                        "verify_per_s_e2e": n / wall, "valid": int((st == 1).sum()),
                                        "invalid": int((st == 0).sum()), "raises": int((st == 2).sum()),
                                        "first_valid_ok": bool((st[:n_valid] == 1).all())}
+    # sign -> verify round trip at the configs[4] size: every signature the kernel makes must verify
+    n = 65536
+    msg, priv = rand_felts(n, 51), rand_felts(n, 52)
+    msg[:, 3] &= np.uint64(0x07ffffffffffffff)
+    priv[:, 3] &= np.uint64(0x03ffffffffffffff)
+    priv[:, 0] |= np.uint64(1)
+    ctx.sign(msg, priv)
+    t0 = time.perf_counter()
+    sr, ss, sst = ctx.sign(msg, priv)
+    wall = time.perf_counter() - t0
+    sign_ms = ctx.last_kernel_ms
+    spx, _ = ctx.private_to_stark_key(priv)
+    vst = ctx.ecdsa_verify(msg, sr, ss, spx)
+    out["sign_n%d" % n] = {"kernel_ms": sign_ms, "wall_ms": wall * 1e3, "sign_per_s_kernel": n / (sign_ms * 1e-3),
+                           "sign_per_s_e2e": n / wall, "bad_status": int((sst != 0).sum()),
+                           "verified": int((vst == 1).sum())}
     # BASELINE.json configs[4]: 65536 limit orders, packing + 4-deep hash chain + ECDSA in one device pipeline
     n = 65536
     g = np.random.Generator(np.random.PCG64(1005))
