@@ -158,7 +158,7 @@ class Context:
     def field_op(self, op, a, b=None):
         """a, b: (n,4) uint64 canonical felts. op: 'mul','add','sub','inv','pow'."""
         code = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "pow": 4, "rawmul": 5, "widelo": 6, "widehi": 7, "reduce": 8, "sublazy2": 9,
-                "partial": 10, "reducefull": 11, "addraw": 12}[op]
+                "partial": 10, "reducefull": 11, "addraw": 12, "rawsqr": 13, "sqrwidelo": 14, "sqrwidehi": 15}[op]
         a = np.ascontiguousarray(a, dtype=np.uint64)
         out = np.empty_like(a)
         bp = None

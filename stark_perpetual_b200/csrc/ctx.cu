@@ -141,7 +141,12 @@ __global__ void k_field_op(int op, const Fp* a, const Fp* b, Fp* out, size_t n) 
     else if (op == 10) r = fp_partial(a[i]);
     else if (op == 11) r = fp_reduce_full(a[i]);
     else if (op == 12) r = fp_add_raw(a[i], b[i]);
-    else {
+    else if (op == 13) r = fp_sqr(a[i]);
+    else if (op == 14 || op == 15) {
+      uint32_t t[16];
+      fpd_sqr_wide(t, a[i]);
+      for (int k = 0; k < 8; k++) r.v[k] = t[(op == 14 ? 0 : 8) + k];
+    } else {
       uint32_t t[16];
       fpd_mul_wide(t, a[i], b[i]);
       for (int k = 0; k < 8; k++) r.v[k] = t[(op == 6 ? 0 : 8) + k];
@@ -165,8 +170,8 @@ __global__ void k_field_op(int op, const Fp* a, const Fp* b, Fp* out, size_t n) 
 
 extern "C" int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
                             size_t n, int flags) {
-  SPG_ARG(ctx && a && out && op >= 0 && op <= 12, "spg_field_op");
-  SPG_ARG(op == 3 || op == 8 || op == 10 || op == 11 || b, "spg_field_op: b required");
+  SPG_ARG(ctx && a && out && op >= 0 && op <= 15, "spg_field_op");
+  SPG_ARG(op == 3 || op == 8 || op == 10 || op == 11 || op >= 13 || b, "spg_field_op: b required");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
   const Fp *da = (const Fp*)a, *db = (const Fp*)b;

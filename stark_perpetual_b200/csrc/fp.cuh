@@ -333,6 +333,120 @@ SPG_D void fpd_mul_wide(uint32_t (&t)[16], const Fp& a, const Fp& b) {
         "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
 }
 
+// ---- dedicated squaring: 28 cross products + 8 diagonal ones = 36 wide multiplies instead of 64.
+// Chains of 3, 2 and 1 products (the 4-product chain is SPG_ROW_MAD); each ends with its carry into the next limb,
+// which at that point holds nothing but earlier carries (chains run in ascending order of their multiplier limb).
+#define SPG_CHAIN3(acc, k, A0, A1, A2, B)                                               \
+  asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"                                              \
+      "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"                                             \
+      "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"                                             \
+      "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"                                             \
+      "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"                                             \
+      "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"                                             \
+      "addc.u32 %6, %6, 0;"                                                             \
+      : "+r"(acc[k]), "+r"(acc[k + 1]), "+r"(acc[k + 2]), "+r"(acc[k + 3]), "+r"(acc[k + 4]), \
+        "+r"(acc[k + 5]), "+r"(acc[k + 6])                                               \
+      : "r"(A0), "r"(A1), "r"(A2), "r"(B))
+#define SPG_CHAIN2(acc, k, A0, A1, B)                                                   \
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"                                               \
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"                                              \
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"                                              \
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"                                              \
+      "addc.u32 %4, %4, 0;"                                                             \
+      : "+r"(acc[k]), "+r"(acc[k + 1]), "+r"(acc[k + 2]), "+r"(acc[k + 3]), "+r"(acc[k + 4]) \
+      : "r"(A0), "r"(A1), "r"(B))
+#define SPG_CHAIN1(acc, k, A0, B)                                                       \
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"                                               \
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"                                              \
+      "addc.u32 %2, %2, 0;"                                                             \
+      : "+r"(acc[k]), "+r"(acc[k + 1]), "+r"(acc[k + 2])                                 \
+      : "r"(A0), "r"(B))
+
+// t[0..15] = a * a + p * 2^256 for a < 2^254: exactly what fpd_mul_wide(t, a, a) produces.
+//   X = sum_{i<j} a_i a_j 2^(32(i+j))  on the even/odd accumulators (E: i+j even, O: i+j odd),
+//   t = 2 X + sum_i (a_i^2 + seed_i) 2^(64 i),  seed = the limbs of p * 2^256 (they fit under the squares: a_7 < 2^30).
+SPG_D void fpd_sqr_wide(uint32_t (&t)[16], const Fp& a) {
+  uint32_t E[16], O[15];
+#pragma unroll
+  for (int i = 0; i < 16; i++) E[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 15; i++) O[i] = 0;
+  // E[k] has weight 2^(32k); O[k] has weight 2^(32(k+1)).
+  SPG_ROW_MAD(O, 0, a.v[1], a.v[3], a.v[5], a.v[7], a.v[0]);
+  SPG_CHAIN3(E, 2, a.v[2], a.v[4], a.v[6], a.v[0]);
+  SPG_CHAIN3(O, 2, a.v[2], a.v[4], a.v[6], a.v[1]);
+  SPG_CHAIN3(E, 4, a.v[3], a.v[5], a.v[7], a.v[1]);
+  SPG_CHAIN3(O, 4, a.v[3], a.v[5], a.v[7], a.v[2]);
+  SPG_CHAIN2(E, 6, a.v[4], a.v[6], a.v[2]);
+  SPG_CHAIN2(O, 6, a.v[4], a.v[6], a.v[3]);
+  SPG_CHAIN2(E, 8, a.v[5], a.v[7], a.v[3]);
+  SPG_CHAIN2(O, 8, a.v[5], a.v[7], a.v[4]);
+  SPG_CHAIN1(E, 10, a.v[6], a.v[4]);
+  SPG_CHAIN1(O, 10, a.v[6], a.v[5]);
+  SPG_CHAIN1(E, 12, a.v[7], a.v[5]);
+  SPG_CHAIN1(O, 12, a.v[7], a.v[6]);
+  // X[1] = O[0];  X[k] = E[k] + O[k-1], k = 2..15
+  uint32_t X[16];
+  X[1] = O[0];
+  asm("add.cc.u32 %0, %14, %28;\n\t"
+      "addc.cc.u32 %1, %15, %29;\n\t"
+      "addc.cc.u32 %2, %16, %30;\n\t"
+      "addc.cc.u32 %3, %17, %31;\n\t"
+      "addc.cc.u32 %4, %18, %32;\n\t"
+      "addc.cc.u32 %5, %19, %33;\n\t"
+      "addc.cc.u32 %6, %20, %34;\n\t"
+      "addc.cc.u32 %7, %21, %35;\n\t"
+      "addc.cc.u32 %8, %22, %36;\n\t"
+      "addc.cc.u32 %9, %23, %37;\n\t"
+      "addc.cc.u32 %10, %24, %38;\n\t"
+      "addc.cc.u32 %11, %25, %39;\n\t"
+      "addc.cc.u32 %12, %26, %40;\n\t"
+      "addc.u32 %13, %27, %41;"
+      : "=&r"(X[2]), "=&r"(X[3]), "=&r"(X[4]), "=&r"(X[5]), "=&r"(X[6]), "=&r"(X[7]), "=&r"(X[8]), "=&r"(X[9]),
+        "=&r"(X[10]), "=&r"(X[11]), "=&r"(X[12]), "=&r"(X[13]), "=&r"(X[14]), "=&r"(X[15])
+      : "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]), "r"(E[10]),
+        "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+        "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]),
+        "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+  // 2 X
+  uint32_t Y[16];
+  Y[1] = X[1] << 1;
+#pragma unroll
+  for (int k = 2; k < 16; k++) Y[k] = __funnelshift_l(X[k - 1], X[k], 1);
+  // diagonal squares with the seed limbs of p * 2^256 (limb 8: p0 = 1; limbs 14, 15: p6, p7) as addends
+  uint32_t D[16];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint64_t seed = (i == 4) ? (uint64_t)SPG_P0 : (i == 7) ? (((uint64_t)SPG_P7 << 32) | SPG_P6) : 0ull;
+    uint64_t w;
+    asm("mad.wide.u32 %0, %1, %1, %2;" : "=l"(w) : "r"(a.v[i]), "l"(seed));
+    D[2 * i] = (uint32_t)w; D[2 * i + 1] = (uint32_t)(w >> 32);
+  }
+  t[0] = D[0];
+  asm("add.cc.u32 %0, %15, %30;\n\t"
+      "addc.cc.u32 %1, %16, %31;\n\t"
+      "addc.cc.u32 %2, %17, %32;\n\t"
+      "addc.cc.u32 %3, %18, %33;\n\t"
+      "addc.cc.u32 %4, %19, %34;\n\t"
+      "addc.cc.u32 %5, %20, %35;\n\t"
+      "addc.cc.u32 %6, %21, %36;\n\t"
+      "addc.cc.u32 %7, %22, %37;\n\t"
+      "addc.cc.u32 %8, %23, %38;\n\t"
+      "addc.cc.u32 %9, %24, %39;\n\t"
+      "addc.cc.u32 %10, %25, %40;\n\t"
+      "addc.cc.u32 %11, %26, %41;\n\t"
+      "addc.cc.u32 %12, %27, %42;\n\t"
+      "addc.cc.u32 %13, %28, %43;\n\t"
+      "addc.u32 %14, %29, %44;"
+      : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]),
+        "=&r"(t[8]), "=&r"(t[9]), "=&r"(t[10]), "=&r"(t[11]), "=&r"(t[12]), "=&r"(t[13]), "=&r"(t[14]),
+        "=&r"(t[15])
+      : "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]), "r"(Y[8]),
+        "r"(Y[9]), "r"(Y[10]), "r"(Y[11]), "r"(Y[12]), "r"(Y[13]), "r"(Y[14]), "r"(Y[15]),
+        "r"(D[1]), "r"(D[2]), "r"(D[3]), "r"(D[4]), "r"(D[5]), "r"(D[6]), "r"(D[7]), "r"(D[8]),
+        "r"(D[9]), "r"(D[10]), "r"(D[11]), "r"(D[12]), "r"(D[13]), "r"(D[14]), "r"(D[15]));
+}
+
 SPG_D uint32_t spg_lo32(uint64_t x) { return (uint32_t)x; }
 SPG_D uint32_t spg_hi32(uint64_t x) { return (uint32_t)(x >> 32); }
 SPG_D uint64_t spg_mulw(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
@@ -583,7 +697,15 @@ SPG_D Fp fpd_mul(const Fp& a, const Fp& b) {
   fpd_mul_wide(t, a, b);
   return fpd_redc(t);
 }
-SPG_D Fp fpd_sqr(const Fp& a) { return fpd_mul(a, a); }
+SPG_D Fp fpd_sqr(const Fp& a) {
+#if defined(SPG_SQR_AS_MUL)
+  return fpd_mul(a, a);
+#else
+  uint32_t t[16];
+  fpd_sqr_wide(t, a);
+  return fpd_redc(t);
+#endif
+}
 
 #endif  // __CUDACC__
 
@@ -760,7 +882,7 @@ inline Fp fph_mul_lazy(const Fp& a, const Fp& b) { return fph_mul(a, b); }
 #define SPG_DISPATCH(dev, hst) return hst
 #endif
 SPG_HD Fp fp_mul(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_mul(a, b), fph_mul(a, b)); }
-SPG_HD Fp fp_sqr(const Fp& a) { SPG_DISPATCH(fpd_mul(a, a), fph_mul(a, a)); }
+SPG_HD Fp fp_sqr(const Fp& a) { SPG_DISPATCH(fpd_sqr(a), fph_mul(a, a)); }
 SPG_HD Fp fp_add(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_add(a, b), fph_add(a, b)); }
 SPG_HD Fp fp_sub(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_sub(a, b), fph_sub(a, b)); }
 SPG_HD Fp fp_reduce(const Fp& a) { SPG_DISPATCH(fpd_reduce(a), fph_reduce(a)); }

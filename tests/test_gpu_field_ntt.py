@@ -121,3 +121,23 @@ def test_lazy_field_ops_raw(ctx):
     lo = [a >> 3 for a in big]
     assert limbs_to_ints(ctx.field_op("addraw", ints_to_limbs(lo), B)) == [a + b for a, b in zip(lo, small)]
     assert limbs_to_ints(ctx.field_op("sublazy2", ints_to_limbs(lo), B)) == [a + 2 * P - b for a, b in zip(lo, small)]
+
+
+def test_dedicated_squaring_equals_product(ctx):
+    """fpd_sqr_wide (36 wide multiplies: doubled cross products + diagonal) against the general product on the same
+    operand: the 512-bit intermediate a*a + p*2^256 and the reduced representative must be identical bit for bit, for
+    every a below 2^254 (the a*b < 2^508 contract), including all-ones limbs and single-limb values."""
+    rng = random.Random(123)
+    n = 8192
+    vals = [rng.randrange(2**254) for _ in range(n)]
+    vals[:12] = [0, 1, 2**254 - 1, P - 1, P, 2 * P - 1, 2**32 - 1, 2**64 - 1, (2**254 - 1) ^ (2**128 - 1), 2**253, 2**224 - 1,
+                 int("55" * 31, 16)]
+    for i in range(12, 76):                      # limbs drawn from {0, 1, 2^31, 2^32 - 1}: carries and the doubling bit
+        limbs = [rng.choice([0, 1, 2**31, 2**32 - 1, 2**32 - 2]) for _ in range(8)]
+        limbs[7] &= 2**30 - 1
+        vals[i] = sum(l << (32 * k) for k, l in enumerate(limbs))
+    A = ints_to_limbs(vals)
+    lo, hi = limbs_to_ints(ctx.field_op("sqrwidelo", A)), limbs_to_ints(ctx.field_op("sqrwidehi", A))
+    for a, l, h in zip(vals, lo, hi):
+        assert l + (h << 256) == a * a + (P << 256), hex(a)
+    assert (ctx.field_op("rawsqr", A) == ctx.field_op("rawmul", A, A)).all()

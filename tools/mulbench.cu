@@ -15,6 +15,22 @@ SPG_D Fp mul_variant(const Fp& a, const Fp& b) {
   if (V == 0) return fpd_redc_imad(t);
   if (V == 1) return fpd_redc_shift(t);
   if (V == 2) return fpd_redc_hybrid(t);
+  if (V == 4) return fpd_sqr(a);                 // dedicated squaring (36 wide multiplies), shift reduction
+  if (V == 7 || V == 8) {                        // dedicated squaring with the IMAD / hybrid reduction
+    uint32_t t3[16];
+    fpd_sqr_wide(t3, a);
+    return V == 7 ? fpd_redc_imad(t3) : fpd_redc_hybrid(t3);
+  }
+  if (V == 5) return fpd_mul(a, a);              // squaring through the general product
+  if (V == 6) {   // squaring product only
+    uint32_t t2[16];
+    fpd_sqr_wide(t2, a);
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t2[i] ^ t2[8 + i];
+    r.v[7] &= 0x03ffffffu;
+    return r;
+  }
   if (V == 3) {   // product only: fold the halves so nothing is dead
     Fp r;
 #pragma unroll
@@ -46,7 +62,7 @@ static void run(const char* name, Fp* d_io, const std::vector<Fp>& h_in, int blo
     cudaMemcpy(out.data(), d_io, 2 * n * sizeof(Fp), cudaMemcpyDeviceToHost);
     for (size_t i = 0; i < n; i += 97) {
       Fp x = h_in[2 * i], y = h_in[2 * i + 1];
-      for (int k = 0; k < 8; k++) x = fph_mul(x, y);
+      for (int k = 0; k < 8; k++) x = (V == 4 || V == 5 || V == 7 || V == 8) ? fph_mul(x, x) : fph_mul(x, y);
       if (!fp_eq_raw(fph_reduce(out[2 * i]), x)) bad++;
     }
   }
@@ -83,6 +99,11 @@ int main() {
   run<1>("shift_redc", d, h, blocks, threads, iters, true);
   run<2>("hybrid_redc", d, h, blocks, threads, iters, true);
   run<3>("product_only", d, h, blocks, threads, iters, false);
+  run<4>("sqr_dedicated", d, h, blocks, threads, iters, true);
+  run<5>("sqr_as_mul", d, h, blocks, threads, iters, true);
+  run<6>("sqr_product_only", d, h, blocks, threads, iters, false);
+  run<7>("sqr_imad_redc", d, h, blocks, threads, iters, true);
+  run<8>("sqr_hybrid_redc", d, h, blocks, threads, iters, true);
   printf(" \"sms\": %d}\n", prop.multiProcessorCount);
   return 0;
 }
