@@ -154,6 +154,30 @@ int spg_limit_order_msg_batch(spg_ctx* ctx, const spg_limit_orders* orders, uint
 int spg_limit_order_verify_batch(spg_ctx* ctx, const spg_limit_orders* orders, const uint64_t* r, const uint64_t* s,
                                  const uint64_t* pub_x, uint8_t* status, size_t n, int flags);
 
+/* The other perpetual messages: field packing and the Pedersen chain on the device.
+ *   kind 4  get_transfer_msg              (perpetual_messages.py:97-162)
+ *           felts: asset_id, asset_id_fee, receiver_public_key
+ *           ints:  sender_position_id, receiver_position_id, src_fee_position_id, nonce, amount, max_amount_fee,
+ *                  expiration_timestamp
+ *   kind 5  get_conditional_transfer_msg  (:24-94)   felts: asset_id, asset_id_fee, receiver_public_key, condition;
+ *           ints as kind 4
+ *   kind 7  get_withdrawal_to_address_msg (:165-209) felts: asset_id_collateral, eth_address (as an integer);
+ *           ints:  position_id, nonce, amount, expiration_timestamp
+ *   kind 100 get_price_msg                (:311-326) felts: asset_pair, price;  ints: oracle_name, timestamp
+ * felts[k]: [n][4] u64 canonical values; ints[k]: [n] u64 (narrower reference fields are range-checked).
+ * msg_out[i]: the message hash.  status[i]: 0 ok; 1 a bound the reference asserts (:38-48, :110-119, :174-179, :314-317)
+ * is violated; 2 "Unhashable input." (signature.py:313). */
+#define SPG_MSG_TRANSFER 4
+#define SPG_MSG_CONDITIONAL_TRANSFER 5
+#define SPG_MSG_WITHDRAWAL_TO_ADDRESS 7
+#define SPG_MSG_PRICE 100
+typedef struct spg_message_fields {
+  const uint64_t* felts[4];
+  const uint64_t* ints[7];
+} spg_message_fields;
+int spg_message_hash_batch(spg_ctx* ctx, int kind, const spg_message_fields* fields, uint64_t* msg_out, uint8_t* status,
+                           size_t n, int flags);
+
 /* ---- NTT over the STARK prime (no reference symbol, field from signature.py:41-42) */
 /* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
  * inverse != 0 uses omega^-1 and scales by 2^-log_n. */

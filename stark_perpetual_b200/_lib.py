@@ -63,6 +63,7 @@ def _load():
             "spg_mimic_ec_mult_air_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_pedersen_merkle_tree": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_int]),
             "spg_limit_order_msg_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_message_hash_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_limit_order_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_set_stream": (C.c_int, [vp, vp]),
             "spg_stage_ms": (C.c_double, [vp, C.c_int]),
@@ -274,6 +275,27 @@ class Context:
         self._check(self._lib.spg_sign_batch(self._h, _ptr(m), _ptr(d), _ptr(sd) if sd is not None else None, _ptr(r), _ptr(s),
                                              _ptr(st), m.shape[0], 0))
         return r, s, st
+
+    MSG_KINDS = {"transfer": (4, 3, 7), "conditional_transfer": (5, 4, 7), "withdrawal_to_address": (7, 2, 4),
+                 "price": (100, 2, 2)}
+
+    def message_hash(self, kind, felts, ints):
+        """kind: a key of MSG_KINDS; felts: list of (n, 4) uint64 arrays, ints: list of (n,) uint64 arrays, in the
+        order include/spg.h lists for the kind -> (msg (n, 4), status (n,))."""
+        code, nf, ni = self.MSG_KINDS[kind]
+        assert len(felts) == nf and len(ints) == ni
+        fa = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in felts]
+        ia = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1) for a in ints]
+        n = fa[0].shape[0]
+        assert all(a.shape[0] == n for a in fa + ia)
+        ptrs = (C.c_void_p * 11)()
+        for k, a in enumerate(fa):
+            ptrs[k] = a.ctypes.data
+        for k, a in enumerate(ia):
+            ptrs[4 + k] = a.ctypes.data
+        out, st = np.empty((n, 4), dtype=np.uint64), np.empty(n, dtype=np.uint8)
+        self._check(self._lib.spg_message_hash_batch(self._h, code, C.cast(ptrs, C.c_void_p), _ptr(out), _ptr(st), n, 0))
+        return out, st
 
     # ---- perpetual limit orders ----
     _ORDER_LAYOUT = (("asset_id_synthetic", np.uint64, 4), ("asset_id_collateral", np.uint64, 4), ("asset_id_fee", np.uint64, 4),

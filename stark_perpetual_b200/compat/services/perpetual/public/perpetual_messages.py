@@ -194,3 +194,63 @@ def verify_limit_orders_batch(orders, rs, ss, public_keys):
     st = spg.get_context(0).limit_order_verify(arr, ints_to_limbs(rs), ints_to_limbs(ss), ints_to_limbs(public_keys))
     assert not (st == 2).any(), "precondition violated (order bound, unhashable message, or signature operand out of range)"
     return [bool(v) for v in st]
+
+
+# the other messages through spg_message_hash_batch: (kind, full-width arguments, narrow arguments) in the order of
+# include/spg.h; every bound the reference asserts is checked on the device
+_MESSAGE_ARGS = {
+    "transfer": (("asset_id", "asset_id_fee", "receiver_public_key"),
+                 ("sender_position_id", "receiver_position_id", "src_fee_position_id", "nonce", "amount", "max_amount_fee",
+                  "expiration_timestamp")),
+    "conditional_transfer": (("asset_id", "asset_id_fee", "receiver_public_key", "condition"),
+                             ("sender_position_id", "receiver_position_id", "src_fee_position_id", "nonce", "amount",
+                              "max_amount_fee", "expiration_timestamp")),
+    "withdrawal_to_address": (("asset_id_collateral", "eth_address"), ("position_id", "nonce", "amount", "expiration_timestamp")),
+    "price": (("asset_pair", "price"), ("oracle_name", "timestamp")),
+}
+
+
+def get_msg_batch(kind, messages):
+    """[get_<kind>_msg(**m) for m in messages] in one device pipeline (packing kernel + Pedersen chain); kind is one of
+    'transfer', 'conditional_transfer', 'withdrawal_to_address', 'price'.  Raises AssertionError where the reference
+    would for any element."""
+    import stark_perpetual_b200 as spg
+    from stark_perpetual_b200._lib import ints_to_limbs, limbs_to_ints
+    fnames, inames = _MESSAGE_ARGS[kind]
+    if not messages:
+        return []
+
+    def val(m, name):
+        v = m[name]
+        return int(v, 16) if isinstance(v, str) else int(v)
+    felts, ints = [], []
+    for name in fnames:
+        col = [val(m, name) for m in messages]
+        for v in col:
+            assert 0 <= v < 2**256
+        felts.append(ints_to_limbs(col))
+    for name in inames:
+        col = [val(m, name) for m in messages]
+        for v in col:
+            assert 0 <= v < 2**64
+        ints.append(np.array(col, dtype=np.uint64))
+    out, st = spg.get_context(0).message_hash(kind, felts, ints)
+    assert not (st == 1).any()                                   # the bounds of reference :38-48, :110-119, :174-179, :314-317
+    assert not (st == 2).any(), "Unhashable input."              # signature.py:313
+    return limbs_to_ints(out)
+
+
+def get_transfer_msg_batch(messages):
+    return get_msg_batch("transfer", messages)
+
+
+def get_conditional_transfer_msg_batch(messages):
+    return get_msg_batch("conditional_transfer", messages)
+
+
+def get_withdrawal_to_address_msg_batch(messages):
+    return get_msg_batch("withdrawal_to_address", messages)
+
+
+def get_price_msg_batch(messages):
+    return get_msg_batch("price", messages)

@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include "common.h"
+#include "messages.cuh"
 #include "../../include/spg.h"
 
 int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len, uint64_t* out, uint8_t* status, size_t n,
@@ -20,12 +21,7 @@ int spg_ecdsa_verify_device(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r
 
 #define SPG_LIMIT_ORDER_WITH_FEES 3ull   // perpetual_messages.py:8
 
-// OR a 64-bit value into a 256-bit little-endian word at bit offset `off` (off + 64 <= 256)
-__device__ __forceinline__ void put_bits(uint64_t (&w)[4], uint64_t v, int off) {
-  const int k = off >> 6, sh = off & 63;
-  w[k] |= v << sh;
-  if (sh && k + 1 < 4) w[k + 1] |= v >> (64 - sh);
-}
+#define put_bits spg_put_bits
 
 __global__ void __launch_bounds__(128) k_pack_limit_orders(spg_limit_orders o, uint64_t* __restrict__ elems,
                                                            uint8_t* __restrict__ status, size_t n) {
@@ -161,6 +157,74 @@ extern "C" int spg_limit_order_verify_batch(spg_ctx* ctx, const spg_limit_orders
   SPG_LAUNCH_CHECK();
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   if (!(flags & SPG_DEVICE_PTRS)) SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}
+
+// ------------------------------------------------------------------ the other perpetual messages (messages.cuh)
+struct MsgFieldsDev {
+  const uint64_t* felts[SPG_MSG_MAX_FELTS];
+  const uint64_t* ints[SPG_MSG_MAX_INTS];
+};
+
+__global__ void __launch_bounds__(128) k_pack_messages(int kind, MsgFieldsDev f, uint64_t* __restrict__ elems,
+                                                       uint8_t* __restrict__ status, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int nf = spg_msg_n_felts(kind), ni = spg_msg_n_ints(kind), len = spg_msg_chain_len(kind);
+  const uint64_t* fp[SPG_MSG_MAX_FELTS];
+  uint64_t iv[SPG_MSG_MAX_INTS];
+#pragma unroll
+  for (int k = 0; k < SPG_MSG_MAX_FELTS; k++) fp[k] = k < nf ? f.felts[k] + 4 * i : nullptr;
+#pragma unroll
+  for (int k = 0; k < SPG_MSG_MAX_INTS; k++) iv[k] = k < ni ? f.ints[k][i] : 0;
+  status[i] = (uint8_t)spg_pack_message(kind, fp, iv, elems + i * (size_t)len * 4);
+}
+
+extern "C" int spg_message_hash_batch(spg_ctx* ctx, int kind, const spg_message_fields* fields, uint64_t* msg_out,
+                                      uint8_t* status, size_t n, int flags) {
+  SPG_ARG(ctx && fields && msg_out && status, "spg_message_hash_batch: null");
+  const int len = spg_msg_chain_len(kind);
+  SPG_ARG(len != 0, "spg_message_hash_batch: unknown message kind");
+  const int nf = spg_msg_n_felts(kind), ni = spg_msg_n_ints(kind);
+  for (int k = 0; k < nf; k++) SPG_ARG(fields->felts[k], "spg_message_hash_batch: null felt array");
+  for (int k = 0; k < ni; k++) SPG_ARG(fields->ints[k], "spg_message_hash_batch: null integer array");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  MsgFieldsDev d;
+  for (int k = 0; k < SPG_MSG_MAX_FELTS; k++) d.felts[k] = k < nf ? fields->felts[k] : nullptr;
+  for (int k = 0; k < SPG_MSG_MAX_INTS; k++) d.ints[k] = k < ni ? fields->ints[k] : nullptr;
+  DevBuf bf[SPG_MSG_MAX_FELTS], bi[SPG_MSG_MAX_INTS], elems, pack_st, chain_st, bmsg, bst;
+  uint64_t* dmsg = msg_out; uint8_t* dst = status;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    for (int k = 0; k < nf; k++) {
+      SPG_CUDA(bf[k].alloc(ctx, n * 32));
+      SPG_CUDA(cudaMemcpyAsync(bf[k].p, fields->felts[k], n * 32, cudaMemcpyHostToDevice, ctx->stream));
+      d.felts[k] = bf[k].as<uint64_t>();
+    }
+    for (int k = 0; k < ni; k++) {
+      SPG_CUDA(bi[k].alloc(ctx, n * 8));
+      SPG_CUDA(cudaMemcpyAsync(bi[k].p, fields->ints[k], n * 8, cudaMemcpyHostToDevice, ctx->stream));
+      d.ints[k] = bi[k].as<uint64_t>();
+    }
+    SPG_CUDA(bmsg.alloc(ctx, n * 32)); SPG_CUDA(bst.alloc(ctx, n));
+    dmsg = bmsg.as<uint64_t>(); dst = bst.as<uint8_t>();
+  }
+  SPG_CUDA(elems.alloc(ctx, n * (size_t)len * 32)); SPG_CUDA(pack_st.alloc(ctx, n)); SPG_CUDA(chain_st.alloc(ctx, n));
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_pack_messages<<<blocks, 128, 0, ctx->stream>>>(kind, d, elems.as<uint64_t>(), pack_st.as<uint8_t>(), n);
+  SPG_LAUNCH_CHECK();
+  int rc;
+  if ((rc = spg_pedersen_chain_device(ctx, elems.as<uint64_t>(), len, dmsg, chain_st.as<uint8_t>(), n))) return rc;
+  k_merge_order_status<<<blocks, 128, 0, ctx->stream>>>(pack_st.as<uint8_t>(), chain_st.as<uint8_t>(), dst, n, 0);
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    SPG_CUDA(cudaMemcpyAsync(msg_out, dmsg, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
   return SPG_OK;

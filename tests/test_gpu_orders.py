@@ -10,6 +10,7 @@ import pytest
 from oracle import ecdsa as oecdsa
 from oracle.params import EC_ORDER, FIELD_PRIME as P
 from oracle.pedersen import pedersen_hash as opedersen
+from stark_perpetual_b200._lib import ints_to_limbs
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
@@ -101,3 +102,45 @@ def test_limit_order_verify_pipeline(ctx, pm):
     # a signature operand out of range makes the reference raise (signature.py:219)
     with pytest.raises(AssertionError):
         pm.verify_limit_orders_batch(orders[:2], rs[:2], [ss[0], EC_ORDER], keys[:2])
+
+
+def test_other_message_batches_vs_reference_vectors(ctx, golden, pm):
+    """spg_message_hash_batch (device packing + Pedersen chain) for transfers, conditional transfers, withdrawals to
+    an address and oracle prices: the 32 message hashes generated from the reference (tests/golden), the scalar
+    builders with the oracle's hash on random fields at the edges of every range, and the status of each violated
+    bound."""
+    rng = random.Random(2024)
+    for kind, scalar in (("transfer", pm.get_transfer_msg), ("conditional_transfer", pm.get_conditional_transfer_msg),
+                         ("withdrawal_to_address", pm.get_withdrawal_to_address_msg), ("price", pm.get_price_msg)):
+        vec = [(f, w) for k, f, w in golden["messages"] if k == kind]
+        assert len(vec) == 8
+        assert [hex(g) for g in pm.get_msg_batch(kind, [f for f, _w in vec])] == [w for _f, w in vec]
+        fnames, inames = pm._MESSAGE_ARGS[kind]
+        width = {"asset_id": 250, "asset_id_fee": 250, "receiver_public_key": 251, "condition": 251, "nonce": 32,
+                 "expiration_timestamp": 32, "asset_id_collateral": 250, "eth_address": 160, "asset_pair": 128, "price": 120,
+                 "oracle_name": 40, "timestamp": 32}
+        msgs = []
+        for i in range(40):
+            m = {}
+            for name in fnames + inames:
+                bits = width.get(name, 64)
+                m[name] = rng.choice([0, 1, 2**bits - 1, rng.randrange(2**bits), rng.randrange(2**bits)])
+            if "eth_address" in m:
+                m["eth_address"] = hex(m["eth_address"])
+            msgs.append(m)
+        got = pm.get_msg_batch(kind, msgs)
+        assert got == [scalar(hash_function=opedersen, **m) for m in msgs], kind
+        # every bound: one element out of range fails the whole batch like the reference's assert, and the C-ABI
+        # reports exactly that element
+        for name in fnames + inames:
+            if name not in width:
+                continue
+            bad = dict(msgs[3])
+            bad[name] = hex(2**width[name]) if name == "eth_address" else 2**width[name]
+            with pytest.raises(AssertionError):
+                pm.get_msg_batch(kind, msgs[:3] + [bad] + msgs[4:6])
+    assert pm.get_msg_batch("price", []) == []
+    felts = [ints_to_limbs([1, 2**250, 3]), ints_to_limbs([4, 5, 6]), ints_to_limbs([7, 8, 2**251])]
+    ints = [np.array([1, 2, 3], dtype=np.uint64)] * 7
+    _out, st = ctx.message_hash("transfer", felts, ints)
+    assert st.tolist() == [0, 1, 1]

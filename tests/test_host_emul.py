@@ -106,3 +106,76 @@ def test_emulated_sign_vs_golden_and_oracle(golden):
         st, rr, ss = o.split()
         assert st == "0" and int(rr, 16) == r and int(ss, 16) == s, (hex(m), seed)
     assert [o.split()[0] for o in out[len(cases):]] == ["1", "2", "2"]
+
+
+_MSG_ARGS = {   # kind -> (code, felt arguments, integer arguments) in the order include/spg.h lists
+    "transfer": (4, ("asset_id", "asset_id_fee", "receiver_public_key"),
+                 ("sender_position_id", "receiver_position_id", "src_fee_position_id", "nonce", "amount", "max_amount_fee",
+                  "expiration_timestamp")),
+    "conditional_transfer": (5, ("asset_id", "asset_id_fee", "receiver_public_key", "condition"),
+                             ("sender_position_id", "receiver_position_id", "src_fee_position_id", "nonce", "amount",
+                              "max_amount_fee", "expiration_timestamp")),
+    "withdrawal_to_address": (7, ("asset_id_collateral", "eth_address"), ("position_id", "nonce", "amount", "expiration_timestamp")),
+    "price": (100, ("asset_pair", "price"), ("oracle_name", "timestamp")),
+}
+
+
+def _msg_line(kind, fields):
+    code, fnames, inames = _MSG_ARGS[kind]
+    fv = [int(fields[f], 16) if isinstance(fields[f], str) else fields[f] for f in fnames]
+    return "%d %s %s" % (code, " ".join("%x" % v for v in fv), " ".join("%d" % fields[i] for i in inames))
+
+
+def test_emulated_message_packing_vs_reference_vectors(golden):
+    """The device packing code of the transfer / conditional transfer / withdrawal / oracle-price messages
+    (csrc/messages.cuh) run on the host: its chain elements, hashed with the oracle's Pedersen hash, must give the 32
+    message hashes the reference produced (tests/golden) and its own KATs (perpetual_messages_test.py:22-88); every
+    bound the reference asserts must be reported."""
+    from oracle.pedersen import pedersen_hash
+    exe = _build("emul_messages")
+    cases = [(k, f, int(w, 16)) for k, f, w in golden["messages"] if k in _MSG_ARGS]
+    pre = golden["messages_precomputed"]
+    for want, d in pre["transfer"].items():
+        cases.append(("transfer", dict(asset_id=d["assetId"], asset_id_fee=d["assetIdFee"], receiver_public_key=d["receiverPublicKey"],
+                                       sender_position_id=d["senderPositionId"], receiver_position_id=d["receiverPositionId"],
+                                       src_fee_position_id=d["feePositionId"], nonce=d["nonce"], amount=d["amount"],
+                                       max_amount_fee=d["maxAmountFee"], expiration_timestamp=d["expirationTimestamp"]), int(want, 16)))
+    for want, d in pre["conditional_transfer"].items():
+        cases.append(("conditional_transfer",
+                      dict(asset_id=d["assetId"], asset_id_fee=d["assetIdFee"], receiver_public_key=d["receiverPublicKey"],
+                           condition=d["condition"], sender_position_id=d["senderPositionId"],
+                           receiver_position_id=d["receiverPositionId"], src_fee_position_id=d["srcFeePositionId"],
+                           nonce=d["nonce"], amount=d["amount"], max_amount_fee=d["maxAmountFee"],
+                           expiration_timestamp=d["expirationTimestamp"]), int(want, 16)))
+    for want, d in pre["withdrawal_to_address"].items():
+        cases.append(("withdrawal_to_address",
+                      dict(asset_id_collateral=d["assetIdCollateral"], eth_address=d["ethAddress"], position_id=d["positionId"],
+                           nonce=d["nonce"], amount=d["amount"], expiration_timestamp=d["expirationTimestamp"]), int(want, 16)))
+    assert len(cases) >= 35
+    # out-of-range variants of the first case of each kind: (field, first value outside the reference's bound)
+    bad = []
+    limits = {"asset_id": 250, "asset_id_fee": 250, "receiver_public_key": 251, "condition": 251, "nonce": 32,
+              "expiration_timestamp": 32, "asset_id_collateral": 250, "eth_address": 160, "asset_pair": 128, "price": 120,
+              "oracle_name": 40, "timestamp": 32}
+    for kind in _MSG_ARGS:
+        base = next(f for k, f, _w in cases if k == kind)
+        for name, bits in limits.items():
+            if name in base:
+                bad.append((kind, dict(base, **{name: 2**bits})))
+                ok_edge = dict(base, **{name: 2**bits - 1})
+                cases.append((kind, ok_edge, None))
+    lines = [_msg_line(k, f) for k, f, _w in cases] + [_msg_line(k, f) for k, f in bad]
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout.strip().split("\n")
+    assert len(out) == len(lines)
+    for (kind, fields, want), o in zip(cases, out):
+        tok = o.split()
+        assert tok[0] == "0", (kind, fields)
+        el = [int(t, 16) for t in tok[1:]]
+        if want is None:
+            continue
+        h = pedersen_hash(el[0], el[1])
+        for e in el[2:]:
+            h = pedersen_hash(h, e)
+        assert h == want, kind
+    for (kind, fields), o in zip(bad, out[len(cases):]):
+        assert o.split()[0] == "1", (kind, fields)
