@@ -30,6 +30,10 @@ def test_empty_batches(ctx):
                     "expiration_timestamp": np.empty(0, np.uint32)}
     out, st = ctx.limit_order_msg(empty_orders)
     assert out.shape == (0, 4) and st.shape == (0,)
+    r, s, st = ctx.sign(E4, E4)
+    assert r.shape == (0, 4) and s.shape == (0, 4) and st.shape == (0,)
+    out, st = ctx.message_hash("price", [E4, E4], [np.empty(0, np.uint64)] * 2)
+    assert out.shape == (0, 4) and st.shape == (0,)
 
 
 def test_single_element_and_size_one_transforms(ctx):
@@ -100,5 +104,12 @@ def test_argument_errors_are_reported_not_crashed(ctx):
     assert lib.spg_pedersen_merkle_tree(h, x.ctypes.data_as(C.c_void_p), 6, root.ctypes.data_as(C.c_void_p), None,
                                         st.ctypes.data_as(C.c_void_p), 0) == -2                                         # 6 leaves
     assert b"bad argument" in lib.spg_last_error(h)
+    vp = C.c_void_p
+    fields = (vp * 11)(*([x.ctypes.data] * 11))
+    assert lib.spg_message_hash_batch(h, 6, C.cast(fields, vp), x.ctypes.data_as(vp), st.ctypes.data_as(vp), 1, 0) == -2   # kind
+    fields[1] = None
+    assert lib.spg_message_hash_batch(h, 4, C.cast(fields, vp), x.ctypes.data_as(vp), st.ctypes.data_as(vp), 1, 0) == -2   # null array
+    assert lib.spg_sign_batch(h, x.ctypes.data_as(vp), None, None, x.ctypes.data_as(vp), x.ctypes.data_as(vp),
+                              st.ctypes.data_as(vp), 1, 0) == -2                                                        # null key
     # still healthy
     assert np.array_equal(ctx.ntt(ctx.ntt(x, 3, False, NTT_NAT_TO_REV), 3, True, NTT_REV_TO_NAT), x)
