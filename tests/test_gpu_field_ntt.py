@@ -78,7 +78,7 @@ def test_ntt_2_18_config2(ctx):
     assert np.array_equal(back, x)
 
 
-@pytest.mark.parametrize("log_n,batch", [(13, 5), (16, 3), (20, 2), (21, 1), (22, 1)])
+@pytest.mark.parametrize("log_n,batch", [(13, 5), (16, 3), (20, 2), (21, 1), (22, 1), (23, 1)])   # 23: three passes
 def test_ntt_large_vs_c_oracle(ctx, log_n, batch):
     x = rand_felts(batch << log_n, 500 + log_n)
     for inverse in (False, True):

@@ -8,7 +8,8 @@ from oracle import clib
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("log_n,n_cols,log_blowup", [(0, 1, 1), (3, 2, 3), (9, 3, 2), (12, 5, 3), (16, 3, 3), (20, 1, 1)])
+@pytest.mark.parametrize("log_n,n_cols,log_blowup", [(0, 1, 1), (3, 2, 3), (9, 3, 2), (12, 5, 3), (16, 3, 3), (20, 1, 1), (21, 1, 2),
+                                                     (23, 1, 1)])   # 21: the 2^11 tile; 23: three passes
 def test_lde_vs_c_oracle(ctx, log_n, n_cols, log_blowup):
     tr = rand_felts(n_cols << log_n, 700 + log_n)
     got = ctx.lde(tr, log_n, n_cols, log_blowup)
