@@ -102,12 +102,6 @@ static int ensure_air_tables(spg_ctx* ctx, unsigned log_n, unsigned chain_log) {
 }
 
 // ------------------------------------------------------------------ composition evaluation
-struct AirEvalConsts {
-  Fp alpha[SPG_AIR_LANES * SPG_AIR_NCONSTR];
-  Fp x0[SPG_AIR_LANES], outs[SPG_AIR_LANES];
-  Fp shift_x, shift_y;
-};
-
 #ifndef AIR_MIN_CTAS
 #define AIR_MIN_CTAS 1
 #endif
@@ -121,58 +115,21 @@ __global__ void __launch_bounds__(128, AIR_MIN_CTAS) k_air_eval(unsigned log_n, 
   const size_t jj = (idx >> log_n) + jj0, i = idx & (n - 1), j = 2 * jj;
   const size_t in = (i + 1) & (n - 1);
   const Fp px = plde[(j * 2 + 0) * 512 + (i & 511)], py = plde[(j * 2 + 1) * 512 + (i & 511)];
-  const Fp one = fp_one();
-  // accumulators per zerofier group.  Lazy arithmetic (fp.cuh): trace values are canonical (< p), products are below
-  // 2p, sums are plain additions and differences add K*p (K = bound of the subtrahend in units of p, in brackets
-  // below); each accumulator is brought back below 2p once per lane, so it never exceeds 2p + 4 * 2p = 10p.
-  Fp a_step = fp_zero(), a_act = fp_zero(), a_pad = fp_zero(), a_mid = fp_zero(), a_link = fp_zero(),
-     a_inst = fp_zero(), a_seg = fp_zero(), a_last = fp_zero();
+  AirAcc A;
+  air_acc_init(A);
   const Fp* base = t_lde + ((j - first_coset) * SPG_AIR_COLS << log_n);
 #pragma unroll 1
   for (int l = 0; l < SPG_AIR_LANES; l++) {
     const Fp* c0 = base + ((size_t)(5 * l) << log_n);
-    const Fp X = c0[i], Y = c0[n + i], S = c0[2 * n + i], M = c0[3 * n + i], I = c0[4 * n + i];
-    const Fp Xn = c0[in], Yn = c0[n + in], Mn = c0[3 * n + in];
-    const Fp* al = K->alpha + SPG_AIR_NCONSTR * l;
-    const Fp bit = fp_sub_lazy(M, fp_add_raw(Mn, Mn), 2);                  // [< 3p]
-    const Fp dx = fp_sub_lazy(X, px, 1);                                   // [< 2p]
-    const Fp dXn = fp_sub_lazy(Xn, X, 1), dYn = fp_sub_lazy(Yn, Y, 1);     // Xn - X, Yn - Y  [< 2p]
-    // c1 = bit (bit - 1)
-    const Fp c1 = fp_mul_lazy(bit, fp_sub_lazy(bit, one, 1));
-    // c2 = bit (S (X - px) - (Y - py))
-    const Fp c2 = fp_mul_lazy(bit, fp_sub_lazy(fp_mul_lazy(S, dx), fp_sub_lazy(Y, py, 1), 2));
-    // c3 = bit (S^2 - px - 2 Xn) + (Xn - X)      [== bit (S^2 - X - px - Xn) + (1 - bit)(Xn - X)]
-    const Fp c3 = fp_add_raw(fp_mul_lazy(bit, fp_sub_lazy(fp_sub_lazy(fp_sqr(S), px, 1), fp_add_raw(Xn, Xn), 2)), dXn);
-    // c4 = bit (S (X - Xn) - 2 Yn) + (Yn - Y)    [== bit (S (X - Xn) - Y - Yn) + (1 - bit)(Yn - Y)]
-    const Fp c4 = fp_add_raw(fp_mul_lazy(bit, fp_sub_lazy(fp_mul_lazy(S, fp_sub_lazy(X, Xn, 1)), fp_add_raw(Yn, Yn), 2)), dYn);
-    a_step = fp_partial(fp_add_raw(fp_add_raw(a_step, fp_add_raw(fp_mul_lazy(al[0], c1), fp_mul_lazy(al[1], c2))),
-                                   fp_add_raw(fp_mul_lazy(al[2], c3), fp_mul_lazy(al[3], c4))));
-    // c5 = I (X - px) - 1
-    a_act = fp_partial(fp_add_raw(a_act, fp_mul_lazy(al[4], fp_sub_lazy(fp_mul_lazy(I, dx), one, 1))));
-    // c6 = M
-    a_pad = fp_partial(fp_add_raw(a_pad, fp_mul_lazy(al[5], M)));
-    // c7 = Xn - X, c8 = Yn - Y
-    a_mid = fp_partial(fp_add_raw(a_mid, fp_add_raw(fp_mul_lazy(al[6], dXn), fp_mul_lazy(al[7], dYn))));
-    // c9 = Mn - X
-    a_link = fp_partial(fp_add_raw(a_link, fp_mul_lazy(al[8], fp_sub_lazy(Mn, X, 1))));
-    // c10 = X - shift.x, c11 = Y - shift.y
-    a_inst = fp_partial(fp_add_raw(a_inst, fp_add_raw(fp_mul_lazy(al[9], fp_sub_lazy(X, K->shift_x, 1)),
-                                                      fp_mul_lazy(al[10], fp_sub_lazy(Y, K->shift_y, 1)))));
-    // c12 = M - x0
-    a_seg = fp_partial(fp_add_raw(a_seg, fp_mul_lazy(al[11], fp_sub_lazy(M, K->x0[l], 1))));
-    // c13 = X - out
-    a_last = fp_partial(fp_add_raw(a_last, fp_mul_lazy(al[12], fp_sub_lazy(X, K->outs[l], 1))));
+    AirRow r;
+    r.X = c0[i]; r.Y = c0[n + i]; r.S = c0[2 * n + i]; r.M = c0[3 * n + i]; r.I = c0[4 * n + i];
+    r.Xn = c0[in]; r.Yn = c0[n + in]; r.Mn = c0[3 * n + in];
+    air_lane_accumulate(A, r, K->alpha + SPG_AIR_NCONSTR * l, px, py, K->shift_x, K->shift_y, K->x0[l], K->outs[l]);
   }
   const size_t stride = 4 * seg, zi = jj * seg + (i & (seg - 1));
-  Fp acc = fp_mul_lazy(a_step, izt[0 * stride + zi]);
-  acc = fp_add_raw(acc, fp_mul_lazy(a_act, izt[1 * stride + zi]));
-  acc = fp_add_raw(acc, fp_mul_lazy(a_pad, izt[2 * stride + zi]));
-  acc = fp_add_raw(acc, fp_mul_lazy(a_mid, izt[3 * stride + zi]));
-  acc = fp_add_raw(acc, fp_mul_lazy(a_link, izt[4 * stride + zi]));
-  acc = fp_add_raw(acc, fp_mul_lazy(a_inst, izt[5 * stride + zi]));
-  acc = fp_add_raw(acc, fp_mul_lazy(a_seg, izt[6 * stride + zi]));
-  acc = fp_add_raw(acc, fp_mul_lazy(a_last, ilast[(jj << log_n) + i]));      // eight products: < 16p
-  cp[idx] = fp_reduce_full(acc);
+  const Fp acc = air_combine(A, izt[0 * stride + zi], izt[1 * stride + zi], izt[2 * stride + zi], izt[3 * stride + zi],
+                             izt[4 * stride + zi], izt[5 * stride + zi], izt[6 * stride + zi], ilast[(jj << log_n) + i]);
+  cp[idx] = acc;
 }
 
 int spg_air_eval_device(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const Fp* t_lde, const AirPublic& pub,

@@ -890,6 +890,7 @@ SPG_HD Fp fp_reduce(const Fp& a) { SPG_DISPATCH(fpd_reduce(a), fph_reduce(a)); }
 SPG_HD Fp fp_add_raw(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_add_raw(a, b), fph_add_raw(a, b)); }
 // the lazy family used by the NTT butterflies (bounds: see each fpd_* function)
 SPG_HD Fp fp_mul_lazy(const Fp& a, const Fp& b) { SPG_DISPATCH(fpd_mul(a, b), fph_mul_lazy(a, b)); }
+SPG_HD Fp fp_sqr_lazy(const Fp& a) { SPG_DISPATCH(fpd_sqr(a), fph_mul_lazy(a, a)); }
 SPG_HD Fp fp_sub_lazy(const Fp& a, const Fp& b, uint32_t K) { SPG_DISPATCH(fpd_sub_lazy(a, b, K), fph_sub_lazy(a, b, K)); }
 SPG_HD Fp fp_partial(const Fp& a) { SPG_DISPATCH(fpd_partial(a), fph_partial(a)); }
 SPG_HD Fp fp_reduce_full(const Fp& a) { SPG_DISPATCH(fpd_reduce_full(a), fph_reduce_full(a)); }

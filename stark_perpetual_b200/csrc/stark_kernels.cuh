@@ -5,10 +5,9 @@
 #include "common.h"
 #include "ec.cuh"
 #include "ntt.cuh"
+#include "air_point.cuh"   // SPG_AIR_LANES, SPG_AIR_NCONSTR
 
-#define SPG_AIR_LANES 5
 #define SPG_AIR_COLS 25
-#define SPG_AIR_NCONSTR 13
 #define SPG_LOG_BLOWUP 3
 #define SPG_BLOWUP 8
 #define SPG_FRI_LAST_MAX 64
