@@ -9,16 +9,19 @@
 // products live in the output buffers themselves, and ONE Fermat inversion (of the product of the three running
 // products) serves all chains of the thread.  Per output: (1 + 2/3) multiplications forward, (2 + 2/3) backward,
 // plus 271 / (3 ch) for the inversion.
+#ifndef INV_THREADS
+#define INV_THREADS 128     // 160 registers per thread: three CTAs of 128 threads per SM (12 warps) instead of one of 256
+#endif
 template <int NA>
-__global__ void __launch_bounds__(256) k_inv_x_minus(unsigned log_n, int j0, int jstep, int nj, const Fp* __restrict__ A,
+__global__ void __launch_bounds__(INV_THREADS) k_inv_x_minus(unsigned log_n, int j0, int jstep, int nj, const Fp* __restrict__ A,
                                                      Fp* __restrict__ out, int ch, Fp g, const Fp* __restrict__ uniA,
                                                      const Fp* __restrict__ uniB) {
   const size_t n = (size_t)1 << log_n;
   const int jj = blockIdx.y, a0 = blockIdx.z * NA, j = j0 + jstep * jj;
-  const size_t i0 = (size_t)blockIdx.x * 256 * ch + threadIdx.x;
+  const size_t i0 = (size_t)blockIdx.x * INV_THREADS * ch + threadIdx.x;
   const int sh = SPG_UNI_LOG - (int)log_n - SPG_LOG_BLOWUP;
   Fp x = fp_mul(g, spg_uni_pow(uniA, uniB, ((unsigned long long)j + 8ull * i0) << sh));
-  const unsigned long long step_e = (256ull << (SPG_UNI_LOG - log_n));
+  const unsigned long long step_e = ((unsigned long long)INV_THREADS << (SPG_UNI_LOG - log_n));
   const Fp step = spg_uni_pow(uniA, uniB, step_e), stepinv = spg_uni_pow(uniA, uniB, 0ull - step_e);
   Fp av[NA], acc[NA];
   Fp* o[NA];
@@ -29,7 +32,7 @@ __global__ void __launch_bounds__(256) k_inv_x_minus(unsigned log_n, int j0, int
     o[a] = out + (((size_t)(a0 + a) * nj + jj) << log_n);
   }
   for (int k = 0; k < ch; k++) {
-    const size_t i = i0 + 256ull * k;
+    const size_t i = i0 + (size_t)INV_THREADS * k;
     if (i < n) {
 #pragma unroll
       for (int a = 0; a < NA; a++) { o[a][i] = acc[a]; acc[a] = fp_mul(acc[a], fp_sub(x, av[a])); }
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(256) k_inv_x_minus(unsigned log_n, int j0, int
   }
   for (int k = ch - 1; k >= 0; k--) {
     x = fp_mul(x, stepinv);
-    const size_t i = i0 + 256ull * k;
+    const size_t i = i0 + (size_t)INV_THREADS * k;
     if (i < n) {
 #pragma unroll
       for (int a = 0; a < NA; a++) {
@@ -69,16 +72,29 @@ static Fp host_gen() { uint64_t three[4] = {3, 0, 0, 0}; return spg_host_from_u6
 
 int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int nj, const Fp* d_A, int n_a, Fp* out) {
   const size_t n = (size_t)1 << log_n;
-  int ch = (int)(n / 256 / 8);
-  if (ch < 1) ch = 1;
-  if (ch > 64) ch = 64;
-  const unsigned tiles = (unsigned)((n + 256ull * ch - 1) / (256ull * ch));
+  // points per thread: as many as keep the grid at a whole number of waves of sm_count * 3 resident CTAs (the single
+  // Fermat inversion of a thread is amortised over 3 * ch outputs), between 16 and 96
+  const size_t per_cta_min = INV_THREADS;
+  int ch = 1;
+  if (n > per_cta_min * 16) {
+    const int groups = (n_a % 3 == 0) ? n_a / 3 : n_a;
+    const double slots = (double)ctx->sm_count * 3;
+    for (int waves = 1; waves <= 64; waves++) {
+      const double tiles_f = waves * slots / ((double)nj * groups);
+      const size_t tiles_w = tiles_f < 1.0 ? 1 : (size_t)tiles_f;
+      const size_t c = (n + tiles_w * INV_THREADS - 1) / (tiles_w * INV_THREADS);
+      ch = (int)c;
+      if (c <= 96) break;
+    }
+    if (ch < 16) ch = 16;
+  }
+  const unsigned tiles = (unsigned)((n + (size_t)INV_THREADS * ch - 1) / ((size_t)INV_THREADS * ch));
   if (n_a % 3 == 0) {
     dim3 grid(tiles, (unsigned)nj, (unsigned)(n_a / 3));
-    k_inv_x_minus<3><<<grid, 256, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
+    k_inv_x_minus<3><<<grid, INV_THREADS, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
   } else {
     dim3 grid(tiles, (unsigned)nj, (unsigned)n_a);
-    k_inv_x_minus<1><<<grid, 256, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
+    k_inv_x_minus<1><<<grid, INV_THREADS, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
   }
   SPG_LAUNCH_CHECK();
   return SPG_OK;
