@@ -1,6 +1,8 @@
 #!/bin/bash
 # One GPU-box session: parity tests, probes, bench, ncu launch list, per-kernel pipe metrics and a full capture of the
 # dominant kernel.  Usage (from the repo root on the GPU box):  bash tools/gpu_round.sh <tag> [kernel-regex]
+# Cost: about 17 GPU-minutes, 11 of them the per-kernel pipe-metric pass (ncu replays all launches of four proofs);
+# set SKIP_PIPES=1 to leave that pass out (about 6 minutes).
 TAG=${1:-r1}
 KREGEX=${2:-k_ntt_pass}
 mkdir -p gpurun_out
@@ -17,8 +19,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_bench.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_bench.log | cut -c1-300
 echo "=== ncu pipes (all kernels of one step)"
-bash tools/ncu_pipes.sh ${TAG} > /dev/null 2>&1
-head -4 gpurun_out/${TAG}_pipes_summary.txt
+if [ -z "$SKIP_PIPES" ]; then
+  bash tools/ncu_pipes.sh ${TAG} > /dev/null 2>&1
+  head -4 gpurun_out/${TAG}_pipes_summary.txt
+fi
 echo "=== ncu full"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 60 -c 2 -f -o gpurun_out/${TAG}_prof \
   python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_full.log 2>&1
