@@ -26,6 +26,8 @@ RINV = pow(R_MOD_P, -1, P)
 MAGIC = b"SPGP"
 VERSION = 1
 LAST_LAYER_MAX = 64
+CANON_BITS = 251          # scalars are unpacked into 251 bits (M = 0 from row 251 on): unique decomposition mod p
+MIN_QUERIES = 30          # the protocol's query count; verify() rejects proofs carrying fewer unless told otherwise
 
 
 def inv(a):
@@ -116,8 +118,10 @@ def periodic_points():
     return px, py
 
 
-def gen_trace(log_n, chain_log, x0, ys):
-    """x0: LANES seeds; ys[lane][instance] second hash inputs.  Returns (columns [25][N], outputs [LANES])."""
+def gen_trace(log_n, chain_log, x0, ys, unpack_override=None):
+    """x0: LANES seeds; ys[lane][instance] second hash inputs.  Returns (columns [25][N], outputs [LANES]).
+    unpack_override (negative tests only): {(lane, instance, element): integer w} walks the bits of w (w = v mod p,
+    e.g. v + p) instead of the canonical v -- the cheating witness the canonical-unpacking constraint must reject."""
     n = 1 << log_n
     inst = n // 512
     cols = [[0] * n for _ in range(N_COLS)]
@@ -132,9 +136,14 @@ def gen_trace(log_n, chain_log, x0, ys):
             for e in range(2):
                 v = elems[e]
                 assert 0 <= v < P
+                if unpack_override and (l, q, e) in unpack_override:
+                    assert unpack_override[(l, q, e)] % P == v
+                    v = unpack_override[(l, q, e)]
+                else:
+                    assert v < (1 << CANON_BITS), "hash input >= 2^251: outside the AIR's canonical range"
                 for t in range(256):
                     r = 512 * q + 256 * e + t
-                    X[r], Y[r], M[r] = pt_sum[0], pt_sum[1], v >> t
+                    X[r], Y[r], M[r] = pt_sum[0], pt_sum[1], (v >> t) % P
                     if t < 252:
                         cx, cy = CONSTANT_POINTS[2 + 252 * e + t]
                         d = (pt_sum[0] - cx) % P
@@ -176,11 +185,15 @@ class Air:
         z_pad = 1
         for k in range(252, 256):
             z_pad = z_pad * (u256 - pow(self.w256, k, P)) % P
+        # c6 (M = 0) also covers row 251: the scalar is unpacked into 251 bits only, so the integer the bits spell
+        # is below 2^251 < p and therefore THE canonical representative of M_0 (signature.py:307 `0 <= x < p`
+        # uses the integer; a 252-bit unpacking would also accept x + p for x < 2^252 - p)
+        z_zero = z_pad * (u256 - pow(self.w256, CANON_BITS, P)) % P
         iz_all = inv(z_all)
         return {
             "step": e_step * iz_all % P,
             "act": z_pad * iz_all % P,
-            "pad": inv(z_pad),
+            "pad": inv(z_zero),
             "mid": inv(u512 - pow(self.w512, 255, P)),
             "link": (useg - inv(self.wseg)) * inv(u512 - pow(self.w512, 511, P)) % P,
             "inst0": inv(u512 - 1),
@@ -422,14 +435,18 @@ class _Reader:
             raise ProofError(str(e))
 
 
-def verify(proof):
-    """Returns the public statement {log_n, chain_log, x0, outs} if the proof is valid, raises ProofError otherwise."""
+def verify(proof, min_queries=MIN_QUERIES):
+    """Returns the public statement {log_n, chain_log, x0, outs} if the proof is valid, raises ProofError otherwise.
+    The query count is read from the proof header; proofs with fewer than `min_queries` queries are rejected
+    (blowup 8, no grinding: each query is worth 3 bits)."""
     rd = _Reader(proof)
     if rd.take(4) != MAGIC or rd.u32() != VERSION:
         raise ProofError("bad header")
     log_n, chain_log, n_queries, n_folds = rd.u32(), rd.u32(), rd.u32(), rd.u32()
     if not (9 <= log_n <= 23) or 512 << chain_log > 1 << log_n or n_queries < 1:
         raise ProofError("bad parameters")
+    if n_queries < min_queries:
+        raise ProofError("proof carries %d queries, fewer than the %d required" % (n_queries, min_queries))
     sizes = fri_layer_sizes(log_n)
     if n_folds != len(sizes) - 1:
         raise ProofError("bad layer count")

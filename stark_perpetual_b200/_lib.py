@@ -426,10 +426,15 @@ class Context:
 
 
 _CTX = {}
+_CTX_LOCK = threading.Lock()
 
 
 def get_context(device=0):
-    """Process-wide cached Context per device."""
-    if device not in _CTX:
-        _CTX[device] = Context(device)
-    return _CTX[device]
+    """Process-wide cached Context per device.  Safe to call and to use from several threads: creation is guarded here,
+    and every libspg entry point serialises on the context's own mutex (csrc/common.h SPG_LOCK), so concurrent
+    pedersen_hash / verify calls on the shared context queue up instead of racing on its stream and buffer pool.  For
+    parallel streams of work create one Context per thread."""
+    with _CTX_LOCK:
+        if device not in _CTX:
+            _CTX[device] = Context(device)
+        return _CTX[device]

@@ -150,21 +150,37 @@ def inv_mod_curve_size(x: int) -> int:
 
 # ---------------------------------------------------------------------------------- verify
 def verify_batch(msg_hashes, rs, ss, public_keys):
-    """public_keys: all ints (x-only) or all (x, y) tuples.  Returns a list of bool; raises AssertionError if the
-    reference would raise for any element (signature.py:219, :225-227, :241)."""
+    """public_keys: per element an integer (x-only key, signature.py:229-238) or an (x, y) pair (:239-241); the two kinds
+    may be mixed.  Returns a list of bool; raises AssertionError if the reference would raise for any element
+    (signature.py:219, :225-227, :241).  Key coordinates are reduced mod p before they go to the device: the reference's
+    arithmetic does the same implicitly (get_y_coordinate :90, is_point_on_curve :200 and every EC formula work mod p)."""
+    import numbers
     n = len(msg_hashes)
+    assert len(rs) == n and len(ss) == n and len(public_keys) == n
     if n == 0:
         return []
-    point = not isinstance(public_keys[0], int)
-    vals = list(msg_hashes) + list(rs) + list(ss)
-    keys_x = [k[0] if point else k for k in public_keys]
-    keys_y = [k[1] for k in public_keys] if point else None
-    for v in vals + keys_x + (keys_y or []):
+    for v in list(msg_hashes) + list(rs) + list(ss):
         assert 0 <= v < 2**256, "operand does not fit 256 bits"
-    st = _ctx().ecdsa_verify(ints_to_limbs(msg_hashes), ints_to_limbs(rs), ints_to_limbs(ss), ints_to_limbs(keys_x),
-                             ints_to_limbs(keys_y) if point else None)
-    assert not (st == 2).any(), "precondition violated (s, r, w or msg_hash out of range, or key not on curve)"
-    return [bool(v) for v in st]
+    is_x = [isinstance(k, numbers.Integral) for k in public_keys]
+    out = [None] * n
+    for kind in (True, False):
+        sel = [i for i in range(n) if is_x[i] == kind]
+        if not sel:
+            continue
+        if kind:
+            keys_x, keys_y = [int(public_keys[i]) % FIELD_PRIME for i in sel], None
+        else:
+            for i in sel:
+                assert len(public_keys[i]) == 2, "public key must be an integer or an (x, y) pair"
+            keys_x = [int(public_keys[i][0]) % FIELD_PRIME for i in sel]
+            keys_y = [int(public_keys[i][1]) % FIELD_PRIME for i in sel]
+        st = _ctx().ecdsa_verify(ints_to_limbs([int(msg_hashes[i]) for i in sel]), ints_to_limbs([int(rs[i]) for i in sel]),
+                                 ints_to_limbs([int(ss[i]) for i in sel]), ints_to_limbs(keys_x),
+                                 ints_to_limbs(keys_y) if keys_y is not None else None)
+        assert not (st == 2).any(), "precondition violated (s, r, w or msg_hash out of range, or key not on curve)"
+        for i, v in zip(sel, st):
+            out[i] = bool(v)
+    return out
 
 
 def verify(msg_hash: int, r: int, s: int, public_key: Union[int, ECPoint]) -> bool:

@@ -9,6 +9,7 @@
 struct AirTableConsts {
   Fp g256, g512, gseg;          // g^(N/256), g^(N/512), g^(N/seg)
   Fp w256[4];                   // w_256^252 .. w_256^255
+  Fp w256_canon;                // w_256^251: c6 (M = 0) starts at row 251 -- canonical 251-bit unpacking (DESIGN.md "AIR")
   Fp w512_255, w512_511, wseg_inv;
   Fp iz_all[4];                 // 1 / (x^N - 1) on cosets 0, 2, 4, 6
 };
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(128) k_air_tables(unsigned log_seg, AirTableCo
 #pragma unroll
   for (int k = 1; k < 4; k++) z_pad = fp_mul(z_pad, fp_sub(u256, K.w256[k]));
   // five inversions with one Fermat chain
-  const Fp a = z_pad, b = fp_sub(u512, K.w512_255), c = fp_sub(u512, K.w512_511), d = fp_sub(u512, fp_one()),
+  const Fp a = fp_mul(z_pad, fp_sub(u256, K.w256_canon)), b = fp_sub(u512, K.w512_255), c = fp_sub(u512, K.w512_511), d = fp_sub(u512, fp_one()),
            f = fp_sub(useg, fp_one());
   const Fp p2 = fp_mul(a, b), p3 = fp_mul(p2, c), p4 = fp_mul(p3, d), p5 = fp_mul(p4, f);
   Fp inv = fp_inv_chain(p5);
@@ -65,6 +66,7 @@ static int ensure_air_tables(spg_ctx* ctx, unsigned log_n, unsigned chain_log) {
   K.g256 = fp_pow_u64(g, n >> 8); K.g512 = fp_pow_u64(g, n >> 9); K.gseg = fp_pow_u64(g, n >> log_seg);
   const Fp w256 = spg_host_root_of_unity(8), w512 = spg_host_root_of_unity(9), wseg = spg_host_root_of_unity((int)log_seg);
   for (int k = 0; k < 4; k++) K.w256[k] = fp_pow_u64(w256, 252 + k);
+  K.w256_canon = fp_pow_u64(w256, SPG_AIR_CANON_BITS);
   K.w512_255 = fp_pow_u64(w512, 255); K.w512_511 = fp_pow_u64(w512, 511); K.wseg_inv = fp_inv(wseg);
   const Fp gn = fp_pow_u64(g, n), w8 = spg_host_root_of_unity(3);
   for (int jj = 0; jj < 4; jj++) K.iz_all[jj] = fp_inv(fp_sub(fp_mul(gn, fp_pow_u64(w8, 2 * jj)), fp_one()));
@@ -203,7 +205,8 @@ Fp spg_air_composition_at_host(unsigned log_n, unsigned chain_log, const AirPubl
   Fp z_pad = one;
   for (int k = 252; k < 256; k++) z_pad = fp_mul(z_pad, fp_sub(u256, fp_pow_u64(w256, k)));
   const Fp iz_step = fp_mul(fp_sub(u256, fp_pow_u64(w256, 255)), iz_all);
-  const Fp iz_act = fp_mul(z_pad, iz_all), iz_pad = fp_inv(z_pad);
+  const Fp iz_act = fp_mul(z_pad, iz_all);
+  const Fp iz_pad = fp_inv(fp_mul(z_pad, fp_sub(u256, fp_pow_u64(w256, SPG_AIR_CANON_BITS))));   // M = 0 on rows >= 251
   const Fp iz_mid = fp_inv(fp_sub(u512, fp_pow_u64(w512, 255)));
   const Fp iz_link = fp_mul(fp_sub(useg, fp_inv(wseg)), fp_inv(fp_sub(u512, fp_pow_u64(w512, 511))));
   const Fp iz_inst = fp_inv(fp_sub(u512, one)), iz_seg = fp_inv(fp_sub(useg, one));
@@ -273,7 +276,8 @@ __global__ void __launch_bounds__(64) k_pedersen_trace(unsigned log_n, unsigned 
     APoint ps = cp[0];
     for (int e = 0; e < 2; e++) {
       Fp v = e ? ys[l * inst + q] : a;            // canonical scalar, shifted right one bit per row
-      if (spg_canon_geq_p(v.v)) st = 1;
+      if (spg_canon_geq_p(v.v)) st |= 1;
+      else if (v.v[7] >> 27) st |= 4;             // >= 2^251: outside the AIR's canonical 251-bit unpacking
       for (int t = 0; t < 256; t++) {
         const size_t r = (q << 9) + 256 * e + t;
         X[r] = fp_from_mont(ps.x); Y[r] = fp_from_mont(ps.y); M[r] = v;
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(64) k_pedersen_trace(unsigned log_n, unsigned 
         if (t < SPG_HASH_BITS) {
           const APoint pt = cp[2 + SPG_HASH_BITS * e + t];
           const Fp d = fp_sub(ps.x, pt.x);
-          if (fp_is_zero(d)) st = 2;              // "Unhashable input." (signature.py:313)
+          if (fp_is_zero(d)) st |= 2;             // "Unhashable input." (signature.py:313)
           const Fp di = fp_inv_chain(d);
           i_out = fp_from_mont(di);
           if (v.v[0] & 1u) {

@@ -8,6 +8,10 @@
 
 #define SPG_AIR_LANES 5
 #define SPG_AIR_NCONSTR 13
+// Scalars are unpacked into 251 bits: c6 (M = 0) holds from row 251 of every 256-row element block on, so the bits spell
+// an integer below 2^251 < p -- the unique canonical representative the reference hashes (signature.py:307).  With the
+// 252 steps the reference walks, x and x + p (x < 2^252 - p) would both satisfy the constraints.
+#define SPG_AIR_CANON_BITS 251
 
 struct AirEvalConsts {
   Fp alpha[SPG_AIR_LANES * SPG_AIR_NCONSTR];

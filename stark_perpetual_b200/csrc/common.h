@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -10,6 +11,11 @@
 #include "fp.cuh"
 
 struct spg_ctx {
+  // Every C-ABI entry point holds this lock for its whole duration (SPG_LOCK): a context owns one stream, one temporary
+  // pool, one error string and one set of timing events, so concurrent calls on the SAME context are serialised here
+  // (ctypes releases the GIL around calls; the reference's functions are pure and callers may be threaded).  Distinct
+  // contexts never share state and run concurrently.  Recursive because pipeline entry points call stage entry points.
+  std::recursive_mutex mu;
   int device = -1;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
@@ -91,6 +97,10 @@ static inline cudaError_t spg_scratch(spg_ctx* ctx, int slot, size_t bytes, void
   *out = ctx->scratch_p[slot];
   return cudaSuccess;
 }
+
+#define SPG_LOCK(ctx)                                   \
+  std::unique_lock<std::recursive_mutex> spg_lock_;     \
+  if (ctx) spg_lock_ = std::unique_lock<std::recursive_mutex>((ctx)->mu)
 
 #define SPG_CUDA(call)                                                                  \
   do {                                                                                  \

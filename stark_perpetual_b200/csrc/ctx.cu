@@ -109,9 +109,12 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
 }
 
 extern "C" const char* spg_last_error(spg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-extern "C" double spg_last_kernel_ms(spg_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
-extern "C" uint64_t spg_launch_count(spg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" double spg_last_kernel_ms(spg_ctx* ctx) {
+  SPG_LOCK(ctx); return ctx ? ctx->last_ms : 0.0; }
+extern "C" uint64_t spg_launch_count(spg_ctx* ctx) {
+  SPG_LOCK(ctx); return ctx ? ctx->launches : 0; }
 extern "C" int spg_set_stream(spg_ctx* ctx, void* cuda_stream) {
+  SPG_LOCK(ctx);
   if (!ctx) return SPG_E_ARG;
   SPG_CUDA(cudaSetDevice(ctx->device));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -121,9 +124,11 @@ extern "C" int spg_set_stream(spg_ctx* ctx, void* cuda_stream) {
   return SPG_OK;
 }
 extern "C" double spg_stage_ms(spg_ctx* ctx, int stage) {
+  SPG_LOCK(ctx);
   return (ctx && stage >= 0 && stage < 16) ? ctx->stage_ms[stage] : 0.0;
 }
 extern "C" int spg_synchronize(spg_ctx* ctx) {
+  SPG_LOCK(ctx);
   SPG_CUDA(cudaSetDevice(ctx->device));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
@@ -170,6 +175,7 @@ __global__ void k_field_op(int op, const Fp* a, const Fp* b, Fp* out, size_t n) 
 
 extern "C" int spg_field_op(spg_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
                             size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && a && out && op >= 0 && op <= 15, "spg_field_op");
   SPG_ARG(op == 3 || op == 8 || op == 10 || op == 11 || op >= 13 || b, "spg_field_op: b required");
   SPG_CUDA(cudaSetDevice(ctx->device));
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(256) k_bench_imad_wide(unsigned long long* out
 
 extern "C" int spg_bench_field_mul(spg_ctx* ctx, int iters, int chains, double* mul_per_s,
                                    double* imad_wide_per_s) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && iters > 0 && (chains == 1 || chains == 2 || chains == 4), "spg_bench_field_mul");
   SPG_CUDA(cudaSetDevice(ctx->device));
   const int threads = 256, blocks = ctx->sm_count * 8;

@@ -139,6 +139,7 @@ int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len
 // ------------------------------------------------------------------ C-ABI
 extern "C" int spg_pedersen_chain_batch(spg_ctx* ctx, const uint64_t* elems, size_t chain_len, uint64_t* out,
                                         uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && elems && out && status, "spg_pedersen_chain_batch: null");
   SPG_ARG(chain_len >= 1 && chain_len <= 1024, "spg_pedersen_chain_batch: chain_len");
   SPG_CUDA(cudaSetDevice(ctx->device));
@@ -166,6 +167,7 @@ extern "C" int spg_pedersen_chain_batch(spg_ctx* ctx, const uint64_t* elems, siz
 
 extern "C" int spg_pedersen_hash2_batch(spg_ctx* ctx, const uint64_t* x, const uint64_t* y, uint64_t* out,
                                         uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && x && y && out && status, "spg_pedersen_hash2_batch: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
@@ -194,6 +196,7 @@ extern "C" int spg_pedersen_hash2_batch(spg_ctx* ctx, const uint64_t* x, const u
 
 extern "C" int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, const uint8_t* y, uint8_t* out,
                                              uint8_t* status, size_t n) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && x && y && out && status, "spg_pedersen_hash2_batch_be32: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
@@ -223,6 +226,7 @@ extern "C" int spg_pedersen_hash2_batch_be32(spg_ctx* ctx, const uint8_t* x, con
 // kernel with chain_len = 2 applied to the previous level in place of a pair list (children are adjacent).
 extern "C" int spg_pedersen_merkle_tree(spg_ctx* ctx, const uint64_t* leaves, size_t n_leaves, uint64_t* root_out,
                                         uint64_t* nodes_out, uint8_t* status_out, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && leaves && root_out && status_out, "spg_pedersen_merkle_tree: null");
   SPG_ARG(n_leaves >= 2 && (n_leaves & (n_leaves - 1)) == 0, "spg_pedersen_merkle_tree: n_leaves must be a power of two >= 2");
   SPG_CUDA(cudaSetDevice(ctx->device));
@@ -266,6 +270,7 @@ extern "C" int spg_pedersen_merkle_tree(spg_ctx* ctx, const uint64_t* leaves, si
 // pedersen_hash_as_point (signature.py:300-318): both coordinates of the hash point of 1 or 2 elements per item.
 extern "C" int spg_pedersen_hash_point_batch(spg_ctx* ctx, const uint64_t* elems, size_t n_elems, uint64_t* out_x, uint64_t* out_y,
                                              uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && elems && out_x && out_y && status, "spg_pedersen_hash_point_batch: null");
   SPG_ARG(n_elems == 1 || n_elems == 2, "spg_pedersen_hash_point_batch: the constant-point table covers one or two elements");
   SPG_ARG(!(flags & SPG_DEVICE_PTRS), "spg_pedersen_hash_point_batch: host pointers only");

@@ -113,6 +113,7 @@ int spg_ecdsa_verify_device(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r
 extern "C" int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
                                       const uint64_t* pub_x, const uint64_t* pub_y_or_null, uint8_t* status, size_t n,
                                       int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && msg && r && s && pub_x && status, "spg_ecdsa_verify_batch: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
@@ -146,6 +147,7 @@ extern "C" int spg_ecdsa_verify_batch(spg_ctx* ctx, const uint64_t* msg, const u
 
 extern "C" int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv, uint64_t* pub_x, uint64_t* pub_y_or_null,
                                               uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && priv && pub_x && status, "spg_private_to_stark_key_batch: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
@@ -167,6 +169,10 @@ extern "C" int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv
     SPG_CUDA(cudaMemcpyAsync(pub_x, dx, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     if (pub_y_or_null) SPG_CUDA(cudaMemcpyAsync(pub_y_or_null, dy, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+    // the staging copies of the private keys and seeds go back to the context's buffer pool: scrub them first so that
+    // key material does not outlive the call in recycled device memory
+    SPG_CUDA(cudaMemsetAsync(bp.p, 0, n * 32, ctx->stream));
+    if (bseed.p) SPG_CUDA(cudaMemsetAsync(bseed.p, 0, n * 8, ctx->stream));
   }
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
@@ -261,6 +267,10 @@ static int run_simple(spg_ctx* ctx, const uint64_t* const* ins, const size_t* in
   if (!(flags & SPG_DEVICE_PTRS)) {
     SPG_CUDA(cudaMemcpyAsync(out, dout, n * out_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+    // the staging copies of the private keys and seeds go back to the context's buffer pool: scrub them first so that
+    // key material does not outlive the call in recycled device memory
+    SPG_CUDA(cudaMemsetAsync(bp.p, 0, n * 32, ctx->stream));
+    if (bseed.p) SPG_CUDA(cudaMemsetAsync(bseed.p, 0, n * 8, ctx->stream));
   }
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
@@ -268,6 +278,7 @@ static int run_simple(spg_ctx* ctx, const uint64_t* const* ins, const size_t* in
 }
 
 extern "C" int spg_get_y_coordinate_batch(spg_ctx* ctx, const uint64_t* x, uint64_t* y, uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && x && y && status, "spg_get_y_coordinate_batch: null");
   if (n == 0) return SPG_OK;
   const uint64_t* ins[1] = {x};
@@ -279,6 +290,7 @@ extern "C" int spg_get_y_coordinate_batch(spg_ctx* ctx, const uint64_t* x, uint6
 
 extern "C" int spg_mimic_ec_mult_air_batch(spg_ctx* ctx, const uint64_t* m, const uint64_t* point_xy, const uint64_t* shift_xy,
                                            uint64_t* out_xy, uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && m && point_xy && shift_xy && out_xy && status, "spg_mimic_ec_mult_air_batch: null");
   if (n == 0) return SPG_OK;
   const uint64_t* ins[3] = {m, point_xy, shift_xy};
@@ -309,6 +321,7 @@ __global__ void __launch_bounds__(64) k_ecdsa_sign(const uint64_t* __restrict__ 
 
 extern "C" int spg_sign_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t* priv, const uint64_t* seed_or_null,
                               uint64_t* r, uint64_t* s, uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && msg && priv && r && s && status, "spg_sign_batch: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
@@ -336,6 +349,10 @@ extern "C" int spg_sign_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t*
     SPG_CUDA(cudaMemcpyAsync(r, dr, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaMemcpyAsync(s, ds, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+    // the staging copies of the private keys and seeds go back to the context's buffer pool: scrub them first so that
+    // key material does not outlive the call in recycled device memory
+    SPG_CUDA(cudaMemsetAsync(bp.p, 0, n * 32, ctx->stream));
+    if (bseed.p) SPG_CUDA(cudaMemsetAsync(bseed.p, 0, n * 8, ctx->stream));
   }
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;

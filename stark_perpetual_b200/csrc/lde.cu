@@ -135,6 +135,7 @@ static int finish(spg_ctx* ctx, int flags) {
 
 extern "C" int spg_lde_coeffs(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size_t n_cols,
                               const uint64_t* coset_offset, uint64_t* coeffs, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && trace && coeffs, "spg_lde_coeffs: null");
   SPG_ARG(flags & SPG_DEVICE_PTRS, "spg_lde_coeffs: device pointers only");
   SPG_ARG(log_n <= SPG_UNI_LOG, "spg_lde_coeffs: log_n");
@@ -148,6 +149,7 @@ extern "C" int spg_lde_coeffs(spg_ctx* ctx, const uint64_t* trace, unsigned log_
 
 extern "C" int spg_lde_cosets(spg_ctx* ctx, const uint64_t* coeffs, unsigned log_n, size_t n_cols,
                               unsigned log_blowup, size_t coset_begin, size_t coset_count, uint64_t* out, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && coeffs && out, "spg_lde_cosets: null");
   SPG_ARG(flags & SPG_DEVICE_PTRS, "spg_lde_cosets: device pointers only");
   SPG_CUDA(cudaSetDevice(ctx->device));
@@ -160,6 +162,7 @@ extern "C" int spg_lde_cosets(spg_ctx* ctx, const uint64_t* coeffs, unsigned log
 
 extern "C" int spg_lde(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, size_t n_cols, unsigned log_blowup,
                        const uint64_t* coset_offset, uint64_t* out, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && trace && out, "spg_lde: null");
   SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG && log_blowup <= 6, "spg_lde: size");
   SPG_CUDA(cudaSetDevice(ctx->device));

@@ -150,6 +150,7 @@ int spg_merkle_open_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows
 // ------------------------------------------------------------------ C-ABI
 extern "C" int spg_merkle_commit(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, uint8_t* root32,
                                  uint8_t* tree_out, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && table && root32, "spg_merkle_commit: null");
   SPG_ARG(n_cols >= 1 && n_cols <= 4096, "spg_merkle_commit: n_cols");
   SPG_ARG(rows >= 8 && (rows & (rows - 1)) == 0, "spg_merkle_commit: rows must be a power of two >= 8");

@@ -139,6 +139,7 @@ __global__ void k_fill(Fp* p, Fp v, size_t n) {
 
 extern "C" int spg_ntt(spg_ctx* ctx, uint64_t* data, unsigned log_n, size_t batch, int inverse, int order,
                        int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && data, "spg_ntt: null");
   SPG_ARG(order >= 0 && order <= 2, "spg_ntt: order");
   SPG_ARG(log_n <= 26, "spg_ntt: log_n");

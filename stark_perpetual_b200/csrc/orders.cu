@@ -99,6 +99,7 @@ static int stage_orders(spg_ctx* ctx, const spg_limit_orders* o, size_t n, int f
 
 extern "C" int spg_limit_order_msg_batch(spg_ctx* ctx, const spg_limit_orders* orders, uint64_t* msg_out, uint8_t* status,
                                          size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && orders && msg_out && status, "spg_limit_order_msg_batch: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
@@ -130,6 +131,7 @@ extern "C" int spg_limit_order_msg_batch(spg_ctx* ctx, const spg_limit_orders* o
 
 extern "C" int spg_limit_order_verify_batch(spg_ctx* ctx, const spg_limit_orders* orders, const uint64_t* r, const uint64_t* s,
                                             const uint64_t* pub_x, uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && orders && r && s && pub_x && status, "spg_limit_order_verify_batch: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (n == 0) return SPG_OK;
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(128) k_pack_messages(int kind, MsgFieldsDev f,
 
 extern "C" int spg_message_hash_batch(spg_ctx* ctx, int kind, const spg_message_fields* fields, uint64_t* msg_out,
                                       uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && fields && msg_out && status, "spg_message_hash_batch: null");
   const int len = spg_msg_chain_len(kind);
   SPG_ARG(len != 0, "spg_message_hash_batch: unknown message kind");

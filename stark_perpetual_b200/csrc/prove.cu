@@ -338,6 +338,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
 // ------------------------------------------------------------------ C-ABI
 extern "C" int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
                          unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && trace && x0 && proof_len, "spg_prove: null");
   SPG_ARG(log_n >= 9 && log_n <= 23, "spg_prove: log_n must be in [9, 23]");
   SPG_CUDA(cudaSetDevice(ctx->device));
@@ -367,6 +368,7 @@ extern "C" int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, un
 
 extern "C" int spg_pedersen_chain_trace(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* x0,
                                         const uint64_t* ys, uint64_t* trace_out, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && x0 && ys && trace_out, "spg_pedersen_chain_trace: null");
   SPG_ARG(log_n >= 9 && log_n <= 23 && 9 + chain_log <= log_n, "spg_pedersen_chain_trace: size");
   SPG_CUDA(cudaSetDevice(ctx->device));
@@ -393,6 +395,7 @@ extern "C" int spg_pedersen_chain_trace(spg_ctx* ctx, unsigned log_n, unsigned c
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
   if (st & 1) { ctx->err = "spg_pedersen_chain_trace: an input is >= p"; return SPG_E_ARG; }
   if (st & 2) { ctx->err = "spg_pedersen_chain_trace: Unhashable input."; return SPG_E_ARG; }
+  if (st & 4) { ctx->err = "spg_pedersen_chain_trace: a hash input is >= 2^251 (outside the AIR's canonical 251-bit range)"; return SPG_E_ARG; }
   return SPG_OK;
 }
 
@@ -400,6 +403,7 @@ extern "C" int spg_pedersen_chain_trace(spg_ctx* ctx, unsigned log_n, unsigned c
 // trace [25][N] canonical -> cp [4][N] canonical;  alpha canonical.
 extern "C" int spg_air_eval(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
                             const uint64_t* outs, const uint64_t* alpha, uint64_t* cp_out, int flags) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && trace && x0 && outs && alpha && cp_out, "spg_air_eval: null");
   SPG_ARG(log_n >= 9 && log_n <= 23 && 9 + chain_log <= log_n, "spg_air_eval: size");
   SPG_ARG(!(flags & SPG_DEVICE_PTRS), "spg_air_eval: host pointers only");

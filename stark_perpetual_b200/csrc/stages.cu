@@ -11,6 +11,7 @@ static Fp gen_mont() { uint64_t three[4] = {3, 0, 0, 0}; return spg_host_from_u6
 
 extern "C" int spg_stage_merkle(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, int n_cosets,
                                 uint8_t* tree_out) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && table && tree_out, "spg_stage_merkle: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   return spg_merkle_build_device(ctx, (const Fp*)table, (int)n_cols, rows, (uint32_t*)tree_out, n_cosets);
@@ -19,6 +20,7 @@ extern "C" int spg_stage_merkle(spg_ctx* ctx, const uint64_t* table, size_t n_co
 extern "C" int spg_stage_air(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* t_lde, int first_coset,
                              int jj0, int n_even, const uint64_t* x0, const uint64_t* outs, const uint64_t* alpha,
                              uint64_t* cp_out) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && t_lde && x0 && outs && alpha && cp_out, "spg_stage_air: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   AirPublic pub;
@@ -31,6 +33,7 @@ extern "C" int spg_stage_air(spg_ctx* ctx, unsigned log_n, unsigned chain_log, c
 }
 
 extern "C" int spg_stage_cp_split(spg_ctx* ctx, unsigned log_n, const uint64_t* cp, int jj0, int n_even, uint64_t* hev) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && cp && hev, "spg_stage_cp_split: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   return spg_cp_split_device(ctx, log_n, (const Fp*)cp, (Fp*)hev, jj0, n_even);
@@ -40,6 +43,7 @@ extern "C" int spg_stage_cp_split(spg_ctx* ctx, unsigned log_n, const uint64_t* 
 // canonical; out: [n_items][4] canonical.  Evaluates column k at pts[pt_idx[k]] / g.
 extern "C" int spg_stage_poly_eval(spg_ctx* ctx, unsigned log_n, const uint64_t* const* cols, const int* pt_idx,
                                    int n_items, const uint64_t* pts, int n_pts, uint64_t* out) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && cols && pt_idx && pts && out && n_items > 0 && n_items <= 256 && n_pts > 0 && n_pts <= 16, "spg_stage_poly_eval");
   SPG_CUDA(cudaSetDevice(ctx->device));
   const Fp ginv = fp_inv(gen_mont());
@@ -55,6 +59,7 @@ extern "C" int spg_stage_poly_eval(spg_ctx* ctx, unsigned log_n, const uint64_t*
 extern "C" int spg_stage_deep(spg_ctx* ctx, unsigned log_n, const uint64_t* t_lde, const uint64_t* h_lde, int first_coset,
                               int n_cosets, const uint64_t* z, const uint64_t* gamma, const uint64_t* oods,
                               uint64_t* inv_scratch, uint64_t* out) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && t_lde && h_lde && z && gamma && oods && inv_scratch && out, "spg_stage_deep: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
   const int C = SPG_AIR_COLS;
@@ -83,6 +88,7 @@ extern "C" int spg_stage_deep(spg_ctx* ctx, unsigned log_n, const uint64_t* t_ld
 // fold layer `layer_index` (0 = the DEEP quotient, rows = 2^log_rows per coset) by 8 with challenge beta
 extern "C" int spg_stage_fri_fold(spg_ctx* ctx, const uint64_t* in, unsigned log_rows, int first_coset, int n_cosets,
                                   const uint64_t* beta, int layer_index, uint64_t* out) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && in && beta && out && layer_index >= 0 && layer_index < 16, "spg_stage_fri_fold");
   SPG_CUDA(cudaSetDevice(ctx->device));
   Fp g_l = gen_mont();
@@ -95,6 +101,7 @@ extern "C" int spg_stage_fri_fold(spg_ctx* ctx, const uint64_t* in, unsigned log
 // paths_out [count][levels 32] bytes with levels = log2(n_cosets rows / 8)   (host buffers)
 extern "C" int spg_stage_open(spg_ctx* ctx, const uint64_t* table, size_t n_cols, size_t rows, int n_cosets,
                               const uint8_t* tree, const uint32_t* idx, int count, uint8_t* leaves_out, uint8_t* paths_out) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && table && tree && idx && leaves_out && paths_out && count >= 0, "spg_stage_open");
   SPG_CUDA(cudaSetDevice(ctx->device));
   if (count == 0) return SPG_OK;
@@ -119,6 +126,7 @@ extern "C" int spg_stage_open(spg_ctx* ctx, const uint64_t* table, size_t n_cols
 // canonical.  SPG_E_PROOF when the trace does not satisfy the AIR.
 extern "C" int spg_stage_check_oods(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const uint64_t* x0, const uint64_t* outs,
                                     const uint64_t* alpha, const uint64_t* z, const uint64_t* oods) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && x0 && outs && alpha && z && oods, "spg_stage_check_oods: null");
   const int C = SPG_AIR_COLS;
   AirPublic pub;
@@ -139,6 +147,7 @@ extern "C" int spg_stage_check_oods(spg_ctx* ctx, unsigned log_n, unsigned chain
 // coset-major.  Writes the 2^log_rows_last proof coefficients (32 bytes each, proof serialisation) to coeffs_out;
 // SPG_E_PROOF when the layer is not of low degree.
 extern "C" int spg_stage_last_layer(spg_ctx* ctx, const uint64_t* vals, unsigned log_rows_last, int n_folds, uint8_t* coeffs_out) {
+  SPG_LOCK(ctx);
   SPG_ARG(ctx && vals && coeffs_out && log_rows_last <= 6 && n_folds >= 0 && n_folds < 16, "spg_stage_last_layer");
   const size_t n_last = (size_t)1 << log_rows_last;
   std::vector<Fp> v(8 * n_last), coeffs;

@@ -93,7 +93,8 @@ def composition_at(log_n, chain_log, x0, outs, alpha_pows, z, tz, tzw, const_poi
     z_pad = 1
     for k in range(252, 256):
         z_pad = z_pad * (u256 - pow(w256, k, P)) % P
-    iz = [(u256 - pow(w256, 255, P)) * iz_all % P, z_pad * iz_all % P, inv(z_pad), inv(u512 - pow(w512, 255, P)),
+    z_zero = z_pad * (u256 - pow(w256, 251, P)) % P      # c6 (M = 0) from row 251 on: canonical 251-bit unpacking
+    iz = [(u256 - pow(w256, 255, P)) * iz_all % P, z_pad * iz_all % P, inv(z_zero), inv(u512 - pow(w512, 255, P)),
           (useg - inv(wseg)) * inv(u512 - pow(w512, 511, P)) % P, inv(u512 - 1), inv(useg - 1),
           inv(z - inv(root_of_unity(log_n)))]
     # periodic columns at z (Lagrange over the 512-th roots of unity)

@@ -34,7 +34,7 @@ def main():
     proof = prover.prove_sharded(be, prover.TorchComm(rank, world), block, log_n, chain_log, x0, outs, nq)
     if rank == 0:
         want = stark.prove_trace(log_n, chain_log, x0, outs, cols, n_queries=nq)
-        stark.verify(proof)
+        stark.verify(proof, min_queries=nq)
         with open(out_path, "w") as f:
             f.write("OK" if proof == want else "MISMATCH %d %d" % (len(proof), len(want)))
     dist.destroy_process_group()

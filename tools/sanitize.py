@@ -35,7 +35,7 @@ def main():
     ys = [[rng.randrange(P) for _ in range(2)] for _ in range(5)]
     pv = Prover(ctx)
     proof = pv.prove_host(pv.witness(10, 1, x0, ys), 10, 1, x0, n_queries=8)
-    ostark.verify(proof)
+    ostark.verify(proof, min_queries=8)
     out, st = ctx.pedersen_hash2(ints_to_limbs([1, 2]), ints_to_limbs([3, 4]))
     assert limbs_to_ints(out) == [pedersen_hash(1, 3), pedersen_hash(2, 4)]
     print("sanitize workload OK")
