@@ -169,10 +169,9 @@ extern "C" int spg_private_to_stark_key_batch(spg_ctx* ctx, const uint64_t* priv
     SPG_CUDA(cudaMemcpyAsync(pub_x, dx, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     if (pub_y_or_null) SPG_CUDA(cudaMemcpyAsync(pub_y_or_null, dy, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
-    // the staging copies of the private keys and seeds go back to the context's buffer pool: scrub them first so that
-    // key material does not outlive the call in recycled device memory
+    // the staging copy of the private keys goes back to the context's buffer pool: scrub it first so that key material
+    // does not outlive the call in recycled device memory
     SPG_CUDA(cudaMemsetAsync(bp.p, 0, n * 32, ctx->stream));
-    if (bseed.p) SPG_CUDA(cudaMemsetAsync(bseed.p, 0, n * 8, ctx->stream));
   }
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
@@ -267,10 +266,6 @@ static int run_simple(spg_ctx* ctx, const uint64_t* const* ins, const size_t* in
   if (!(flags & SPG_DEVICE_PTRS)) {
     SPG_CUDA(cudaMemcpyAsync(out, dout, n * out_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
-    // the staging copies of the private keys and seeds go back to the context's buffer pool: scrub them first so that
-    // key material does not outlive the call in recycled device memory
-    SPG_CUDA(cudaMemsetAsync(bp.p, 0, n * 32, ctx->stream));
-    if (bseed.p) SPG_CUDA(cudaMemsetAsync(bseed.p, 0, n * 8, ctx->stream));
   }
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
