@@ -16,6 +16,7 @@ host-buffer C-ABI call spg_prove (H2D of the 840 MB trace and D2H of the proof i
 reference repository itself contains no prover to time, so kind = "port".
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -365,6 +366,7 @@ def main():
                                    (1 + 8) * 29 * n * 32 / 1e9),
                                parallelism=pv.parallelism()),
                 "proof_gen_s": ms_per_step * 1e-3, "proof_bytes": len(proof) if proof else None,
+                "proof_sha256": hashlib.sha256(proof).hexdigest() if proof else None,
                 "stage_ms": ({s: round(float(v), 4) for s, v in zip(STAGES, stage_ms)} if world == 1 else
                              {k: v[0] for k, v in sharded_stages.items()}),
                 "stage_host_ms": None if world == 1 else {k: v[1] for k, v in sharded_stages.items()},

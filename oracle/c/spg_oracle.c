@@ -198,3 +198,16 @@ int spgo_num_threads(void) {
   return 1;
 #endif
 }
+
+/* Horner evaluation of `batch` polynomials (canonical coefficients, natural order, n each) at one canonical point each:
+ * out[b] = sum_k coef[b][k] * pt[b]^k.  Used by the 2^20 parity tests for the out-of-domain values. */
+void spgo_poly_eval(const uint64_t* coef, size_t n, const uint64_t* pts, size_t batch, uint64_t* out) {
+#pragma omp parallel for schedule(dynamic)
+  for (size_t b = 0; b < batch; b++) {
+    fe x, acc = {{0, 0, 0, 0}};
+    memcpy(&x, pts + 4 * b, 32); to_mont(&x, &x);
+    const fe* c = (const fe*)(coef + 4 * n * b);
+    for (size_t k = n; k-- > 0;) { fe_mul(&acc, &acc, &x); fe_add(&acc, &acc, &c[k]); }   /* canonical * Mont / R = canonical */
+    memcpy(out + 4 * b, &acc, 32);
+  }
+}

@@ -62,3 +62,15 @@ def lde(trace, log_n, n_cols, log_blowup, offset=3):
     g = np.frombuffer(int(offset).to_bytes(32, "little"), dtype="<u8").copy()
     lib().spgo_lde(_p(tr), C.c_uint(log_n), C.c_size_t(n_cols), C.c_uint(log_blowup), _p(g), _p(out))
     return out
+
+
+def poly_eval(coefs, n, points):
+    """coefs (batch * n, 4) canonical natural-order coefficients, points: list of ints (one per polynomial) -> list of ints"""
+    cf = np.ascontiguousarray(coefs, dtype=np.uint64).reshape(-1, 4)
+    batch = cf.shape[0] // n
+    assert len(points) == batch
+    pts = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in points), dtype="<u8").reshape(-1, 4).copy()
+    out = np.empty((batch, 4), dtype=np.uint64)
+    lib().spgo_poly_eval(_p(cf), C.c_size_t(n), _p(pts), C.c_size_t(batch), _p(out))
+    raw = out.tobytes()
+    return [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(batch)]

@@ -366,9 +366,12 @@ class TorchComm:
 
 
 # ------------------------------------------------------------------ the sharded prover
-def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_queries=30, check=True):
+def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_queries=30, check=True, probe=None):
     """trace_cols_local: this rank's block of trace columns, tensor [my_cols][N][4] canonical (columns
-    [rank*per, ...) with per = ceil(25/world)).  Returns the proof bytes on every rank."""
+    [rank*per, ...) with per = ceil(25/world)).  Returns the proof bytes on every rank.
+    probe (tests): callable(stage_name, **tensors_and_challenges) invoked after every stage with the stage's device
+    tables and the Fiat-Shamir challenges, so that parity tests can compare sampled values of the very run that
+    produced the proof."""
     rank, world = comm.rank, comm.world
     assert BLOWUP % world == 0
     n, cs = 1 << log_n, BLOWUP // world
@@ -383,6 +386,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
             + b"".join(ser(v) for v in x0) + b"".join(ser(v) for v in outs))
     ch = Channel(seed)
     tick = getattr(be, "tick", lambda name: None)
+    probe = probe or (lambda name, **kw: None)
     if hasattr(be, "reset_ticks"):
         be.reset_ticks()
     proof = [b"SPGP", (1).to_bytes(4, "little"), log_n.to_bytes(4, "little"), chain_log.to_bytes(4, "little"),
@@ -405,6 +409,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
     tick("lde_trace")
     t_lde = be.felts(cs, N_COLS, n)
     be.lde_cosets(coefs, log_n, N_COLS, first, cs, t_lde)
+    probe("lde_trace", coefs=coefs, t_lde=t_lde)
     tick("merkle_trace")
     tree_t, top_t = commit(t_lde, N_COLS, n)
     root_t = top_t[-1][0]
@@ -418,6 +423,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
         cp = be.felts(len(even), n)
         be.air(t_lde, log_n, chain_log, first, even[0], len(even), x0, outs, alpha, cp)
         be.cp_split(cp, log_n, even[0], len(even), hev)
+        probe("air_composition", alpha=alpha, cp=cp, even=even)
     hv = hev.view(4, n // 4, 4, 4)
     tick("chunk_exchange")
     if world > 1:
@@ -430,6 +436,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
     be.lde_coeffs(hev, log_n, 4, h_coef, offset=pow(GEN, -3, P), mont=False)
     h_lde = be.felts(cs, 4, n)
     be.lde_cosets(h_coef, log_n, 4, first, cs, h_lde)
+    probe("lde_chunks", hev=hev, h_coef=h_coef, h_lde=h_lde)
     tick("merkle_chunks")
     tree_h, top_h = commit(h_lde, 4, n)
     root_h = top_h[-1][0]
@@ -453,6 +460,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
             oods[k] = int.from_bytes(part[32 * i:32 * i + 32], "little")
     if check:
         be.check_oods(log_n, chain_log, x0, outs, alpha, z, oods)
+    probe("oods_eval", z=z, oods=oods)
     ob = b"".join(ser(v) for v in oods)
     ch.absorb(ob)
     # 4. DEEP quotient on the local cosets
@@ -460,6 +468,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
     gamma = ch.draw_felt()
     layers, trees = [be.felts(cs, n)], [None]
     be.deep(t_lde, h_lde, log_n, first, cs, z, gamma, oods, layers[0])
+    probe("deep_quotient", gamma=gamma, layer0=layers[0])
     # 5. FRI.  Only the first fold works on sharded data: its output (N/8 rows per coset, 32 MB at 2^20) is
     # all-gathered once, and every rank then folds and commits the remaining, geometrically shrinking layers
     # locally -- no further collective or root exchange on the latency-bound tail of the protocol.
@@ -480,6 +489,7 @@ def prove_sharded(be, comm, trace_cols_local, log_n, chain_log, x0, outs, n_quer
         else:
             nxt = be.felts(BLOWUP, rows_l)
             be.fri_fold(layers[l - 1], log_rows[l - 1], 0, BLOWUP, beta, l - 1, nxt)
+        probe("fri", l=l, beta=beta, prev=layers[l - 1], layer=nxt)
         tree = be.merkle(nxt, 1, rows_l, BLOWUP)
         root = be.root(tree).cpu().numpy().tobytes()
         layers.append(nxt); trees.append(tree); full_tops.append([[root]])
@@ -575,8 +585,8 @@ class Prover:
         block = self.be.upload(tr[c0:c1]) if c1 > c0 else self.be.felts(1, n)
         return block, outs
 
-    def prove_sharded_device(self, cols_local, log_n, chain_log, x0, outs, n_queries=30):
-        return prove_sharded(self.be, self.comm, cols_local, log_n, chain_log, x0, outs, n_queries)
+    def prove_sharded_device(self, cols_local, log_n, chain_log, x0, outs, n_queries=30, probe=None):
+        return prove_sharded(self.be, self.comm, cols_local, log_n, chain_log, x0, outs, n_queries, probe=probe)
 
     def parallelism(self):
         if self.world == 1:

@@ -57,3 +57,29 @@ def test_verify_enforces_query_floor(honest):
     with pytest.raises(stark.ProofError, match="queries"):
         stark.verify(weak)
     assert stark.verify(weak, min_queries=2)["n_queries"] == 2
+
+
+def test_stage_probe_on_cpu_backend():
+    """The sampled-point stage checker the 2^20 GPU parity test uses (tests/stage_probe.py), exercised here on the
+    oracle-backed CPU stage backend: it must see every stage and agree with it."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from cpu_stage_backend import CpuBackend
+    from stage_probe import StageChecker
+    from stark_perpetual_b200 import prover
+    from stark_perpetual_b200._lib import ints_to_limbs
+    log_n, chain_log = 9, 0
+    x0, ys = _inputs(11)
+    cols, outs = stark.gen_trace(log_n, chain_log, x0, ys)
+    tr = ints_to_limbs([v for c in cols for v in c])
+    be = CpuBackend()
+    chk = StageChecker(be, tr, log_n, chain_log, x0, outs, n_groups=24)
+    block = be.upload(tr.reshape(25, 1 << log_n, 4))
+    proof = prover.prove_sharded(be, prover.TorchComm(0, 1), block, log_n, chain_log, x0, outs, 30, probe=chk)
+    chk.assert_complete()
+    assert proof == stark.prove_trace(log_n, chain_log, x0, outs, cols, n_queries=30)
+    # the checker must notice a wrong value: corrupt the sample's expectation and replay one stage
+    pt = chk.points[0]
+    chk.h_vals[pt][0] ^= 1
+    with pytest.raises(AssertionError):
+        chk.on_deep_quotient(gamma=5, layer0=be.felts(8, 1 << log_n))
