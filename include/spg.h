@@ -10,6 +10,9 @@
  *     in `flags`, in which case they are device pointers on the context's GPU;
  *   - every function returns 0 or a negative SPG_E* code and never throws; spg_last_error()
  *     gives the message.  There is NO CPU fallback: without a CUDA device spg_create fails.
+ *   - threading: every entry point locks its context for the duration of the call, so a context may be shared by
+ *     threads (calls queue up); distinct contexts run concurrently.  spg_last_error / spg_last_kernel_ms /
+ *     spg_stage_ms report the most recent call on the context, whichever thread made it.
  *   - per-element outcomes of batched calls are reported in `status` arrays (one byte each) so
  *     the Python layer can raise exactly the exception the reference raises.
  */
@@ -126,6 +129,19 @@ int spg_get_y_coordinate_batch(spg_ctx* ctx, const uint64_t* x, uint64_t* y, uin
  * a field element. */
 int spg_mimic_ec_mult_air_batch(spg_ctx* ctx, const uint64_t* m, const uint64_t* point_xy, const uint64_t* shift_xy,
                                 uint64_t* out_xy, uint8_t* status, size_t n, int flags);
+
+/* ---- math_utils.py as batched device operations -----------------------------------
+ * Replaces src/starkware/crypto/signature/math_utils.py:59-68 ec_add (op 0), :79-88 ec_double (op 1, alpha = 1) and
+ * :91-100 ec_mult (op 2) over the STARK prime.  a_xy, out_xy: [n][8] canonical (x, y); b: [n][8] second point (op 0),
+ * unused (op 1), [n][4] scalar m (op 2).  ec_mult follows the reference's recursion: every doubling 2^k P up to the top
+ * bit of m first, then the additions from the highest set bit down, so the inputs on which an assertion fires are the
+ * reference's own.  status[i]: 0 ok; 1 the reference raises AssertionError (x1 == x2 in ec_add, :64; y == 0 in
+ * ec_double, :84); 2 a coordinate is not a field element; 3 m == 0 (the reference recurses forever).  Host pointers. */
+int spg_ec_op_batch(spg_ctx* ctx, int op, const uint64_t* a_xy, const uint64_t* b, uint64_t* out_xy, uint8_t* status,
+                    size_t n, int flags);
+/* math_utils.py:36-47 is_quad_residue / sqrt_mod over the STARK prime: y[i] = the SMALLER square root of a[i].
+ * status[i]: 0 ok (a is a quadratic residue, 0 included), 1 non-residue, 2 a >= p. */
+int spg_field_sqrt_batch(spg_ctx* ctx, const uint64_t* a, uint64_t* y, uint8_t* status, size_t n, int flags);
 
 /* ---- perpetual limit orders (BASELINE.json configs[4]) ------------------------------
  * Replaces src/services/perpetual/public/perpetual_messages.py:212-286 get_limit_order_msg: field packing and the 4-deep

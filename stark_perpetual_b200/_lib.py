@@ -62,6 +62,8 @@ def _load():
             "spg_get_y_coordinate_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_mimic_ec_mult_air_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_pedersen_merkle_tree": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_int]),
+            "spg_ec_op_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_field_sqrt_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_limit_order_msg_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_message_hash_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_limit_order_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
@@ -227,6 +229,24 @@ class Context:
         out, st = np.empty_like(p), np.empty(m.shape[0], np.uint8)
         self._check(self._lib.spg_mimic_ec_mult_air_batch(self._h, _ptr(m), _ptr(p), _ptr(s), _ptr(out), _ptr(st), m.shape[0], 0))
         return out, st
+
+    def ec_op(self, op, a_xy, b=None):
+        """math_utils.py:59-100 on the device.  op 0: ec_add(a, b) with b (n, 8); op 1: ec_double(a); op 2: ec_mult(m, a) with
+        b = m (n, 4).  a_xy (n, 8) canonical (x, y).  Returns (out_xy (n, 8), status): 0 ok, 1 the reference's assertion
+        fails (equal x / y == 0), 2 a coordinate >= p, 3 m == 0."""
+        a = np.ascontiguousarray(a_xy, dtype=np.uint64).reshape(-1, 8)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.uint64).reshape(a.shape[0], -1)
+        out, st = np.empty_like(a), np.empty(a.shape[0], np.uint8)
+        self._check(self._lib.spg_ec_op_batch(self._h, op, _ptr(a), _ptr(bb) if bb is not None else None, _ptr(out), _ptr(st),
+                                              a.shape[0], 0))
+        return out, st
+
+    def field_sqrt(self, a):
+        """math_utils.py:36-47: (smaller square root (n, 4), status) with status 0 ok, 1 non-residue, 2 a >= p."""
+        x = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        y, st = np.empty_like(x), np.empty(x.shape[0], np.uint8)
+        self._check(self._lib.spg_field_sqrt_batch(self._h, _ptr(x), _ptr(y), _ptr(st), x.shape[0], 0))
+        return y, st
 
     def pedersen_merkle_tree(self, leaves, want_nodes=False):
         """leaves: (n, 4) canonical felts, n a power of two -> (root (4,), nodes (n - 1, 4) or None, status)."""

@@ -353,3 +353,87 @@ extern "C" int spg_sign_batch(spg_ctx* ctx, const uint64_t* msg, const uint64_t*
   float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
   return SPG_OK;
 }
+
+// ------------------------------------------------------------------ math_utils.py:59-100 as batched device ops
+// ec_add / ec_double / ec_mult with the reference's assertions reported as statuses.  ec_mult follows the reference's
+// recursion exactly -- all doublings 2^k P first (each asserting y != 0), then the additions from the highest set bit
+// down to the lowest, each asserting acc.x != (2^k P).x -- so the exceptional inputs are the reference's, not those of
+// some other addition chain.  The doubles a thread needs again are parked in a global scratch array [k][thread].
+__device__ __forceinline__ void store_canon(uint64_t* dst, const Fp& mont) {
+  const Fp c = fp_from_mont(mont);
+  uint4* o = reinterpret_cast<uint4*>(dst);
+  o[0] = make_uint4(c.v[0], c.v[1], c.v[2], c.v[3]);
+  o[1] = make_uint4(c.v[4], c.v[5], c.v[6], c.v[7]);
+}
+
+__global__ void __launch_bounds__(64) k_ec_op(int op, const uint64_t* __restrict__ a_xy, const uint64_t* __restrict__ b,
+                                              uint64_t* __restrict__ out_xy, uint8_t* __restrict__ status, size_t n,
+                                              JPoint* __restrict__ scratch, size_t stride) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t ax[8], ay[8], b0[8] = {0}, b1[8] = {0};
+  load8(a_xy + 8 * i, ax); load8(a_xy + 8 * i + 4, ay);
+  if (op == 0) { load8(b + 8 * i, b0); load8(b + 8 * i + 4, b1); }
+  else if (op == 2) load8(b + 4 * i, b0);
+  APoint R;
+  const int st = ec_op_one(op, ax, ay, b0, b1, scratch + i, stride, &R);
+  store_canon(out_xy + 8 * i, R.x); store_canon(out_xy + 8 * i + 4, R.y);
+  status[i] = (uint8_t)st;
+}
+
+extern "C" int spg_ec_op_batch(spg_ctx* ctx, int op, const uint64_t* a_xy, const uint64_t* b, uint64_t* out_xy,
+                               uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
+  SPG_ARG(ctx && a_xy && out_xy && status && op >= 0 && op <= 2, "spg_ec_op_batch: arguments");
+  SPG_ARG(op == 1 || b, "spg_ec_op_batch: second operand required");
+  SPG_ARG(!(flags & SPG_DEVICE_PTRS), "spg_ec_op_batch: host pointers only");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  const size_t chunk = 8192, b_words = op == 0 ? 8 : 4;
+  DevBuf da, db, dout, dst, dscr;
+  SPG_CUDA(da.alloc(ctx, chunk * 64)); SPG_CUDA(db.alloc(ctx, chunk * 64)); SPG_CUDA(dout.alloc(ctx, chunk * 64));
+  SPG_CUDA(dst.alloc(ctx, chunk));
+  if (op == 2) SPG_CUDA(dscr.alloc(ctx, 255 * chunk * sizeof(JPoint)));
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  for (size_t c0 = 0; c0 < n; c0 += chunk) {
+    const size_t nc = n - c0 < chunk ? n - c0 : chunk;
+    SPG_CUDA(cudaMemcpyAsync(da.p, a_xy + 8 * c0, nc * 64, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) SPG_CUDA(cudaMemcpyAsync(db.p, b + b_words * c0, nc * b_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_ec_op<<<(unsigned)((nc + 63) / 64), 64, 0, ctx->stream>>>(op, da.as<uint64_t>(), db.as<uint64_t>(), dout.as<uint64_t>(),
+                                                                dst.as<uint8_t>(), nc, dscr.as<JPoint>(), chunk);
+    SPG_LAUNCH_CHECK();
+    SPG_CUDA(cudaMemcpyAsync(out_xy + 8 * c0, dout.p, nc * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(status + c0, dst.p, nc, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}
+
+// math_utils.py:36-47 is_quad_residue / sqrt_mod over the STARK prime: y[i] = the smaller square root of a[i].
+// status: 0 ok, 1 not a quadratic residue, 2 a >= p.
+__global__ void __launch_bounds__(128) k_field_sqrt(const uint64_t* __restrict__ a, uint64_t* __restrict__ y,
+                                                    uint8_t* __restrict__ status, size_t n, EcdsaTables T) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t av[8];
+  load8(a + 4 * i, av);
+  Fp am, r = fp_zero();
+  uint8_t st = 0;
+  if (!canon_to_mont(av, &am)) st = 2;
+  else if (!fp_sqrt_min(am, T, &r)) { st = 1; r = fp_zero(); }
+  store_canon(y + 4 * i, r);
+  status[i] = st;
+}
+
+extern "C" int spg_field_sqrt_batch(spg_ctx* ctx, const uint64_t* a, uint64_t* y, uint8_t* status, size_t n, int flags) {
+  SPG_LOCK(ctx);
+  SPG_ARG(ctx && a && y && status, "spg_field_sqrt_batch: null");
+  if (n == 0) return SPG_OK;
+  const uint64_t* ins[1] = {a};
+  const size_t words[1] = {4};
+  return run_simple(ctx, ins, words, 1, y, 4, status, n, flags, [&](const uint64_t* const* d, uint64_t* o, uint8_t* st) {
+    k_field_sqrt<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d[0], o, st, n, make_tables(ctx, true));
+  });
+}

@@ -260,3 +260,60 @@ SPG_HD APoint gen_mult(const uint32_t (&k)[8], const EcdsaTables& T) {
   o.y = fp_mul(a.p.Y, fp_mul(zi2, zi));
   return o;
 }
+
+// ------------------------------------------------------------------ math_utils.py:59-100, one operation
+SPG_HD bool canon_to_mont(const uint32_t (&v)[8], Fp* mont) {
+  if (spg_canon_geq_p(v)) return false;
+  Fp c; for (int i = 0; i < 8; i++) c.v[i] = v[i];
+  *mont = fp_to_mont(c);
+  return true;
+}
+SPG_HD int u256_top_bit(const uint32_t (&m)[8]) {
+  for (int k = 7; k >= 0; k--) {
+    if (!m[k]) continue;
+    int b = 31;
+    while (!((m[k] >> b) & 1u)) b--;
+    return 32 * k + b;
+  }
+  return -1;
+}
+// op 0: R = ec_add((ax, ay), (b0, b1));  op 1: R = ec_double((ax, ay));  op 2: R = ec_mult(b0, (ax, ay)).
+// Inputs canonical, R Montgomery affine.  Returns 0 ok; 1 the reference's assertion fails (math_utils.py:64 x1 == x2,
+// :84 y == 0); 2 a coordinate >= p; 3 m == 0.  scratch: this thread's column of parked doubles, scratch[k * stride].
+SPG_HD int ec_op_one(int op, const uint32_t (&ax)[8], const uint32_t (&ay)[8], const uint32_t (&b0)[8], const uint32_t (&b1)[8],
+                     JPoint* scratch, size_t stride, APoint* R) {
+  R->x = fp_zero(); R->y = fp_zero();
+  APoint P;
+  if (!canon_to_mont(ax, &P.x) || !canon_to_mont(ay, &P.y)) return 2;
+  if (op == 0) {
+    APoint Q;
+    if (!canon_to_mont(b0, &Q.x) || !canon_to_mont(b1, &Q.y)) return 2;
+    if (fp_eq(P.x, Q.x)) return 1;                        // assert (x1 - x2) % p != 0
+    *R = ec_affine_add(P, Q);
+    return 0;
+  }
+  if (op == 1) {
+    if (fp_is_zero(P.y)) return 1;                        // assert y % p != 0
+    *R = ec_affine_double(P);
+    return 0;
+  }
+  // ec_mult(m, P): m == 1 -> P;  m even -> ec_mult(m / 2, ec_double(P));  m odd -> ec_add(ec_mult(m - 1, P), P).
+  // Unrolled: D_k = 2^k P for k up to the top bit (every doubling asserts y != 0), then acc = D_top and, from the
+  // highest set bit below the top one down to bit 0, acc = ec_add(acc, D_k) (asserting acc.x != D_k.x).
+  const int top = u256_top_bit(b0);
+  if (top < 0) return 3;
+  JPoint D; D.X = P.x; D.Y = P.y; D.Z = fp_one();
+  for (int k = 0; k < top; k++) {
+    if ((b0[k >> 5] >> (k & 31)) & 1u) scratch[(size_t)k * stride] = D;
+    if (fp_is_zero(D.Y)) return 1;
+    D = ec_jdouble_nocheck(D);
+  }
+  for (int k = top - 1; k >= 0; k--) {
+    if (!((b0[k >> 5] >> (k & 31)) & 1u)) continue;
+    const JPoint Q = scratch[(size_t)k * stride];
+    if (!jadd_checked(D, Q, &D)) return 1;
+  }
+  const Fp zi = fp_inv_chain(D.Z), zi2 = fp_sqr(zi);
+  R->x = fp_mul(D.X, zi2); R->y = fp_mul(D.Y, fp_mul(zi2, zi));
+  return 0;
+}

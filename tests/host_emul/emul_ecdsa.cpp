@@ -61,6 +61,33 @@ int main() {
              (unsigned long long)out[1], (unsigned long long)out[0]);
       continue;
     }
+    if (a[0][0] == 'E') {                       // E op ax ay b0 b1 -> "status x y"   (math_utils ec_add / ec_double / ec_mult)
+      char e[5][128];
+      for (int k = 0; k < 5; k++) if (scanf("%100s", e[k]) != 1) return 1;
+      uint32_t ax[8], ay[8], b0[8], b1[8];
+      parse_hex(e[1], ax); parse_hex(e[2], ay); parse_hex(e[3], b0); parse_hex(e[4], b1);
+      std::vector<JPoint> scratch(256);
+      APoint R;
+      const int st = ec_op_one(atoi(e[0]), ax, ay, b0, b1, scratch.data(), 1, &R);
+      uint64_t ox[4], oy[4];
+      fp_to_u64(fp_from_mont(R.x), ox); fp_to_u64(fp_from_mont(R.y), oy);
+      printf("%d %016llx%016llx%016llx%016llx %016llx%016llx%016llx%016llx\n", st, (unsigned long long)ox[3], (unsigned long long)ox[2],
+             (unsigned long long)ox[1], (unsigned long long)ox[0], (unsigned long long)oy[3], (unsigned long long)oy[2],
+             (unsigned long long)oy[1], (unsigned long long)oy[0]);
+      continue;
+    }
+    if (a[0][0] == 'Q') {                       // Q a -> "status y"   (math_utils sqrt_mod / is_quad_residue)
+      if (scanf("%100s", a[1]) != 1) break;
+      uint32_t av[8]; parse_hex(a[1], av);
+      Fp am, y = fp_zero();
+      int st = 0;
+      if (!canon_to_mont(av, &am)) st = 2;
+      else if (!fp_sqrt_min(am, T, &y)) { st = 1; y = fp_zero(); }
+      uint64_t oy[4]; fp_to_u64(fp_from_mont(y), oy);
+      printf("%d %016llx%016llx%016llx%016llx\n", st, (unsigned long long)oy[3], (unsigned long long)oy[2], (unsigned long long)oy[1],
+             (unsigned long long)oy[0]);
+      continue;
+    }
     if (a[0][0] == 'S') {
       for (int k = 1; k < 4; k++) if (scanf("%100s", a[k]) != 1) return 1;
       uint32_t m[8], d[8], r[8] = {0}, s[8] = {0};

@@ -223,3 +223,33 @@ def test_emulated_air_point_lazy_bounds_and_value():
     assert len(out) == len(want)
     for k, (o, w) in enumerate(zip(out, want)):
         assert int(o, 16) == w, k
+
+
+def test_emulated_math_utils_vs_reference_golden():
+    """csrc/ecdsa.cuh ec_op_one (ec_add / ec_double / ec_mult in the reference's evaluation order, with its assertions)
+    and fp_sqrt_min, run on the host against vectors generated by the reference's math_utils.py
+    (tests/golden/math_utils_golden.json: math_utils.py:36-100)."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "math_utils_golden.json")))
+    exe = _build("emul_ecdsa")
+    lines, want = [], []
+    for a, b, res in g["ec_add"]:
+        lines.append("E 0 %x %x %x %x" % (a[0], a[1], b[0], b[1])); want.append(res)
+    for a, res in g["ec_double"]:
+        lines.append("E 1 %x %x 0 0" % (a[0], a[1])); want.append(res)
+    for m, a, res in g["ec_mult"]:
+        lines.append("E 2 %x %x %x 0" % (a[0], a[1], m)); want.append(res)
+    for a, qr, root in g["sqrt_mod"]:
+        lines.append("Q %x" % a); want.append((qr, root))
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout.strip().split("\n")
+    assert len(out) == len(want)
+    for line, w, src in zip(out, want, lines):
+        f = line.split()
+        if isinstance(w, tuple):
+            assert (f[0] == "0") == w[0], src
+            if w[0]:
+                assert int(f[1], 16) == w[1], src
+        elif w == "AssertionError":
+            assert f[0] == "1", src
+        else:
+            assert f[0] == "0" and [int(f[1], 16), int(f[2], 16)] == list(w), src
