@@ -51,10 +51,11 @@ struct spg_ctx {
   struct PoolBlock { void* p; size_t size; bool in_use; };
   std::vector<PoolBlock> pool;
   // direct diagonal-twiddle tables of the coset transforms, per (log_n, log_blowup): [2^log_blowup][S][R] (see lde.cu)
-  struct DiagTables { int log_n, log_blowup; Fp* t; };
+  struct DiagTables { int log_n, log_blowup; Fp* t; Fp* t0; };   // t: [2^log_blowup][N] (strided pass), t0: [2^log_blowup][R]
   std::vector<DiagTables> diag_tables;
   // LDE scale tables cached per (log_n, offset, mont): lo[R] , hi[B]
-  struct LdeTables { int log_n; uint64_t offset[4]; int mont; Fp* lo; Fp* hi; };
+  // inv_diag: direct diagonal table [N] of the inverse transform's strided pass with hi[] folded in (two-pass sizes; else null)
+  struct LdeTables { int log_n; uint64_t offset[4]; int mont; Fp* lo; Fp* hi; Fp* inv_diag; };
   std::vector<LdeTables> lde_tables;
   // AIR tables cached per (log_n, chain_log)
   int air_log_n = -1, air_chain_log = -1;
@@ -172,11 +173,12 @@ int spg_from_mont_device(spg_ctx* ctx, Fp* data, size_t n);
 // ntt.cu
 int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
-                   const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table = nullptr);
+                   const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table = nullptr, const Fp* diag_table0 = nullptr);
 // ntt.cu: log2 of the shared-memory workspace (= the largest pass) the NTT kernels use for a 2^log_n transform
 int spg_ntt_tile_log_ws(unsigned log_n);
-// ntt.cu: fill a direct diagonal table for the second pass of a two-pass forward DIT with coset exponent coset_exp
-int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, unsigned long long coset_exp, Fp* table);
+// ntt.cu: fill the direct diagonal table of one pass of a two-pass transform (see ntt.cu)
+int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, int inverse, int dit, int pass_index, unsigned long long coset_exp,
+                             const Fp* row_factor, Fp* table);
 int spg_bitrev_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols);
 // lde.cu: device-resident LDE, trace [C][N] -> out [B][C][N]; coeffs (optional) receives the scaled
 // coefficient columns g^k c_k (bit-reversed order)

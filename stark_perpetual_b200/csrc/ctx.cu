@@ -92,8 +92,8 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
   if (ctx->device >= 0) cudaSetDevice(ctx->device);
   cudaFree(ctx->tw_fwd); cudaFree(ctx->tw_inv); cudaFree(ctx->uniA); cudaFree(ctx->uniB);
   cudaFree(ctx->const_points); cudaFree(ctx->gen_doubles); cudaFree(ctx->sqrt_tables);
-  for (auto& t : ctx->lde_tables) { cudaFree(t.lo); cudaFree(t.hi); }
-  for (auto& t : ctx->diag_tables) cudaFree(t.t);
+  for (auto& t : ctx->lde_tables) { cudaFree(t.lo); cudaFree(t.hi); cudaFree(t.inv_diag); }
+  for (auto& t : ctx->diag_tables) { cudaFree(t.t); cudaFree(t.t0); }
   cudaFree(ctx->air_izt); cudaFree(ctx->air_plde); cudaFree(ctx->air_ilast);
   for (void* p : ctx->owned) cudaFree(p);
   for (void* p : ctx->scratch_p) cudaFree(p);

@@ -12,11 +12,20 @@
 #include "common.h"
 #include "ntt.cuh"
 
+static bool two_pass(unsigned log_n) {
+  const unsigned ws = (unsigned)spg_ntt_tile_log_ws(log_n);
+  return log_n > ws && log_n <= 2 * ws;
+}
+
+// lo[r] (contiguous-pass row factor), hi[b] (per-tile factor) and, for two-pass sizes, inv_diag: the inverse transform's
+// inter-pass diagonal twiddle as a direct N-entry table with hi[] folded in -- the tile a value lands in is the row of
+// the strided pass it leaves, so the g^k / N scaling costs ONE multiplication per element (lo) instead of two, and the
+// diagonal twiddle one instead of two (no two-level lookup).  *hi_out is null when inv_diag carries it.
 static int ensure_scale_tables(spg_ctx* ctx, unsigned log_n, const uint64_t* offset, int mont, const Fp** lo_out,
-                               const Fp** hi_out) {
+                               const Fp** hi_out, const Fp** inv_diag_out) {
   for (auto& t : ctx->lde_tables)
     if (t.log_n == (int)log_n && t.mont == mont && memcmp(t.offset, offset, 32) == 0) {
-      *lo_out = t.lo; *hi_out = t.hi;
+      *lo_out = t.lo; *hi_out = t.inv_diag ? nullptr : t.hi; *inv_diag_out = t.inv_diag;
       return SPG_OK;
     }
   std::vector<Fp> lo, hi;
@@ -25,17 +34,24 @@ static int ensure_scale_tables(spg_ctx* ctx, unsigned log_n, const uint64_t* off
   const size_t R = lo.size(), B = hi.size();
   if (ctx->lde_tables.size() >= 8) {   // tiny cache: drop the oldest entry
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->lde_tables[0].lo); cudaFree(ctx->lde_tables[0].hi);
+    cudaFree(ctx->lde_tables[0].lo); cudaFree(ctx->lde_tables[0].hi); cudaFree(ctx->lde_tables[0].inv_diag);
     ctx->lde_tables.erase(ctx->lde_tables.begin());
   }
   spg_ctx::LdeTables t;
-  t.log_n = (int)log_n; t.mont = mont; memcpy(t.offset, offset, 32); t.lo = t.hi = nullptr;
+  t.log_n = (int)log_n; t.mont = mont; memcpy(t.offset, offset, 32); t.lo = t.hi = t.inv_diag = nullptr;
   SPG_CUDA(cudaMalloc((void**)&t.lo, R * sizeof(Fp)));
   SPG_CUDA(cudaMalloc((void**)&t.hi, B * sizeof(Fp)));
   SPG_CUDA(cudaMemcpy(t.lo, lo.data(), R * sizeof(Fp), cudaMemcpyHostToDevice));
   SPG_CUDA(cudaMemcpy(t.hi, hi.data(), B * sizeof(Fp), cudaMemcpyHostToDevice));
+  if (two_pass(log_n) && cudaMalloc((void**)&t.inv_diag, ((size_t)1 << log_n) * sizeof(Fp)) == cudaSuccess) {
+    int rc = spg_ntt_build_diag_table(ctx, log_n, /*inverse=*/1, /*dit=*/0, /*pass=*/0, 0, t.hi, t.inv_diag);
+    if (rc) { cudaFree(t.lo); cudaFree(t.hi); cudaFree(t.inv_diag); return rc; }
+  } else {
+    cudaGetLastError();
+    t.inv_diag = nullptr;
+  }
   ctx->lde_tables.push_back(t);
-  *lo_out = t.lo; *hi_out = t.hi;
+  *lo_out = t.lo; *hi_out = t.inv_diag ? nullptr : t.hi; *inv_diag_out = t.inv_diag;
   return SPG_OK;
 }
 
@@ -44,44 +60,51 @@ int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t 
                           Fp* coeffs, int mont) {
   static const uint64_t three[4] = {3, 0, 0, 0};
   const uint64_t* off = offset_canon ? offset_canon : three;
-  const Fp *lo, *hi;
-  int rc = ensure_scale_tables(ctx, log_n, off, mont, &lo, &hi);
+  const Fp *lo, *hi, *inv_diag;
+  int rc = ensure_scale_tables(ctx, log_n, off, mont, &lo, &hi, &inv_diag);
   if (rc) return rc;
   const size_t n = (size_t)1 << log_n;
   for (size_t c0 = 0; c0 < C; c0 += 32768) {
     const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
     rc = spg_ntt_device(ctx, trace + c0 * n, coeffs + c0 * n, log_n, nc, n, n, /*inverse=*/1, /*dit=*/0, 0,
-                        lo, hi);
+                        lo, hi, inv_diag);
     if (rc) return rc;
   }
   return SPG_OK;
 }
 
-// Direct diagonal-twiddle tables for the coset transforms of a two-pass LDE: one N-entry table per coset, built once
-// per (log_n, log_blowup) and kept in the context (8 x 32 MB at 2^20).  A coset's table is re-read by every column of
-// the launch and stays L2-resident; it replaces the two-level lookup's multiplication in the load phase of pass 2.
-static int ensure_diag_tables(spg_ctx* ctx, unsigned log_n, unsigned log_blowup, const Fp** out) {
-  *out = nullptr;
-  if (log_n <= (unsigned)spg_ntt_tile_log_ws(log_n) || log_n > 2 * (unsigned)spg_ntt_tile_log_ws(log_n) || log_blowup > 3)
-    return SPG_OK;      // single-pass or three-pass sizes: two-level lookup
+// Direct diagonal-twiddle tables for the coset transforms of a two-pass LDE, built once per (log_n, log_blowup) and kept in
+// the context: per coset one N-entry table for the strided second pass (8 x 32 MB at 2^20; a coset's table is re-read by
+// every column of the launch and stays L2-resident) and one R-entry table for the contiguous first pass (the within-tile
+// part of the coset shift w_{BN}^(j k); its per-tile part is already inside the second table).  They replace the
+// two-level lookup's multiplication in the load phase of both passes: one multiplication per element per pass.
+static int ensure_diag_tables(spg_ctx* ctx, unsigned log_n, unsigned log_blowup, const Fp** out, const Fp** out0, size_t* r0) {
+  *out = *out0 = nullptr; *r0 = 0;
+  if (!two_pass(log_n) || log_blowup > 3) return SPG_OK;      // single-pass or three-pass sizes: two-level lookup
+  int lr, lb;
+  spg_ntt_last_pass_geometry(log_n, spg_ntt_tile_log_ws(log_n), &lr, &lb);
+  const size_t n = (size_t)1 << log_n, nb = (size_t)1 << log_blowup, R = (size_t)1 << lr;
+  *r0 = R;
   for (auto& t : ctx->diag_tables)
-    if (t.log_n == (int)log_n && t.log_blowup == (int)log_blowup) { *out = t.t; return SPG_OK; }
-  const size_t n = (size_t)1 << log_n, nb = (size_t)1 << log_blowup;
+    if (t.log_n == (int)log_n && t.log_blowup == (int)log_blowup) { *out = t.t; *out0 = t.t0; return SPG_OK; }
   if (ctx->diag_tables.size() >= 2) {
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->diag_tables[0].t);
+    cudaFree(ctx->diag_tables[0].t); cudaFree(ctx->diag_tables[0].t0);
     ctx->diag_tables.erase(ctx->diag_tables.begin());
   }
   spg_ctx::DiagTables t;
-  t.log_n = (int)log_n; t.log_blowup = (int)log_blowup; t.t = nullptr;
+  t.log_n = (int)log_n; t.log_blowup = (int)log_blowup; t.t = t.t0 = nullptr;
   if (cudaMalloc((void**)&t.t, nb * n * sizeof(Fp)) != cudaSuccess) { cudaGetLastError(); return SPG_OK; }   // optional
+  if (cudaMalloc((void**)&t.t0, nb * R * sizeof(Fp)) != cudaSuccess) { cudaGetLastError(); cudaFree(t.t); return SPG_OK; }
   for (size_t j = 0; j < nb; j++) {
     const unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
-    int rc = spg_ntt_build_diag_table(ctx, log_n, coset_exp, t.t + j * n);
-    if (rc) { cudaFree(t.t); return rc; }
+    int rc = spg_ntt_build_diag_table(ctx, log_n, 0, 1, 1, coset_exp, nullptr, t.t + j * n);
+    // coset 0 has no shift: its contiguous pass carries no factor at all (use_diag = 0)
+    if (!rc && j) rc = spg_ntt_build_diag_table(ctx, log_n, 0, 1, 0, coset_exp, nullptr, t.t0 + j * R);
+    if (rc) { cudaFree(t.t); cudaFree(t.t0); return rc; }
   }
   ctx->diag_tables.push_back(t);
-  *out = t.t;
+  *out = t.t; *out0 = t.t0;
   return SPG_OK;
 }
 
@@ -93,15 +116,17 @@ int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t
   SPG_ARG(log_n + log_blowup <= SPG_UNI_LOG, "spg_lde: log_n + log_blowup above 26");
   SPG_ARG(j0 + nj <= ((size_t)1 << log_blowup), "spg_lde: coset range");
   const size_t n = (size_t)1 << log_n;
-  const Fp* diag = nullptr;
-  int rc0 = ensure_diag_tables(ctx, log_n, log_blowup, &diag);
+  const Fp *diag = nullptr, *diag0 = nullptr;
+  size_t r0 = 0;
+  int rc0 = ensure_diag_tables(ctx, log_n, log_blowup, &diag, &diag0, &r0);
   if (rc0) return rc0;
   for (size_t j = j0; j < j0 + nj; j++) {
     const unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
     for (size_t c0 = 0; c0 < C; c0 += 32768) {
       const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
       int rc = spg_ntt_device(ctx, coeffs + c0 * n, out + ((j - j0) * out_C + col0 + c0) * n, log_n, nc, n, n, /*inverse=*/0,
-                              /*dit=*/1, coset_exp, nullptr, nullptr, diag ? diag + j * n : nullptr);
+                              /*dit=*/1, coset_exp, nullptr, nullptr, diag ? diag + j * n : nullptr,
+                              (diag0 && j) ? diag0 + j * r0 : nullptr);
       if (rc) return rc;
     }
   }

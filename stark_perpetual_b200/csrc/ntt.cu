@@ -68,29 +68,36 @@ __global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
   out[col * n + spg_bitrev((unsigned)r, (int)log_n)] = in[i];
 }
 
-// diag_table[(c << log_r) | k] = omega_{2^26}^(k * (c * ec + e0)) for the pass P (k = bit-reversed row)
-__global__ void k_build_diag_table(NttPass P, Fp* __restrict__ table) {
+// diag_table[(c << log_r) | k] = omega_{2^26}^(+- k * (c * ec + e0)) for the pass P (k = bit-reversed row), optionally
+// times row_factor[bitrev_R(k)] (the LDE folds the per-tile part of its g^k scaling into the inverse transform's table)
+__global__ void k_build_diag_table(NttPass P, Fp* __restrict__ table, const Fp* __restrict__ row_factor) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ((size_t)1 << (P.log_r + P.log_s))) return;
-  const unsigned long long k = idx & ((1ull << P.log_r) - 1), c = idx >> P.log_r;
-  table[idx] = fp_reduce(NttTile<NTT_LOG_WS, NTT_LOG_EPT>::uni_pow(P, k * (c * P.ec + P.e0)));
+  Fp v = NttTile<NTT_LOG_WS, NTT_LOG_EPT>::diag_entry(P, idx);
+  if (row_factor) v = fp_mul(v, row_factor[spg_bitrev((unsigned)(idx & ((1ull << P.log_r) - 1)), P.log_r)]);
+  table[idx] = fp_reduce(v);
 }
 
-int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, unsigned long long coset_exp, Fp* table) {
+// Direct diagonal table of pass `pass_index` (execution order) of a two-pass transform: forward DIT with coset exponent
+// coset_exp (pass 0: the contiguous pass, 2^log_r entries; pass 1: the strided pass, N entries), or inverse DIF
+// (pass 0: the strided pass, N entries).  row_factor: optional device table indexed by the row r of that pass.
+int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, int inverse, int dit, int pass_index, unsigned long long coset_exp,
+                             const Fp* row_factor, Fp* table) {
   NttPass passes[8];
-  const int np = spg_ntt_make_passes(passes, spg_ntt_tile_log_ws(log_n), nullptr, nullptr, log_n, 0, 0, 0, /*dit=*/1, coset_exp, nullptr, nullptr,
-                                     ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
-  SPG_ARG(np == 2, "diag table: two-pass transforms only");
-  const NttPass& P = passes[1];
+  const int np = spg_ntt_make_passes(passes, spg_ntt_tile_log_ws(log_n), nullptr, nullptr, log_n, 0, 0, inverse, dit, coset_exp,
+                                     nullptr, nullptr, ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
+  SPG_ARG(np == 2 && pass_index >= 0 && pass_index < 2, "diag table: two-pass transforms only");
+  const NttPass& P = passes[pass_index];
+  SPG_ARG(P.use_diag, "diag table: pass has no diagonal factor");
   const size_t total = (size_t)1 << (P.log_r + P.log_s);
-  k_build_diag_table<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(P, table);
+  k_build_diag_table<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(P, table, row_factor);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
 
 int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
-                   const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table) {
+                   const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table, const Fp* diag_table0) {
   SPG_ARG(log_n <= 26, "NTT size above 2^26 not supported by the universal twiddle table");
   SPG_ARG(ncols < 65536, "too many columns in one NTT batch");
   if (ncols == 0) return SPG_OK;
@@ -107,7 +114,14 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
   if (!dit && coset_exp != 0) { ctx->err = "coset shift only supported for DIT"; return SPG_E_ARG; }
   const int np = spg_ntt_make_passes(passes, log_ws, in, out, log_n, in_stride, out_stride, inverse, dit,
                                      coset_exp, scale_lo, scale_hi, ctx->tw_fwd, ctx->tw_inv, ctx->uniA, ctx->uniB);
-  if (diag_table && np == 2 && dit && !inverse) passes[1].diag_table = diag_table;
+  // direct diagonal tables (two-pass transforms): forward DIT -- diag_table0 for the contiguous first pass, diag_table for
+  // the strided second pass; inverse DIF -- diag_table for the strided first pass
+  if (np == 2 && dit && !inverse) {
+    if (diag_table) passes[1].diag_table = diag_table;
+    if (diag_table0 && passes[0].use_diag) passes[0].diag_table = diag_table0;
+  } else if (np == 2 && !dit && inverse && diag_table) {
+    passes[0].diag_table = diag_table;
+  }
   const int smem = (1 << log_ws) * (int)sizeof(Fp), threads = (1 << log_ws) >> NTT_LOG_EPT;
   for (int pi = 0; pi < np; pi++) {
     const NttPass& P = passes[pi];

@@ -44,8 +44,10 @@ struct NttPass {
   const Fp* scale_lo;          // R entries
   const Fp* scale_hi;          // B entries
   int final_pass;              // last pass of the transform: store canonical values (otherwise any lazy representative)
-  // optional direct table of the diagonal factor (forward DIT passes of an LDE): diag_table[(c << log_r) | bitrev_R(r)]
-  // = omega_{2^26}^(bitrev_R(r) * (c * ec + e0)); saves the two-level lookup's multiplication (null: use uniA/uniB)
+  // optional direct table of the diagonal factor: diag_table[(c << log_r) | bitrev_R(r)]
+  // = omega_{2^26}^(+- bitrev_R(r) * (c * ec + e0)) [* an extra per-row factor folded in by the LDE, see lde.cu]; saves the
+  // two-level lookup's multiplication (null: use uniA/uniB).  The contiguous pass of a coset transform has c = 0: its
+  // table holds just 2^log_r entries.
   const Fp* diag_table;
 };
 
@@ -126,6 +128,14 @@ struct NttTile {
     if (lo == 0) return P.uniA[hi];
     if (hi == 0) return P.uniB[lo];
     return fp_mul_lazy(P.uniA[hi], P.uniB[lo]);
+  }
+
+  // entry idx = (c << log_r) | k of the direct diagonal table of pass P (k = bit-reversed row)
+  static SPG_HD Fp diag_entry(const NttPass& P, unsigned long long idx) {
+    const unsigned long long k = idx & ((1ull << P.log_r) - 1), c = idx >> P.log_r;
+    unsigned long long E = k * (c * P.ec + P.e0);
+    if (P.inverse) E = (0ull - E);
+    return uni_pow(P, E);
   }
 
   // factor applied to element (b, r, c): diagonal twiddle and optional scale tables.  Whenever the pass has a

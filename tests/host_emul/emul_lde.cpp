@@ -70,14 +70,32 @@ int main(int argc, char** argv) {
   const Fp g = from_u64(3);
   std::vector<Fp> lo, hi;
   spg_lde_scale_tables(log_n, EMUL_LOG_WS, g, lo, hi);
+  // direct diagonal tables exactly as lde.cu / ntt.cu build them (two-pass sizes; argv[3] = 0 disables them)
+  const bool use_tables = (argc > 3 ? atoi(argv[3]) : 1) && log_n > EMUL_LOG_WS && log_n <= 2 * EMUL_LOG_WS;
+  auto build_table = [&](const NttPass& P, const Fp* row_factor) {
+    std::vector<Fp> t((size_t)1 << (P.log_r + P.log_s));
+    for (size_t idx = 0; idx < t.size(); idx++) {
+      Fp v = Tile::diag_entry(P, idx);
+      if (row_factor) v = fp_mul(v, row_factor[spg_bitrev((unsigned)(idx & (((size_t)1 << P.log_r) - 1)), P.log_r)]);
+      t[idx] = fp_reduce(v);
+    }
+    return t;
+  };
   NttPass passes[8];
-  int np = spg_ntt_make_passes(passes, EMUL_LOG_WS, x.data(), coef.data(), log_n, n, n, 1, 0, 0, lo.data(), hi.data(),
-                               twf.data(), twi.data(), A.data(), B.data());
+  int np = spg_ntt_make_passes(passes, EMUL_LOG_WS, x.data(), coef.data(), log_n, n, n, 1, 0, 0, lo.data(),
+                               use_tables ? nullptr : hi.data(), twf.data(), twi.data(), A.data(), B.data());
+  std::vector<Fp> inv_diag;
+  if (use_tables) { inv_diag = build_table(passes[0], hi.data()); passes[0].diag_table = inv_diag.data(); }
   for (int pi = 0; pi < np; pi++) run_pass<false>(passes[pi], C);
   for (size_t j = 0; j < nb; j++) {
     unsigned long long coset_exp = (unsigned long long)j << (SPG_UNI_LOG - (log_n + log_blowup));
     np = spg_ntt_make_passes(passes, EMUL_LOG_WS, coef.data(), out.data() + j * C * n, log_n, n, n, 0, 1, coset_exp, nullptr,
                              nullptr, twf.data(), twi.data(), A.data(), B.data());
+    std::vector<Fp> d0, d1;
+    if (use_tables) {
+      d1 = build_table(passes[1], nullptr); passes[1].diag_table = d1.data();
+      if (passes[0].use_diag) { d0 = build_table(passes[0], nullptr); passes[0].diag_table = d0.data(); }
+    }
     for (int pi = 0; pi < np; pi++) run_pass<true>(passes[pi], C);
   }
   // reference: textbook inverse transform (O(n^2) for small n would be slow; use the iterative DIF) then Horner

@@ -38,7 +38,7 @@ def test_emulated_ntt_passes(args, shape):
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("args", ["3 3", "10 1", "12 3"])
+@pytest.mark.parametrize("args", ["3 3", "10 1", "12 3", "12 3 0", "13 2", "11 3"])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_emulated_lde(args, shape):
     exe = _build("emul_lde", shape)
