@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--orders", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the aux object (BASELINE configs 0, 1, 4 after the timed region)")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle verification of one proof")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -372,19 +373,24 @@ def main():
                 "stage_host_ms": None if world == 1 else {k: v[1] for k, v in sharded_stages.items()},
                 "algorithmic_muls_per_step": muls,
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
-        # dominant kernel: k_ntt_pass (all launches of the two LDE stages); every launch reads and writes each
-        # element of its columns once -> 64 B per element per pass
+        # dominant kernel: k_ntt_pass (all launches of the two LDE stages).  SURVEY.md section 8(d): the compulsory HBM traffic
+        # of a size-N transform is 64 N bytes (read once, write once), of the blowup-8 LDE 32 N C (1 + 8); a transform of
+        # 2^log_n > 2^10 points takes two launches (passes), so one launch is charged half a transform: 32 N bytes per
+        # column.  `frac` is that figure; `per_pass` charges every launch the 64 N bytes it really moves (two-pass
+        # algorithm: each pass reads and writes its columns once), which is what ncu's DRAM counters see (`traffic`).
         ntt_ms = float(stage_ms[0] + stage_ms[3])
         if ntt_ms > 0 and world == 1:
             passes = 2 if log_n > 10 else 1
-            bytes_total = (1 + 8) * 29 * n * 64.0 * passes
             n_launch = (1 + 8) * 2 * passes
-            ach = bytes_total / (ntt_ms * 1e-3) / 1e9
-            traffic = None
+            alg_bytes = (1 + 8) * 29 * n * 64.0                    # = 32 N C (1 + B) + the 4 chunk columns, read + write
+            pass_bytes = alg_bytes * passes
+            ach = alg_bytes / (ntt_ms * 1e-3) / 1e9
+            traffic, traffic_src = None, None
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_ntt_pass"]
                 if log_n == 20:
                     traffic = tj["dram_bytes_per_launch"]
+                    traffic_src = "static: profiles/ncu_traffic.json (%s)" % tj.get("source", "ncu --set full capture of this kernel")
             except (OSError, KeyError, ValueError):
                 pass
             ntt_muls = per_stage["lde_trace"] + per_stage["lde_chunks"]
@@ -393,18 +399,25 @@ def main():
             sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
             imad_peak = 148 * 32 * sm_mhz * 1e6
             line["roofline"] = {"bound": "hbm", "kernel": "k_ntt_pass", "achieved": ach, "peak": peak, "unit": "GB/s",
-                                "frac": ach / peak, "traffic": traffic,
-                                "algorithmic_bytes_per_launch": bytes_total / n_launch,
+                                "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                                "algorithmic_bytes_per_launch": alg_bytes / n_launch,
+                                "per_pass": {"bytes_per_launch": pass_bytes / n_launch,
+                                             "achieved": pass_bytes / (ntt_ms * 1e-3) / 1e9,
+                                             "frac": pass_bytes / (ntt_ms * 1e-3) / 1e9 / peak},
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                                 "launches_per_step": n_launch, "avg_launch_ms": ntt_ms / n_launch,
                                 "share_of_step": ntt_ms / ms_per_step,
                                 "field_mul_per_s": ntt_muls / (ntt_ms * 1e-3),
+                                "executed_muls_per_element": {"inverse": 10.5, "per_coset": 10.5,
+                                                              "note": "8.5 butterfly + 1 diagonal + 1 scale / coset-shift "
+                                                                      "multiplication per element per transform (DESIGN.md section 3)"},
                                 "int_pipe": {"binding": "fmaheavy (IMAD.WIDE)", "imad_wide_per_s_peak": imad_peak,
                                              "field_mul_per_s_ceiling": imad_peak / 64.0,
-                                             "frac_of_ceiling": ntt_muls / (ntt_ms * 1e-3) / (imad_peak / 64.0)},
-                                "note": "HBM fraction reported as the contract asks; the kernel is bound by the integer "
-                                        "multiply pipe, not by HBM (DESIGN.md section 2: 64 IMAD.WIDE per 252-bit "
-                                        "multiplication at 32 lanes/clk/SM; ncu: fmaheavy 65-70 % busy, DRAM 10 %)"}
+                                             "frac_of_ceiling": ntt_muls / (ntt_ms * 1e-3) / (imad_peak / 64.0),
+                                             "executed_frac_of_ceiling": (1 + 8) * 29 * n * 10.5 / (ntt_ms * 1e-3) / (imad_peak / 64.0)},
+                                "note": "HBM fraction reported as the contract asks (SURVEY 8(d) compulsory bytes); the kernel is "
+                                        "bound by the integer multiply pipe, not by HBM (DESIGN.md section 2: 64 IMAD.WIDE per "
+                                        "252-bit multiplication at 32 lanes/clk/SM)"}
         if e2e:
             line["e2e"] = {"value": muls / (e2e["ms_per_step"] * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": e2e["h2d_bytes_per_step"], "d2h_bytes_per_step": e2e["d2h_bytes_per_step"],
@@ -419,6 +432,15 @@ def main():
             v, cores, desc, _dt = cpu_sample(cfg)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                                     "proof_gen_s_extrapolated": muls / v}
+        if world == 1 and not args.no_aux:
+            # BASELINE.json configs[0], [1], [4] on the same record, measured after the timed region (tools/aux_bench.py)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import aux_bench
+            try:
+                line["aux"] = aux_bench.measure(ctx, (clocks or {}).get("sm_mhz") or 1965.0, with_reference=not args.no_cpu,
+                                                n_orders=args.orders, hbm_gbs=peak)
+            except Exception as e:          # the headline line must survive a failure of the side measurements
+                line["aux"] = {"error": repr(e)[:500]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -37,8 +37,18 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
-    d = _run(["--steps", "2", "--warmup", "3", "--log-n", "14"])
-    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches", "proof_gen_s", "stage_ms"} <= set(d)
+    d = _run(["--steps", "2", "--warmup", "3", "--log-n", "14", "--orders", "4096"])
+    assert BASE_KEYS | {"roofline", "clocks", "gpu_launches", "proof_gen_s", "stage_ms", "proof_sha256", "aux"} <= set(d)
+    assert len(d["proof_sha256"]) == 64
+    aux = d["aux"]
+    assert "error" not in aux, aux
+    for k in ("cfg0_pedersen_1024", "cfg1_ntt_2^18_single", "cfg1_ntt_2^18_batch64", "cfg4_orders_valid_mix", "cfg4_orders_invalid_mix"):
+        assert aux[k]["ms"] > 0 and 0 < aux[k]["frac_of_int_ceiling"] < 1, k
+    assert aux["cfg0_pedersen_1024"]["oracle_sample_ok"] and aux["cfg4_orders_valid_mix"]["statuses_as_expected"]
+    if "cpu_reference" in aux["cfg0_pedersen_1024"]:
+        assert aux["cfg0_pedersen_1024"]["cpu_reference"]["kind"] == "reference"
+        assert aux["cfg0_pedersen_1024"]["cpu_reference"]["gpu_equals_reference"]
+        assert aux["cfg4_orders_valid_mix"]["cpu_reference"]["gpu_equals_reference"]
     assert d["gpu_launches"] > 0 and d["verified_by_oracle"] is True and d["scaling"] == "strong"
     r = d["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
