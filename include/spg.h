@@ -194,6 +194,41 @@ typedef struct spg_message_fields {
 int spg_message_hash_batch(spg_ctx* ctx, int kind, const spg_message_fields* fields, uint64_t* msg_out, uint8_t* status,
                            size_t n, int flags);
 
+/* ---- state-tree work of a perpetual batch --------------------------------------------------
+ * Position hashing: replaces src/services/perpetual/cairo/position/hash.cairo:22-74 (position_hash_assets, position_hash),
+ * what state.cairo:143-150 (hash_position_updates) does for every touched position before the Merkle update.
+ *   h = 0;  for each asset: h = H(h, (asset_id * 2^64 + (cached_funding_index + 2^63)) * 2^64 + (balance + 2^63));
+ *   h = H(h, public_key);   h = H(h, (collateral_balance + 2^63) * 2^16 + n_assets)          (constants.cairo:10-38)
+ * Positions in CSR form: the assets of position i are entries [asset_offsets[i], asset_offsets[i+1]) of the asset arrays.
+ * status[i]: 0 ok; 1 a bound is violated (asset_id >= 2^120, n_assets >= 2^16, public_key >= p); 2 "Unhashable input." */
+typedef struct spg_positions {
+  const uint64_t* public_key;            /* [n][4] canonical felt */
+  const int64_t* collateral_balance;     /* [n] */
+  const uint64_t* asset_offsets;         /* [n + 1], non-decreasing, asset_offsets[0] = 0 */
+  const uint64_t* asset_id;              /* [total][2] little-endian 128-bit words, value < 2^120 */
+  const int64_t* balance;                /* [total] */
+  const int64_t* cached_funding_index;   /* [total] */
+} spg_positions;
+int spg_position_hash_batch(spg_ctx* ctx, const spg_positions* positions, uint64_t* hash_out, uint8_t* status, size_t n, int flags);
+
+/* Sparse Merkle multi-update with pedersen_hash nodes: the computation merkle_multi_update performs for the positions and
+ * orders trees (state.cairo:151-173), height <= 64.  keys: n strictly increasing leaf indices (a squashed dict);
+ * prev_leaves / new_leaves: [n][4].  The update tree is the one src/starkware/python/merkle_tree.py:4-29 build_update_tree
+ * describes; wherever a node of it has only one child in the tree, the other child is a SIBLING -- the hash of an untouched
+ * subtree, which the Cairo hints read from the preimage dictionary and the caller supplies here, in this order: level by
+ * level from the leaves up (level l = children at height l above the leaves), ascending node index within a level.
+ * spg_merkle_update_siblings lists (level, node index) of every sibling in that order (null outputs: count only).
+ * Outputs: prev_root (to be compared with the state's current root, as merkle_multi_update asserts) and new_root;
+ * nodes_out (optional): every node of the update tree above the leaves, level by level: for a level with m nodes, m
+ * previous values then m new values ([2][m][4]; per-level counts from spg_merkle_update_node_count, [height] entries).
+ * *status_out: 0 ok, 1 an input is >= p, 2 "Unhashable input." somewhere.  Host pointers. */
+int spg_merkle_update_siblings(spg_ctx* ctx, unsigned height, const uint64_t* keys, size_t n, uint8_t* level_out,
+                               uint64_t* index_out, size_t cap, size_t* count_out);
+int spg_merkle_update_node_count(spg_ctx* ctx, unsigned height, const uint64_t* keys, size_t n, size_t* level_counts_out);
+int spg_merkle_multi_update(spg_ctx* ctx, unsigned height, const uint64_t* keys, const uint64_t* prev_leaves,
+                            const uint64_t* new_leaves, size_t n, const uint64_t* siblings, size_t n_siblings,
+                            uint64_t* prev_root_out, uint64_t* new_root_out, uint64_t* nodes_out, uint8_t* status_out, int flags);
+
 /* ---- NTT over the STARK prime (no reference symbol, field from signature.py:41-42) */
 /* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
  * inverse != 0 uses omega^-1 and scales by 2^-log_n. */

@@ -63,6 +63,10 @@ def _load():
             "spg_mimic_ec_mult_air_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_pedersen_merkle_tree": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_int]),
             "spg_ec_op_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_position_hash_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_merkle_update_siblings": (C.c_int, [vp, C.c_uint, vp, C.c_size_t, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+            "spg_merkle_update_node_count": (C.c_int, [vp, C.c_uint, vp, C.c_size_t, vp]),
+            "spg_merkle_multi_update": (C.c_int, [vp, C.c_uint, vp, vp, vp, C.c_size_t, vp, C.c_size_t, vp, vp, vp, vp, C.c_int]),
             "spg_field_sqrt_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_limit_order_msg_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_message_hash_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, C.c_size_t, C.c_int]),
@@ -247,6 +251,63 @@ class Context:
         y, st = np.empty_like(x), np.empty(x.shape[0], np.uint8)
         self._check(self._lib.spg_field_sqrt_batch(self._h, _ptr(x), _ptr(y), _ptr(st), x.shape[0], 0))
         return y, st
+
+    # ---- state trees (f-4) ----
+    def position_hash(self, public_keys, collateral, offsets, asset_ids, balances, funding):
+        """position_hash (hash.cairo:22-74) of n positions in CSR form: public_keys (n, 4) felts, collateral (n,) int64,
+        offsets (n + 1,) uint64, asset_ids (total, 2) uint64 (128-bit little-endian), balances / funding (total,) int64.
+        Returns (hashes (n, 4), status (n,))."""
+        pk = np.ascontiguousarray(public_keys, dtype=np.uint64).reshape(-1, 4)
+        n = pk.shape[0]
+        col = np.ascontiguousarray(collateral, dtype=np.int64).reshape(n)
+        off = np.ascontiguousarray(offsets, dtype=np.uint64).reshape(n + 1)
+        total = int(off[-1])
+        aid = np.ascontiguousarray(asset_ids, dtype=np.uint64).reshape(-1, 2)
+        bal = np.ascontiguousarray(balances, dtype=np.int64).reshape(-1)
+        fi = np.ascontiguousarray(funding, dtype=np.int64).reshape(-1)
+        assert off[0] == 0 and aid.shape[0] == total and bal.shape[0] == total and fi.shape[0] == total
+        struct = (C.c_void_p * 6)(pk.ctypes.data, col.ctypes.data, off.ctypes.data, aid.ctypes.data if total else None,
+                                  bal.ctypes.data if total else None, fi.ctypes.data if total else None)
+        out, st = np.empty((n, 4), dtype=np.uint64), np.empty(n, dtype=np.uint8)
+        self._check(self._lib.spg_position_hash_batch(self._h, struct, _ptr(out), _ptr(st), n, 0))
+        return out, st
+
+    def merkle_update_siblings(self, height, keys):
+        """[(level, node index)] of the sibling hashes spg_merkle_multi_update needs, in its order."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1)
+        cnt = C.c_size_t(0)
+        self._check(self._lib.spg_merkle_update_siblings(self._h, height, _ptr(k), k.shape[0], None, None, 0, C.byref(cnt)))
+        lv, ix = np.empty(cnt.value, dtype=np.uint8), np.empty(cnt.value, dtype=np.uint64)
+        if cnt.value:
+            self._check(self._lib.spg_merkle_update_siblings(self._h, height, _ptr(k), k.shape[0], _ptr(lv), _ptr(ix), cnt.value,
+                                                             C.byref(cnt)))
+        return list(zip(lv.tolist(), ix.tolist()))
+
+    def merkle_multi_update(self, height, keys, prev_leaves, new_leaves, siblings, want_nodes=False):
+        """Sparse Merkle multi-update (state.cairo:151-173): keys strictly increasing; prev / new leaves (n, 4); siblings
+        (n_siblings, 4) in the order of merkle_update_siblings.  Returns (prev_root (4,), new_root (4,), status, nodes)
+        with nodes = list per level of an array (2, m, 4) (previous values, new values) or None."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64).reshape(-1)
+        n = k.shape[0]
+        pl = np.ascontiguousarray(prev_leaves, dtype=np.uint64).reshape(n, 4)
+        nl = np.ascontiguousarray(new_leaves, dtype=np.uint64).reshape(n, 4)
+        sb = np.ascontiguousarray(siblings, dtype=np.uint64).reshape(-1, 4)
+        pr, nr, st = np.empty(4, dtype=np.uint64), np.empty(4, dtype=np.uint64), np.empty(1, dtype=np.uint8)
+        nodes, counts = None, None
+        if want_nodes:
+            counts = (C.c_size_t * height)()
+            self._check(self._lib.spg_merkle_update_node_count(self._h, height, _ptr(k), n, counts))
+            nodes = np.empty((2 * sum(counts), 4), dtype=np.uint64)
+        self._check(self._lib.spg_merkle_multi_update(self._h, height, _ptr(k), _ptr(pl), _ptr(nl), n, _ptr(sb) if sb.shape[0] else None,
+                                                      sb.shape[0], _ptr(pr), _ptr(nr), _ptr(nodes) if nodes is not None else None,
+                                                      _ptr(st), 0))
+        per_level = None
+        if want_nodes:
+            per_level, off = [], 0
+            for m in counts:
+                per_level.append(nodes[off:off + 2 * m].reshape(2, m, 4))
+                off += 2 * m
+        return pr, nr, int(st[0]), per_level
 
     def pedersen_merkle_tree(self, leaves, want_nodes=False):
         """leaves: (n, 4) canonical felts, n a power of two -> (root (4,), nodes (n - 1, 4) or None, status)."""

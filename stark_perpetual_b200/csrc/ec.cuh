@@ -161,3 +161,16 @@ SPG_HD bool pedersen_absorb(PedersenAcc& a, const uint32_t (&x)[8], const APoint
   return ok;
 }
 
+
+// One pedersen_hash(x, y) (signature.py:296-318) of canonical operands already known to be < p; cp = the 506-point table.
+// Returns false on "Unhashable input." (signature.py:313); *out_canon receives the canonical hash.
+SPG_HD bool pedersen_hash2_one(const uint32_t (&x)[8], const uint32_t (&y)[8], const APoint* cp, Fp* out_canon) {
+  PedersenAcc a;
+  a.init(cp[0]);
+  bool ok = pedersen_absorb(a, x, cp + 2);
+  ok = pedersen_absorb(a, y, cp + 2 + SPG_HASH_BITS) && ok;
+  if (!ok) { *out_canon = fp_zero(); return false; }
+  const Fp zi = fp_inv_chain(a.p.Z);
+  *out_canon = fp_from_mont(fp_mul(a.p.X, fp_sqr(zi)));
+  return true;
+}
