@@ -1,4 +1,5 @@
 // Context lifetime, host-side constant tables, field-op entry points and throughput probes.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -81,6 +82,7 @@ extern "C" int spg_create(int device_ordinal, spg_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream"; return fail(SPG_E_CUDA); }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
+  { const char* e = getenv("SPG_NTT_GENERIC"); ctx->ntt_generic_only = e && e[0] == '1'; }
   int rc = build_tables(ctx);
   if (rc) return fail(rc);
   *out = ctx;

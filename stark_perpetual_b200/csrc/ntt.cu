@@ -60,6 +60,37 @@ __global__ void __launch_bounds__((1 << LOG_WS) >> NTT_LOG_EPT, LOG_WS == 10 ? 4
   }
 }
 
+// The compile-time tile (ntt.cuh NttTileCT): one CTA = one column's tile of 2^LOG_R elements, twiddles staged in shared
+// memory after the workspace.  Barriers as in k_ntt_pass: consecutive phases that stay inside a warp's 128-row window
+// need a warp barrier only; the first barrier is CTA-wide because every warp reads the staged twiddles.
+template <bool DIT, int LOG_R, int K>
+__device__ __forceinline__ void ntt_tile_steps(FpHalf* ws, const FpHalf* tws, int tid) {
+  typedef NttTileCT<LOG_R> T;
+  if constexpr (K < T::NS) {
+    T::template step_k<DIT, K>(ws, tws, tid);
+    constexpr bool warp_only = T::template step_local<DIT>(K) && T::template step_local<DIT>(K + 1);
+    if (warp_only) __syncwarp(); else __syncthreads();
+    ntt_tile_steps<DIT, LOG_R, K + 1>(ws, tws, tid);
+  }
+}
+
+template <bool DIT, int LOG_R>
+__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? 4 : 2) k_ntt_tile(NttPass P) {
+  typedef NttTileCT<LOG_R> T;
+  extern __shared__ uint4 smem_raw[];
+  FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
+  FpHalf* tws = ws + 2 * T::R;
+  const int tid = threadIdx.x;
+  const unsigned cta = blockIdx.x, col = blockIdx.y;
+  T::stage_twiddles(P, tws, tid);
+#pragma unroll
+  for (int j = 0; j < 4; j++) T::template load<DIT>(P, ws, cta, col, T::io_row(tid, j));
+  __syncthreads();
+  ntt_tile_steps<DIT, LOG_R, 0>(ws, tws, tid);
+#pragma unroll
+  for (int j = 0; j < 4; j++) T::template store<DIT>(P, ws, cta, col, T::io_row(tid, j));
+}
+
 __global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t n = (size_t)1 << log_n;
@@ -108,6 +139,10 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, NTT_LOG_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_LOG_WS) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
     attr_set = true;
   }
   NttPass passes[8];
@@ -127,7 +162,16 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     const NttPass& P = passes[pi];
     const size_t ctas = ((size_t)1 << log_n) >> (P.log_r + P.log_g);
     dim3 grid((unsigned)ctas, (unsigned)ncols);
-    if (log_ws == 11) {
+    if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
+      const int smem_ct = (1 << log_ws) * 48;
+      if (log_ws == 11) {
+        if (dit) k_ntt_tile<true, 11><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        else k_ntt_tile<false, 11><<<grid, threads, smem_ct, ctx->stream>>>(P);
+      } else {
+        if (dit) k_ntt_tile<true, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        else k_ntt_tile<false, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P);
+      }
+    } else if (log_ws == 11) {
       if (dit) k_ntt_pass<true, 11><<<grid, threads, smem, ctx->stream>>>(P);
       else k_ntt_pass<false, 11><<<grid, threads, smem, ctx->stream>>>(P);
     } else {

@@ -298,6 +298,193 @@ struct NttTile {
   }
 };
 
+// ------------------------------------------------------------------ compile-time tile (the dominant geometry)
+// A pass whose tile is exactly the workspace and holds one column: log_r = LOG_R, log_g = 0 -- both passes of every 2^20
+// (LOG_R = 10) and 2^22 (LOG_R = 11) transform, i.e. every launch of the headline LDE.  Same butterflies, lazy bounds and
+// workspace layout as NttTile<LOG_R, 2>; what changes is the instruction stream around them:
+//   * every shift, mask and step geometry is a compile-time constant (the generic tile decodes them per element);
+//   * the swizzle is GF(2)-linear, so swz(rbase | f << SH) = swz(rbase) ^ swz_c(f << SH): one swizzle per thread and step,
+//     the per-element parts fold into constants;
+//   * the intra-tile twiddles omega_{2^LOG_R}^e (e < 2^(LOG_R-1)) are staged once per CTA in shared memory, swizzled like the
+//     workspace.  From global memory every lane of a warp reads a different 128-byte line of the twiddle table -- 32 L1
+//     wavefronts per load instruction, which made the twiddle reads 83 % of the kernel's L1 lookups and kept the L1 data
+//     pipe 72 % busy (profiles/r2a_ntt_l1_summary.txt); from shared memory a warp's 16-byte reads are conflict-free.
+SPG_HD constexpr int spg_swz_c(int s) {
+  const int u = s >> 3;
+  return s ^ ((u ^ (u >> 3) ^ (u >> 6) ^ (u >> 9)) & 7) ^ ((u & 2) << 1);
+}
+
+template <int LOG_R>
+struct NttTileCT {
+  typedef NttTile<LOG_R, 2> G;
+  static constexpr int R = 1 << LOG_R, NT = R / 4, HW = R / 2, REM = LOG_R & 1, NS = (LOG_R + 1) / 2;
+  static constexpr int LWIN = 7;          // log2 rows of a warp's window (32 lanes x 4 elements)
+
+  // geometry of butterfly step k (same sequence as NttTile<LOG_R, 2>::step_geom)
+  template <bool DIT> static SPG_HD constexpr int step_w(int k) { return REM ? (DIT ? (k == 0 ? 1 : 2) : (k == NS - 1 ? 1 : 2)) : 2; }
+  template <bool DIT> static SPG_HD constexpr int step_sh(int k) {
+    return DIT ? (REM ? (k == 0 ? 0 : 1 + 2 * (k - 1)) : 2 * k) : ((REM && k == NS - 1) ? 0 : LOG_R - 2 * (k + 1));
+  }
+  // a step that only touches the 2^LWIN-row window of the executing warp (see k_ntt_pass)
+  template <bool DIT> static SPG_HD constexpr bool step_local(int k) {
+    return k >= NS ? true : (step_w<DIT>(k) == 2 && step_sh<DIT>(k) + 2 <= LWIN);
+  }
+
+  static SPG_HD void stage_twiddles(const NttPass& P, FpHalf* tws, int tid) {
+#pragma unroll
+    for (int e = tid; e < HW; e += NT) {
+      const Fp w = P.tw[e << (SPG_TW_LOG - LOG_R)];
+      const int i = G::swz(e);
+      FpHalf lo, hi;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { lo.v[k] = w.v[k]; hi.v[k] = w.v[4 + k]; }
+      tws[i] = lo; tws[HW + i] = hi;
+    }
+  }
+  static SPG_HD Fp tw_at(const FpHalf* tws, int i) {      // i: swizzled position
+    const FpHalf lo = tws[i], hi = tws[HW + i];
+    Fp x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { x.v[k] = lo.v[k]; x.v[4 + k] = hi.v[k]; }
+    return x;
+  }
+  static SPG_HD Fp ws_at(const FpHalf* ws, int i) {
+    const FpHalf lo = ws[i], hi = ws[R + i];
+    Fp x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { x.v[k] = lo.v[k]; x.v[4 + k] = hi.v[k]; }
+    return x;
+  }
+  static SPG_HD void ws_put(FpHalf* ws, int i, const Fp& x) {
+    FpHalf lo, hi;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { lo.v[k] = x.v[k]; hi.v[k] = x.v[4 + k]; }
+    ws[i] = lo; ws[R + i] = hi;
+  }
+
+  // global element offset of row r of this CTA's tile (log_g = 0)
+  static SPG_HD unsigned long long goff(const NttPass& P, unsigned cta, int r, unsigned* b, unsigned* c) {
+    if (P.log_s) {
+      *b = cta >> P.log_s; *c = cta & ((1u << P.log_s) - 1u);
+      return ((unsigned long long)*b << (LOG_R + P.log_s)) + ((unsigned long long)r << P.log_s) + *c;
+    }
+    *b = cta; *c = 0;
+    return ((unsigned long long)cta << LOG_R) + (unsigned)r;
+  }
+  // row handled by (tid, j) in the load / store phases: warp w owns rows [128 w, 128 w + 128)
+  static SPG_HD int io_row(int tid, int j) { return ((tid >> 5) << LWIN) | (j << 5) | (tid & 31); }
+
+  template <bool DIT>
+  static SPG_HD void load(const NttPass& P, FpHalf* ws, unsigned cta, unsigned col, int r) {
+    unsigned b, c;
+    const unsigned long long off = goff(P, cta, r, &b, &c);
+    Fp x = P.in[col * P.in_col_stride + off];
+    if (DIT) x = G::apply_factors(P, x, b, r, c);
+    ws_put(ws, G::swz(r), x);
+  }
+  template <bool DIT>
+  static SPG_HD void store(const NttPass& P, const FpHalf* ws, unsigned cta, unsigned col, int r) {
+    unsigned b, c;
+    const unsigned long long off = goff(P, cta, r, &b, &c);
+    Fp x = ws_at(ws, G::swz(r));
+    if (!DIT) x = G::apply_factors(P, x, b, r, c);
+    P.out[col * P.out_col_stride + off] = P.final_pass ? fp_reduce_full(x) : x;
+  }
+
+  // one butterfly step of width W at bit position SH (both compile-time); arithmetic identical to NttTile::step
+  template <int W, int SH, bool DIT>
+  static SPG_HD void step(FpHalf* ws, const FpHalf* tws, int tid) {
+    constexpr bool EDGE = (SH == 0);
+    constexpr int GS = 1 << W, GROUPS = 4 >> W, t = LOG_R;
+#pragma unroll
+    for (int gi = 0; gi < GROUPS; gi++) {
+      const int x = gi * NT + tid;
+      const int lo = x & ((1 << SH) - 1), hi = x >> SH;
+      const int sbase = G::swz((hi << (SH + W)) | lo);
+      Fp v[GS];
+      int bd[GS];
+#pragma unroll
+      for (int f = 0; f < GS; f++) { v[f] = ws_at(ws, sbase ^ spg_swz_c(f << SH)); bd[f] = 2; }
+      if (DIT) {
+#pragma unroll
+        for (int s = 0; s < W; s++) {
+          const int k = t - 1 - (SH + s);
+          const int tbase = EDGE ? 0 : G::swz(lo << k);
+#pragma unroll
+          for (int f = 0; f < GS; f++) {
+            if (f & (1 << s)) continue;
+            const int f2 = f | (1 << s);
+            const int cf = f & ((1 << s) - 1);
+            const bool trivial = EDGE && cf == 0;
+            Fp tq;
+            int btq;
+            if (trivial) {
+              if (bd[f2] > 4) { tq = fp_partial(v[f2]); btq = 2; }
+              else { tq = v[f2]; btq = bd[f2]; }
+            } else {
+              tq = fp_mul_lazy(v[f2], tw_at(tws, tbase ^ spg_swz_c(cf << (SH + k))));
+              btq = 2;
+            }
+            const Fp a = v[f];
+            v[f] = fp_add_raw(a, tq);
+            v[f2] = fp_sub_lazy(a, tq, (uint32_t)btq);
+            bd[f] = bd[f2] = bd[f] + btq;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = W - 1; s >= 0; s--) {
+          const int k = t - 1 - (SH + s);
+          const int tbase = EDGE ? 0 : G::swz(lo << k);
+#pragma unroll
+          for (int f = 0; f < GS; f++) {
+            if (f & (1 << s)) continue;
+            const int f2 = f | (1 << s);
+            const int cf = f & ((1 << s) - 1);
+            const bool trivial = EDGE && cf == 0;
+            const Fp a = v[f], bb = v[f2];
+            const int bsum = bd[f] + bd[f2];
+            v[f] = fp_add_raw(a, bb);
+            const Fp d = fp_sub_lazy(a, bb, (uint32_t)bd[f2]);
+            if (trivial) { v[f2] = d; bd[f2] = bsum; }
+            else {
+              v[f2] = fp_mul_lazy(d, tw_at(tws, tbase ^ spg_swz_c(cf << (SH + k))));
+              bd[f2] = 2;
+            }
+            bd[f] = bsum;
+          }
+        }
+        if (!EDGE) {
+#pragma unroll
+          for (int f = 0; f < GS; f++)
+            if (bd[f] > 2) v[f] = fp_partial(v[f]);
+        }
+      }
+#pragma unroll
+      for (int f = 0; f < GS; f++) ws_put(ws, sbase ^ spg_swz_c(f << SH), v[f]);
+    }
+  }
+
+  // step K (compile-time) and, for the host emulation, step k (run-time dispatch onto the same instantiations)
+  template <bool DIT, int K>
+  static SPG_HD void step_k(FpHalf* ws, const FpHalf* tws, int tid) {
+    step<step_w<DIT>(K), step_sh<DIT>(K), DIT>(ws, tws, tid);
+  }
+  template <bool DIT>
+  static SPG_HD void step_rt(int k, FpHalf* ws, const FpHalf* tws, int tid) {
+    switch (k) {
+      case 0: step_k<DIT, 0>(ws, tws, tid); break;
+      case 1: step_k<DIT, 1>(ws, tws, tid); break;
+      case 2: step_k<DIT, 2>(ws, tws, tid); break;
+      case 3: step_k<DIT, 3>(ws, tws, tid); break;
+      case 4: step_k<DIT, 4>(ws, tws, tid); break;
+      default: if (NS > 5) step_k<DIT, (NS > 5 ? 5 : 0)>(ws, tws, tid); break;
+    }
+  }
+  // can pass P run on this tile?
+  static SPG_HD bool fits(const NttPass& P) { return P.log_r == LOG_R && P.log_g == 0; }
+};
+
 // ------------------------------------------------------------------ pass planner (host)
 // Split log_n into per-pass tile sizes (each <= max_bits = log2 of the workspace, as even as possible, larger first).
 static inline int spg_ntt_plan_bits(unsigned log_n, int bits[8], int max_bits) {

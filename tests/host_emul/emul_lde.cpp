@@ -24,10 +24,30 @@ static Fp root(int log_n) { uint32_t e[8]; exp_root(log_n, e); return fp_pow(fro
 #endif
 typedef NttTile<EMUL_LOG_WS, EMUL_LOG_EPT> Tile;
 
+static int g_ct_passes = 0;      // passes that ran on the compile-time tile (NttTileCT)
 template <bool DIT>
 static void run_pass(const NttPass& P, unsigned ncols) {
   const size_t ctas = ((size_t)1 << P.log_n) >> (P.log_r + P.log_g);
   std::vector<FpHalf> ws(2 * Tile::WS);
+#if EMUL_LOG_EPT == 2
+  // the compile-time tile kernel (k_ntt_tile) whenever the pass fits it, phase by phase as the barriers order it
+  typedef NttTileCT<EMUL_LOG_WS> CT;
+  if (CT::fits(P) && !getenv("EMUL_GENERIC")) {
+    std::vector<FpHalf> tws(2 * CT::HW);
+    g_ct_passes++;
+    for (unsigned col = 0; col < ncols; col++)
+      for (unsigned cta = 0; cta < ctas; cta++) {
+        for (int tid = 0; tid < CT::NT; tid++) CT::stage_twiddles(P, tws.data(), tid);
+        for (int tid = 0; tid < CT::NT; tid++)
+          for (int j = 0; j < 4; j++) CT::load<DIT>(P, ws.data(), cta, col, CT::io_row(tid, j));
+        for (int k = 0; k < CT::NS; k++)
+          for (int tid = 0; tid < CT::NT; tid++) CT::step_rt<DIT>(k, ws.data(), tws.data(), tid);
+        for (int tid = 0; tid < CT::NT; tid++)
+          for (int j = 0; j < 4; j++) CT::store<DIT>(P, ws.data(), cta, col, CT::io_row(tid, j));
+      }
+    return;
+  }
+#endif
   for (unsigned col = 0; col < ncols; col++)
     for (unsigned cta = 0; cta < ctas; cta++) {
       for (int tid = 0; tid < Tile::NT; tid++)
@@ -127,6 +147,7 @@ int main(int argc, char** argv) {
       checked++;
     }
   }
+  printf("ct_passes=%d ", g_ct_passes);
   printf("lde log_n=%d log_blowup=%d : %s (%zu bad of %zu)\n", log_n, log_blowup, bad ? "FAIL" : "OK", bad, checked);
   return bad ? 1 : 0;
 }
