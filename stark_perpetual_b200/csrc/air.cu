@@ -259,63 +259,116 @@ Fp spg_air_composition_at_host(unsigned log_n, unsigned chain_log, const AirPubl
 }
 
 // ------------------------------------------------------------------ witness generation
-// One thread per (lane, segment): runs the 2^chain_log chained hashes of the segment step by step, exactly
-// as signature.py:300-318 does (affine additions, math_utils.py:59-68), and writes the five columns.
-__global__ void __launch_bounds__(64) k_pedersen_trace(unsigned log_n, unsigned chain_log, const Fp* __restrict__ x0,
-                                                       const Fp* __restrict__ ys, Fp* __restrict__ trace,
-                                                       uint8_t* __restrict__ status, const APoint* __restrict__ cp) {
+// Two kernels.  (1) k_pedersen_walk: one thread per (lane, segment) runs the 2^chain_log chained hashes of the segment
+// step by step as signature.py:300-318 does, but in Jacobian coordinates (no inversion on the sequential path) and parks
+// (X, Y, Z) of the partial sum BEFORE each row's step in the X, Y, S columns, the remaining scalar in M.  (2)
+// k_pedersen_finish: one thread per 16 consecutive rows of a lane turns them into the affine witness -- x = X / Z^2,
+// y = Y / Z^3, I = 1 / (x - px) = Z^2 / (X - px Z^2), S = bit ? (y - py) I : 0 -- with ONE Fermat inversion per 32 values
+// (Montgomery's trick) instead of one per row.  The segment's hashes are chained through the affine x of the last
+// row, which the walk needs: that one inversion per hash stays on the sequential path (4 per thread at chain_log 2).
+#define SPG_WIT_ROWS 16
+__global__ void __launch_bounds__(64) k_pedersen_walk(unsigned log_n, unsigned chain_log, const Fp* __restrict__ x0,
+                                                      const Fp* __restrict__ ys, Fp* __restrict__ trace,
+                                                      uint32_t* __restrict__ status, const APoint* __restrict__ cp) {
   const size_t n = (size_t)1 << log_n, inst = n >> 9, nseg = inst >> chain_log;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= SPG_AIR_LANES * nseg) return;
   const size_t l = idx / nseg, sgi = idx - l * nseg;
   Fp* X = trace + ((5 * l) << log_n);
-  Fp *Y = X + n, *S = X + 2 * n, *M = X + 3 * n, *I = X + 4 * n;
-  uint8_t st = 0;
+  Fp *Y = X + n, *Z = X + 2 * n, *M = X + 3 * n;
+  uint32_t st = 0;
   Fp a = x0[l];                                   // canonical
   for (size_t q = sgi << chain_log; q < ((sgi + 1) << chain_log); q++) {
-    APoint ps = cp[0];
+    JPoint ps; ps.X = cp[0].x; ps.Y = cp[0].y; ps.Z = fp_one();
     for (int e = 0; e < 2; e++) {
       Fp v = e ? ys[l * inst + q] : a;            // canonical scalar, shifted right one bit per row
       if (spg_canon_geq_p(v.v)) st |= 1;
       else if (v.v[7] >> 27) st |= 4;             // >= 2^251: outside the AIR's canonical 251-bit unpacking
       for (int t = 0; t < 256; t++) {
         const size_t r = (q << 9) + 256 * e + t;
-        X[r] = fp_from_mont(ps.x); Y[r] = fp_from_mont(ps.y); M[r] = v;
-        Fp s_out = fp_zero(), i_out = fp_zero();
-        if (t < SPG_HASH_BITS) {
+        X[r] = ps.X; Y[r] = ps.Y; Z[r] = ps.Z; M[r] = v;
+        if (t < SPG_HASH_BITS && (v.v[0] & 1u)) {
           const APoint pt = cp[2 + SPG_HASH_BITS * e + t];
-          const Fp d = fp_sub(ps.x, pt.x);
-          if (fp_is_zero(d)) st |= 2;             // "Unhashable input." (signature.py:313)
-          const Fp di = fp_inv_chain(d);
-          i_out = fp_from_mont(di);
-          if (v.v[0] & 1u) {
-            const Fp s = fp_mul(fp_sub(ps.y, pt.y), di);
-            s_out = fp_from_mont(s);
-            APoint nx;
-            nx.x = fp_sub(fp_sub(fp_sqr(s), ps.x), pt.x);
-            nx.y = fp_sub(fp_mul(s, fp_sub(ps.x, nx.x)), ps.y);
-            ps = nx;
-          }
+          const Fp zz = fp_sqr(ps.Z);
+          ps = ec_madd_nocheck(ps, pt, fp_mul(zz, ps.Z), fp_mul(pt.x, zz));
         }
-        S[r] = s_out; I[r] = i_out;
-        // v >>= 1
 #pragma unroll
         for (int k = 0; k < 7; k++) v.v[k] = (v.v[k] >> 1) | (v.v[k + 1] << 31);
         v.v[7] >>= 1;
       }
     }
-    a = fp_from_mont(ps.x);
+    const Fp zi = fp_inv_chain(ps.Z);             // Z = 0 only after an x-collision, which k_pedersen_finish reports
+    a = fp_from_mont(fp_mul(ps.X, fp_sqr(zi)));
   }
-  if (st) atomicOr((unsigned int*)status, (unsigned int)st);
+  if (st) atomicOr(status, st);
+}
+
+__global__ void __launch_bounds__(128) k_pedersen_finish(unsigned log_n, Fp* __restrict__ trace, uint32_t* __restrict__ status,
+                                                         const APoint* __restrict__ cp) {
+  const size_t n = (size_t)1 << log_n, blocks_per_lane = n / SPG_WIT_ROWS;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= SPG_AIR_LANES * blocks_per_lane) return;
+  const size_t l = idx / blocks_per_lane, r0 = (idx - l * blocks_per_lane) * SPG_WIT_ROWS;
+  Fp* X = trace + ((5 * l) << log_n);
+  Fp *Y = X + n, *S = X + 2 * n, *M = X + 3 * n, *I = X + 4 * n;
+  // values to invert: Z_k and D_k = X_k - px Z_k^2 (1 on the padding rows), prefix products kept in local memory
+  Fp pre[2 * SPG_WIT_ROWS];
+  Fp run = fp_one();
+  uint32_t st = 0;
+#pragma unroll 1
+  for (int k = 0; k < SPG_WIT_ROWS; k++) {
+    const size_t r = r0 + k;
+    const int t = (int)(r & 255), e = (int)((r >> 8) & 1);
+    const Fp z = S[r];
+    Fp d = fp_one();
+    if (t < SPG_HASH_BITS) {
+      d = fp_sub(X[r], fp_mul(cp[2 + SPG_HASH_BITS * e + t].x, fp_sqr(z)));
+      if (fp_is_zero(d)) { st |= 2; d = fp_one(); }           // "Unhashable input." (signature.py:313)
+    }
+    pre[2 * k] = run; run = fp_mul(run, z);
+    pre[2 * k + 1] = run; run = fp_mul(run, d);
+  }
+  if (fp_is_zero(run)) { st |= 2; run = fp_one(); }            // a partial sum at infinity (follows a collision)
+  Fp inv = fp_inv_chain(run);
+#pragma unroll 1
+  for (int k = SPG_WIT_ROWS - 1; k >= 0; k--) {
+    const size_t r = r0 + k;
+    const int t = (int)(r & 255), e = (int)((r >> 8) & 1);
+    const Fp z = S[r], x_j = X[r], y_j = Y[r];
+    const Fp zz = fp_sqr(z);
+    Fp d = fp_one();
+    APoint pt; pt.x = fp_zero(); pt.y = fp_zero();
+    if (t < SPG_HASH_BITS) {
+      pt = cp[2 + SPG_HASH_BITS * e + t];
+      d = fp_sub(x_j, fp_mul(pt.x, zz));
+      if (fp_is_zero(d)) d = fp_one();
+    }
+    const Fp di = fp_mul(inv, pre[2 * k + 1]); inv = fp_mul(inv, d);
+    const Fp zi = fp_mul(inv, pre[2 * k]); inv = fp_mul(inv, z);
+    const Fp zi2 = fp_sqr(zi);
+    const Fp x = fp_mul(x_j, zi2), y = fp_mul(y_j, fp_mul(zi2, zi));
+    Fp s_out = fp_zero(), i_out = fp_zero();
+    if (t < SPG_HASH_BITS) {
+      const Fp ii = fp_mul(zz, di);                            // 1 / (x - px)
+      i_out = fp_from_mont(ii);
+      if (M[r].v[0] & 1u) s_out = fp_from_mont(fp_mul(fp_sub(y, pt.y), ii));
+    }
+    X[r] = fp_from_mont(x); Y[r] = fp_from_mont(y); S[r] = s_out; I[r] = i_out;
+  }
+  if (st) atomicOr(status, st);
 }
 
 int spg_pedersen_trace_device(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const Fp* d_x0, const Fp* d_ys, Fp* trace,
                               uint8_t* d_status) {
   SPG_ARG(log_n >= 9 && 9 + chain_log <= log_n, "pedersen trace: size");
-  const size_t nseg = ((size_t)1 << log_n) >> (9 + chain_log);
+  const size_t n = (size_t)1 << log_n, nseg = n >> (9 + chain_log);
   const size_t total = SPG_AIR_LANES * nseg;
-  k_pedersen_trace<<<(unsigned)((total + 63) / 64), 64, 0, ctx->stream>>>(log_n, chain_log, d_x0, d_ys, trace, d_status,
-                                                                         (const APoint*)ctx->const_points);
+  k_pedersen_walk<<<(unsigned)((total + 63) / 64), 64, 0, ctx->stream>>>(log_n, chain_log, d_x0, d_ys, trace, (uint32_t*)d_status,
+                                                                        (const APoint*)ctx->const_points);
+  SPG_LAUNCH_CHECK();
+  const size_t blocks = SPG_AIR_LANES * (n / SPG_WIT_ROWS);
+  k_pedersen_finish<<<(unsigned)((blocks + 127) / 128), 128, 0, ctx->stream>>>(log_n, trace, (uint32_t*)d_status,
+                                                                              (const APoint*)ctx->const_points);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }

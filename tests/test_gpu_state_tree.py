@@ -20,7 +20,7 @@ def _positions(rng, n, max_assets=6):
     pos = []
     for _ in range(n):
         k = rng.randrange(max_assets + 1)
-        ids = sorted(rng.sample(range(2**120), k))
+        ids = sorted({rng.randrange(2**120) for _ in range(k)})
         assets = [(a, rng.randrange(-2**63, 2**63), rng.randrange(-2**63, 2**63)) for a in ids]
         pos.append((rng.randrange(P), rng.randrange(-2**63, 2**63), assets))
     return pos
