@@ -229,6 +229,13 @@ int spg_merkle_multi_update(spg_ctx* ctx, unsigned height, const uint64_t* keys,
                             const uint64_t* new_leaves, size_t n, const uint64_t* siblings, size_t n_siblings,
                             uint64_t* prev_root_out, uint64_t* new_root_out, uint64_t* nodes_out, uint8_t* status_out, int flags);
 
+/* Right-folded Pedersen hash chain  h(d[0], h(d[1], ... h(d[len-2], d[len-1])))  of n chains of `len` canonical felts each
+ * (data: [n][len][4]): compute_hash_chain of cairo-lang (un-vendored dependency; the reference reaches it through
+ * compute_program_hash_chain at src/starkware/cairo/bootloaders/program_hash_test_utils.py:7-9, golden value
+ * src/services/perpetual/cairo/program_hash.json:2).  len = 1 returns the element.  status[i]: 0 ok, 1 an element >= p,
+ * 2 "Unhashable input.".  Sequential by construction: one device thread per chain.  Host pointers. */
+int spg_hash_chain_rfold_batch(spg_ctx* ctx, const uint64_t* data, size_t len, uint64_t* out, uint8_t* status, size_t n, int flags);
+
 /* ---- NTT over the STARK prime (no reference symbol, field from signature.py:41-42) */
 /* In-place transform of `batch` vectors of 2^log_n felts stored back to back.  omega = 3^((p-1)/2^log_n).
  * inverse != 0 uses omega^-1 and scales by 2^-log_n. */

@@ -63,6 +63,7 @@ def _load():
             "spg_mimic_ec_mult_air_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_pedersen_merkle_tree": (C.c_int, [vp, vp, C.c_size_t, vp, vp, vp, C.c_int]),
             "spg_ec_op_batch": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, C.c_size_t, C.c_int]),
+            "spg_hash_chain_rfold_batch": (C.c_int, [vp, vp, C.c_size_t, vp, vp, C.c_size_t, C.c_int]),
             "spg_position_hash_batch": (C.c_int, [vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_merkle_update_siblings": (C.c_int, [vp, C.c_uint, vp, C.c_size_t, vp, vp, C.c_size_t, C.POINTER(C.c_size_t)]),
             "spg_merkle_update_node_count": (C.c_int, [vp, C.c_uint, vp, C.c_size_t, vp]),
@@ -251,6 +252,15 @@ class Context:
         y, st = np.empty_like(x), np.empty(x.shape[0], np.uint8)
         self._check(self._lib.spg_field_sqrt_batch(self._h, _ptr(x), _ptr(y), _ptr(st), x.shape[0], 0))
         return y, st
+
+    def hash_chain_rfold(self, data, length):
+        """n right-folded chains h(d0, h(d1, ... h(d[len-2], d[len-1]))): data (n * length, 4) -> (out (n, 4), status (n,))."""
+        d = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)
+        assert length >= 1 and d.shape[0] % length == 0
+        n = d.shape[0] // length
+        out, st = np.empty((n, 4), dtype=np.uint64), np.empty(n, dtype=np.uint8)
+        self._check(self._lib.spg_hash_chain_rfold_batch(self._h, _ptr(d), length, _ptr(out), _ptr(st), n, 0))
+        return out, st
 
     # ---- state trees (f-4) ----
     def position_hash(self, public_keys, collateral, offsets, asset_ids, balances, funding):

@@ -260,3 +260,53 @@ extern "C" int spg_merkle_update_node_count(spg_ctx* ctx, unsigned height, const
   for (unsigned l = 0; l < height; l++) level_counts_out[l] = levels[l].index.size();
   return SPG_OK;
 }
+
+// ------------------------------------------------------------------ right-folded hash chain (program hash, row f-2)
+// compute_hash_chain of cairo-lang (starkware/cairo/common/hash_chain.py, un-vendored; call site in the reference:
+// src/starkware/cairo/bootloaders/program_hash_test_utils.py:7-9 via compute_program_hash_chain):
+//   h(data[0], h(data[1], h(..., h(data[n-2], data[n-1]))))        -- inherently sequential: one thread per chain.
+__global__ void __launch_bounds__(32) k_hash_chain_rfold(const uint64_t* __restrict__ data, size_t len, uint64_t* __restrict__ out,
+                                                         uint8_t* __restrict__ status, size_t n, const APoint* __restrict__ cp) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* d = data + 4 * i * len;
+  uint32_t h[8], x[8];
+  uint8_t st = 0;
+  st_load8(d + 4 * (len - 1), h);
+  if (spg_canon_geq_p(h)) st = 1;
+  Fp res;
+#pragma unroll
+  for (int k = 0; k < 8; k++) res.v[k] = h[k];
+  for (size_t k = len - 1; k-- > 0 && !st;) {
+    st_load8(d + 4 * k, x);
+    if (spg_canon_geq_p(x)) { st = 1; break; }
+    if (!pedersen_hash2_one(x, h, cp, &res)) { st = 2; break; }
+#pragma unroll
+    for (int q = 0; q < 8; q++) h[q] = res.v[q];
+  }
+  if (st) res = fp_zero();
+  st_store8(out + 4 * i, res);
+  status[i] = st;
+}
+
+extern "C" int spg_hash_chain_rfold_batch(spg_ctx* ctx, const uint64_t* data, size_t len, uint64_t* out, uint8_t* status, size_t n,
+                                          int flags) {
+  SPG_LOCK(ctx);
+  SPG_ARG(ctx && data && out && status && len >= 1, "spg_hash_chain_rfold_batch: arguments");
+  SPG_ARG(!(flags & SPG_DEVICE_PTRS), "spg_hash_chain_rfold_batch: host pointers only");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  if (n == 0) return SPG_OK;
+  DevBuf dd, dout, dst;
+  SPG_CUDA(dd.alloc(ctx, n * len * 32)); SPG_CUDA(dout.alloc(ctx, n * 32)); SPG_CUDA(dst.alloc(ctx, n));
+  SPG_CUDA(cudaMemcpyAsync(dd.p, data, n * len * 32, cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_hash_chain_rfold<<<(unsigned)((n + 31) / 32), 32, 0, ctx->stream>>>(dd.as<uint64_t>(), len, dout.as<uint64_t>(), dst.as<uint8_t>(), n,
+                                                                       (const APoint*)ctx->const_points);
+  SPG_LAUNCH_CHECK();
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(status, dst.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  return SPG_OK;
+}

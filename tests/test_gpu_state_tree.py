@@ -153,3 +153,34 @@ def test_state_update_throughput_2_16(ctx, capsys):
     # consistency: prev_root of (new state) -> applying no change gives the same root on both planes
     pr2, nr2, st2, _ = ctx.merkle_multi_update(64, keys, new_leaves, new_leaves, sib_vals)
     assert st2 == 0 and np.array_equal(pr2, nr) and np.array_equal(nr2, nr)
+
+
+def test_program_hash_chain_vs_oracle(ctx):
+    """Row f-2: the right-folded chain behind compute_program_hash_chain (program_hash_test_utils.py:7-9) through the
+    compat modules, against the oracle restatement, on a synthetic compiled program."""
+    import os
+    import sys
+    from oracle import hash_chain as ohc
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "stark_perpetual_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        from starkware.cairo.bootloaders.hash_program import compute_program_hash_chain
+        from starkware.cairo.common.hash_chain import compute_hash_chain
+    finally:
+        sys.path.remove(compat)
+    rng = random.Random(2)
+    data = [rng.randrange(P) for _ in range(40)]
+    assert compute_hash_chain(data) == ohc.compute_hash_chain(data)
+    assert compute_hash_chain(data[:1]) == data[0] and compute_hash_chain(data[:2]) == pedersen_hash(data[0], data[1])
+    builtins = ["output", "pedersen", "range_check", "ecdsa", "bitwise"]      # main.cairo:1 of the perpetual program
+    prog = {"builtins": builtins, "data": [hex(v) for v in data], "identifiers": {"__main__.main": {"pc": 17}}}
+    assert compute_program_hash_chain(prog) == ohc.compute_program_hash_chain(builtins, 17, data)
+
+    class Prog:
+        pass
+    p = Prog(); p.builtins, p.main, p.data = builtins, 17, data
+    assert compute_program_hash_chain(p) == compute_program_hash_chain(prog)
+    # batch of chains + range status
+    arr = ints_to_limbs(data[:12] + data[12:23] + [P])
+    out, st = ctx.hash_chain_rfold(arr, 12)
+    assert st.tolist() == [0, 1] and limbs_to_ints(out)[0] == ohc.compute_hash_chain(data[:12])

@@ -74,3 +74,21 @@ def test_position_hash_structure():
     assert calls[1][1] < 2**251
     # empty position: H(H(0, key), (collateral + 2^63) * 2^16)
     assert state_tree.position_hash(9, 0, [], cheap_hash) == cheap_hash(cheap_hash(0, 9), 2**63 * 2**16)
+
+
+def test_hash_chain_is_a_right_fold():
+    from oracle import hash_chain
+    calls = []
+
+    def h(a, b):
+        calls.append((a, b))
+        return cheap_hash(a, b)
+    data = [11, 22, 33, 44]
+    out = hash_chain.compute_hash_chain(data, h)
+    assert calls == [(33, 44), (22, cheap_hash(33, 44)), (11, cheap_hash(22, cheap_hash(33, 44)))] and out == cheap_hash(*calls[-1])
+    assert hash_chain.compute_hash_chain([7], h) == 7
+    # program header: [len, bootloader_version, main, n_builtins, builtins..., data...]
+    calls.clear()
+    hash_chain.compute_program_hash_chain(["output", "pedersen"], 5, [100, 200], hash_func=h)
+    first_args = [c[0] for c in calls][::-1]
+    assert first_args == [6, 0, 5, 2, int.from_bytes(b"output", "big"), int.from_bytes(b"pedersen", "big"), 100][:len(first_args)]
