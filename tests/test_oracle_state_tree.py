@@ -91,4 +91,4 @@ def test_hash_chain_is_a_right_fold():
     calls.clear()
     hash_chain.compute_program_hash_chain(["output", "pedersen"], 5, [100, 200], hash_func=h)
     first_args = [c[0] for c in calls][::-1]
-    assert first_args == [6, 0, 5, 2, int.from_bytes(b"output", "big"), int.from_bytes(b"pedersen", "big"), 100][:len(first_args)]
+    assert first_args == [7, 0, 5, 2, int.from_bytes(b"output", "big"), int.from_bytes(b"pedersen", "big"), 100]
