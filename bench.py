@@ -276,11 +276,13 @@ def main():
     from stark_perpetual_b200._lib import limbs_to_ints
     x0 = limbs_to_ints(x0_limbs)
     trace_host = ctx.pedersen_chain_trace(log_n, cfg["chain_log"], x0, ys_limbs)          # (25 N, 4) uint64
-    # every rank pins and uploads only its own block of columns (world = 1: the whole trace)
-    c0, c1 = pv.column_block()
+    # every rank pins and uploads only its own columns (world = 1: the whole trace; world > 1: the cyclic deal
+    # rank, rank + world, ... of csrc/sharded.cu)
     tr3 = trace_host.reshape(25, n, 4)
     outs = limbs_to_ints(tr3[[5 * l for l in range(5)], n - 1])
-    my = tr3[c0:c1] if c1 > c0 else tr3[:1]
+    my = tr3 if world == 1 else tr3[pv.cyclic_columns()]
+    if world > 1:
+        pv.setup_comm()
     pinned = torch.from_numpy(np.ascontiguousarray(my).view(np.int64)).pin_memory()
     trace = torch.empty_like(pinned, device=dev)
     trace.copy_(pinned)
@@ -290,13 +292,12 @@ def main():
     def step():
         if world == 1:
             return pv.prove_device(trace.data_ptr(), log_n, cfg["chain_log"], x0, cfg["n_queries"])
-        return pv.prove_sharded_device(trace, log_n, cfg["chain_log"], x0, outs, cfg["n_queries"])
+        return pv.prove_cyclic(None, log_n, cfg["chain_log"], x0, outs, cfg["n_queries"], device_ptr=trace.data_ptr())
 
     def step_e2e():
         if world == 1:
             return pv.prove_host(pinned.numpy().view(np.uint64), log_n, cfg["chain_log"], x0, cfg["n_queries"])
-        trace.copy_(pinned, non_blocking=True)
-        return pv.prove_sharded_device(trace, log_n, cfg["chain_log"], x0, outs, cfg["n_queries"])
+        return pv.prove_cyclic(pinned.numpy().view(np.uint64), log_n, cfg["chain_log"], x0, outs, cfg["n_queries"])
 
     def barrier():
         if world > 1:
@@ -329,10 +330,6 @@ def main():
     ms_per_step = float(t.item()) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     stage_ms /= args.steps
-    sharded_stages = None
-    if world > 1 and rank == 0:
-        # rank 0's view of the LAST proof: device ms and host wall ms per stage of the Python-sequenced driver
-        sharded_stages = {k: [round(v[0], 3), round(v[1], 3)] for k, v in pv.be.stage_times().items()}
 
     # ---- e2e: host trace through the C-ABI (pinned host memory): H2D + proof + D2H of the proof bytes
     e2e = None
@@ -368,9 +365,7 @@ def main():
                                parallelism=pv.parallelism()),
                 "proof_gen_s": ms_per_step * 1e-3, "proof_bytes": len(proof) if proof else None,
                 "proof_sha256": hashlib.sha256(proof).hexdigest() if proof else None,
-                "stage_ms": ({s: round(float(v), 4) for s, v in zip(STAGES, stage_ms)} if world == 1 else
-                             {k: v[0] for k, v in sharded_stages.items()}),
-                "stage_host_ms": None if world == 1 else {k: v[1] for k, v in sharded_stages.items()},
+                "stage_ms": {s: round(float(v), 4) for s, v in zip(STAGES, stage_ms)},
                 "algorithmic_muls_per_step": muls,
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
         # dominant kernel: k_ntt_pass (all launches of the two LDE stages).  SURVEY.md section 8(d): the compulsory HBM traffic

@@ -285,6 +285,20 @@ int spg_air_eval(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned c
 int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chain_log, const uint64_t* x0,
               unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
 
+/* ---- multi-GPU prover: one process per GPU, NCCL called from inside libspg (DESIGN.md "Multi-GPU") ----------------------
+ * spg_comm_unique_id: rank 0 obtains a 128-byte NCCL id and hands it to the other ranks by any means (the Python host side
+ * broadcasts it over torch.distributed); spg_comm_init joins the communicator on the context's GPU (world 1, 2, 4 or 8;
+ * world = 1 needs no id and no NCCL).  NCCL is bound at run time (the libnccl already in the process, or SPG_NCCL_LIB).
+ * spg_prove_sharded: cols_local = THIS rank's trace columns, dealt cyclically -- columns rank, rank + world, ... of the 25 --
+ * as [my_cols][2^log_n] canonical felts (host, or device with SPG_DEVICE_PTRS); x0, outs [5] canonical (host; outs = the
+ * public outputs, column 5 l at the last row).  Collective: every rank must call it with the same arguments.  Every
+ * rank receives the proof, byte-identical to spg_prove's.  Stages for spg_stage_ms as spg_prove (stage 0 includes the
+ * column exchange). */
+int spg_comm_unique_id(spg_ctx* ctx, uint8_t* id_out /*[128]*/);
+int spg_comm_init(spg_ctx* ctx, int rank, int world, const uint8_t* id /*[128], may be NULL when world == 1*/);
+int spg_prove_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+                      const uint64_t* outs, unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
+
 /* ---- stage-level entry points for the multi-GPU host driver (device pointers; DESIGN.md "Multi-GPU") ----------
  * A GPU owns n_cosets consecutive cosets starting at first_coset; its tables hold exactly those cosets,
  * [n_cosets][n_cols][rows].  Scalars (alpha, z, gamma, beta, x0, outs, oods) are canonical felts in host memory.

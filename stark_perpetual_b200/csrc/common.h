@@ -24,6 +24,11 @@ struct spg_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[8] = {nullptr};
   cudaEvent_t copy_gate = nullptr;
+  // multi-GPU (sharded.cu): NCCL communicator bound at run time, its stream and the pipeline's events
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ev[16] = {nullptr};
   double last_ms = 0.0;
   uint64_t launches = 0;
   std::string err;
@@ -186,8 +191,11 @@ int spg_bitrev_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_
 int spg_lde_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, unsigned log_blowup,
                    const uint64_t* offset_canon, Fp* out, Fp* coeffs, int mont = 0);
 // the two phases; mont != 0 additionally multiplies by R = 2^256 (canonical input -> Montgomery output)
+// out_stride: elements between output columns (0 = N: contiguous)
 int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, const uint64_t* offset_canon,
-                          Fp* coeffs, int mont = 0);
+                          Fp* coeffs, int mont = 0, size_t out_stride = 0);
+// sharded.cu
+void spg_comm_destroy(spg_ctx* ctx);
 // out_C / col0: the given columns are columns [col0, col0 + C) of a table with out_C columns per coset (0 = C)
 int spg_lde_cosets_device(spg_ctx* ctx, const Fp* coeffs, unsigned log_n, size_t C, unsigned log_blowup, size_t j0,
                           size_t nj, Fp* out, size_t out_C = 0, size_t col0 = 0);

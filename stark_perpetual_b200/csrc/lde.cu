@@ -57,16 +57,17 @@ static int ensure_scale_tables(spg_ctx* ctx, unsigned log_n, const uint64_t* off
 
 // phase A: columns -> scaled coefficient columns  g^k c_k  (bit-reversed order)
 int spg_lde_coeffs_device(spg_ctx* ctx, const Fp* trace, unsigned log_n, size_t C, const uint64_t* offset_canon,
-                          Fp* coeffs, int mont) {
+                          Fp* coeffs, int mont, size_t out_stride) {
   static const uint64_t three[4] = {3, 0, 0, 0};
   const uint64_t* off = offset_canon ? offset_canon : three;
   const Fp *lo, *hi, *inv_diag;
   int rc = ensure_scale_tables(ctx, log_n, off, mont, &lo, &hi, &inv_diag);
   if (rc) return rc;
   const size_t n = (size_t)1 << log_n;
+  if (out_stride == 0) out_stride = n;
   for (size_t c0 = 0; c0 < C; c0 += 32768) {
     const size_t nc = C - c0 < 32768 ? C - c0 : 32768;
-    rc = spg_ntt_device(ctx, trace + c0 * n, coeffs + c0 * n, log_n, nc, n, n, /*inverse=*/1, /*dit=*/0, 0,
+    rc = spg_ntt_device(ctx, trace + c0 * n, coeffs + c0 * out_stride, log_n, nc, n, out_stride, /*inverse=*/1, /*dit=*/0, 0,
                         lo, hi, inv_diag);
     if (rc) return rc;
   }

@@ -588,7 +588,31 @@ class Prover:
     def prove_sharded_device(self, cols_local, log_n, chain_log, x0, outs, n_queries=30, probe=None):
         return prove_sharded(self.be, self.comm, cols_local, log_n, chain_log, x0, outs, n_queries, probe=probe)
 
+    # ---- multi GPU, sequenced inside libspg (csrc/sharded.cu: NCCL called from C++, pipelined column exchange) --------
+    def setup_comm(self):
+        """Join libspg's own NCCL communicator: rank 0 creates the id, torch.distributed carries it to the others."""
+        if getattr(self, "_comm_ready", False):
+            return
+        uid = None
+        if self.world > 1:
+            import torch.distributed as dist
+            box = [self.ctx.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            uid = box[0]
+        self.ctx.comm_init(self.rank, self.world, uid)
+        self._comm_ready = True
+
+    def cyclic_columns(self):
+        """the trace columns this rank owns in the C++ sharded prover: rank, rank + world, ..."""
+        return list(range(self.rank, N_COLS, self.world))
+
+    def prove_cyclic(self, cols_local, log_n, chain_log, x0, outs, n_queries=30, device_ptr=None):
+        """cols_local: this rank's cyclic columns, (my_cols * N, 4) uint64 host array (or device_ptr).  Collective."""
+        self.setup_comm()
+        return self.ctx.prove_sharded(cols_local, log_n, chain_log, x0, outs, n_queries, device_ptr=device_ptr)
+
     def parallelism(self):
         if self.world == 1:
             return "1 GPU"
-        return "%d GPUs: columns -> all_gather(coefficients) -> %d coset(s) per GPU" % (self.world, BLOWUP // self.world)
+        return ("%d GPUs: columns dealt cyclically -> pipelined NCCL all-gather of coefficient columns -> %d coset(s) per GPU "
+                "(sequenced in libspg, csrc/sharded.cu)" % (self.world, BLOWUP // self.world))

@@ -64,3 +64,19 @@ def test_two_gpu_proof_is_byte_identical():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "MATCH" in out.stdout and "MISMATCH" not in out.stdout, out.stdout
+
+
+@pytest.mark.parametrize("log_n,chain_log", [(10, 1), (16, 2)])
+def test_cpp_sharded_prover_world1_equals_monolithic(ctx, log_n, chain_log):
+    """csrc/sharded.cu with a one-rank communicator (no NCCL involved): the cyclic column pipeline, chunked coset evaluation,
+    root / query assembly must reproduce spg_prove byte for byte, from host and from device buffers."""
+    import torch
+    x0, ys = bench_inputs(log_n)
+    trace = ctx.pedersen_chain_trace(log_n, chain_log, x0, ys)
+    n = 1 << log_n
+    outs = limbs_to_ints(trace.reshape(25, n, 4)[[5 * l for l in range(5)], n - 1])
+    want = ctx.prove(trace, log_n, chain_log, x0, n_queries=30)
+    ctx.comm_init(0, 1)
+    assert ctx.prove_sharded(trace, log_n, chain_log, x0, outs, 30) == want
+    dev = torch.from_numpy(trace.view(np.int64)).cuda()
+    assert ctx.prove_sharded(None, log_n, chain_log, x0, outs, 30, device_ptr=dev.data_ptr()) == want

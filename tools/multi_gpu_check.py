@@ -28,8 +28,18 @@ def main():
     x0 = limbs_to_ints(rand_felts(5, 11))
     ys = rand_felts(5 * ((1 << log_n) >> 9), 12)
     trace = ctx.pedersen_chain_trace(log_n, chain_log, x0, ys)
-    block, outs = pv.shard_host_trace(trace, log_n)
-    proof = pv.prove_sharded_device(block, log_n, chain_log, x0, outs, 30)
+    n = 1 << log_n
+    tr3 = trace.reshape(25, n, 4)
+    outs = limbs_to_ints(tr3[[5 * l for l in range(5)], n - 1])
+    mine = np.ascontiguousarray(tr3[pv.cyclic_columns()]).reshape(-1, 4)
+    proof = pv.prove_cyclic(mine, log_n, chain_log, x0, outs, 30)                 # host buffers: the e2e path
+    dev = torch.from_numpy(mine.view(np.int64)).cuda()
+    proof_dev = pv.prove_cyclic(None, log_n, chain_log, x0, outs, 30, device_ptr=dev.data_ptr())
+    assert proof_dev == proof, "device-pointer and host-pointer sharded proofs differ"
+    # the Python-sequenced stage driver (block column deal) must give the same bytes too
+    block, outs2 = pv.shard_host_trace(trace, log_n)
+    assert outs2 == outs
+    assert pv.prove_sharded_device(block, log_n, chain_log, x0, outs, 30) == proof, "Python stage driver differs"
     dist.barrier()
     if rank == 0:
         from oracle import stark
