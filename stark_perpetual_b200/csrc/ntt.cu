@@ -74,7 +74,14 @@ __device__ __forceinline__ void ntt_tile_steps(FpHalf* ws, const FpHalf* tws, in
   }
 }
 
-template <bool DIT, int LOG_R>
+// TMA_IN (A/B variant for contiguous passes, log_s = 0; SPG_NTT_TMA=1): the tile's 2^LOG_R x 32 bytes are fetched by ONE
+// bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier) into the workspace area in linear
+// element order; each thread then takes its four elements out of shared memory, applies the load-phase factor and, after
+// a CTA barrier, writes them back in the planar swizzled layout the butterflies use.  Measured against the per-thread
+// LDG path in DESIGN.md section 3.
+__device__ __forceinline__ uint32_t spg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool DIT, int LOG_R, bool TMA_IN>
 __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? 4 : 2) k_ntt_tile(NttPass P) {
   typedef NttTileCT<LOG_R> T;
   extern __shared__ uint4 smem_raw[];
@@ -82,9 +89,44 @@ __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? 4 : 2) k_ntt_t
   FpHalf* tws = ws + 2 * T::R;
   const int tid = threadIdx.x;
   const unsigned cta = blockIdx.x, col = blockIdx.y;
-  T::stage_twiddles(P, tws, tid);
+  if (TMA_IN) {
+    __shared__ __align__(8) unsigned long long mbar;
+    const uint32_t mb = spg_smem_u32(&mbar);
+    constexpr uint32_t BYTES = (uint32_t)T::R * 32u;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const Fp* src = P.in + col * P.in_col_stride + ((unsigned long long)cta << LOG_R);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(BYTES) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(spg_smem_u32(ws)), "l"(src), "r"(BYTES), "r"(mb) : "memory");
+    }
+    T::stage_twiddles(P, tws, tid);          // overlaps the copy
+    {
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mb) : "memory");
+    }
+    Fp x[4];
+    const Fp* lin = reinterpret_cast<const Fp*>(ws);
 #pragma unroll
-  for (int j = 0; j < 4; j++) T::template load<DIT>(P, ws, cta, col, T::io_row(tid, j));
+    for (int j = 0; j < 4; j++) {
+      const int r = T::io_row(tid, j);
+      x[j] = lin[r];
+      if (DIT) x[j] = T::G::apply_factors(P, x[j], cta, r, 0);
+    }
+    __syncthreads();                         // every element has left the linear image before the swizzled one overwrites it
+#pragma unroll
+    for (int j = 0; j < 4; j++) T::ws_put(ws, T::G::swz(T::io_row(tid, j)), x[j]);
+  } else {
+    T::stage_twiddles(P, tws, tid);
+#pragma unroll
+    for (int j = 0; j < 4; j++) T::template load<DIT>(P, ws, cta, col, T::io_row(tid, j));
+  }
   __syncthreads();
   ntt_tile_steps<DIT, LOG_R, 0>(ws, tws, tid);
 #pragma unroll
@@ -139,10 +181,12 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, NTT_LOG_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_LOG_WS) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
     attr_set = true;
   }
   NttPass passes[8];
@@ -165,11 +209,14 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
       const int smem_ct = (1 << log_ws) * 48;
       if (log_ws == 11) {
-        if (dit) k_ntt_tile<true, 11><<<grid, threads, smem_ct, ctx->stream>>>(P);
-        else k_ntt_tile<false, 11><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        else k_ntt_tile<false, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
+      } else if (ctx->ntt_tma_in && P.log_s == 0) {      // A/B variant: bulk asynchronous copy of the contiguous tile
+        if (dit) k_ntt_tile<true, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        else k_ntt_tile<false, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
       } else {
-        if (dit) k_ntt_tile<true, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P);
-        else k_ntt_tile<false, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        if (dit) k_ntt_tile<true, NTT_LOG_WS, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        else k_ntt_tile<false, NTT_LOG_WS, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
       }
     } else if (log_ws == 11) {
       if (dit) k_ntt_pass<true, 11><<<grid, threads, smem, ctx->stream>>>(P);
