@@ -74,7 +74,7 @@ __device__ __forceinline__ void ntt_tile_steps(FpHalf* ws, const FpHalf* tws, in
   }
 }
 
-// TMA_IN (A/B variant for contiguous passes, log_s = 0; SPG_NTT_TMA=1): the tile's 2^LOG_R x 32 bytes are fetched by ONE
+// TMA_IN (contiguous passes, log_s = 0; default, SPG_NTT_TMA=0 selects the per-thread LDG path): the tile's 2^LOG_R x 32 bytes are fetched by ONE
 // bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier) into the workspace area in linear
 // element order; each thread then takes its four elements out of shared memory, applies the load-phase factor and, after
 // a CTA barrier, writes them back in the planar swizzled layout the butterflies use.  Measured against the per-thread
@@ -211,7 +211,7 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
       if (log_ws == 11) {
         if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
         else k_ntt_tile<false, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-      } else if (ctx->ntt_tma_in && P.log_s == 0) {      // A/B variant: bulk asynchronous copy of the contiguous tile
+      } else if (ctx->ntt_tma_in && P.log_s == 0) {      // bulk asynchronous copy (TMA) of the contiguous tile
         if (dit) k_ntt_tile<true, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
         else k_ntt_tile<false, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
       } else {
