@@ -224,6 +224,72 @@ def orders_arm(args):
     return 0
 
 
+def multi_gpu_aux(ctx, pv, args, rank, world, dev, barrier):
+    """BASELINE.json configs[3] and [4] at N > 1, measured after the timed region: a full 2^22-row proof sharded over the
+    ranks (verified by the oracle on rank 0) and the 65536-order batch verification split n/N per rank (independent
+    units, no collective).  Every rank takes part; returns the object on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from conftest import rand_felts
+    from stark_perpetual_b200._lib import limbs_to_ints
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import aux_bench
+    out = {}
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    # ---- configs[3]: full proof of a 2^22-row trace
+    log_n = args.aux_log_n
+    n = 1 << log_n
+    x0 = limbs_to_ints(rand_felts(5, 2203))
+    trace = ctx.pedersen_chain_trace(log_n, args.chain_log, x0, rand_felts(5 * (n >> 9), 2204))
+    tr3 = trace.reshape(25, n, 4)
+    outs = limbs_to_ints(tr3[[5 * l for l in range(5)], n - 1])
+    mine = torch.from_numpy(np.ascontiguousarray(tr3[pv.cyclic_columns()]).view(np.int64)).to(dev)
+    del trace, tr3
+    proof = None
+    for _ in range(2):
+        proof = pv.prove_cyclic(None, log_n, args.chain_log, x0, outs, args.queries, device_ptr=mine.data_ptr())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream()
+    e0.record(stream)
+    for _ in range(3):
+        proof = pv.prove_cyclic(None, log_n, args.chain_log, x0, outs, args.queries, device_ptr=mine.data_ptr())
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / 3)
+    cfg = dict(workload_cfg(args), log_n=log_n)
+    row = {"log_n": log_n, "n_gpus": world, "ms": ms, "field_mul_per_s": proof_muls(cfg)[0] / (ms * 1e-3),
+           "proof_bytes": len(proof), "proof_sha256": hashlib.sha256(proof).hexdigest()}
+    if rank == 0 and not args.no_verify:
+        from oracle import stark as ostark
+        ostark.verify(proof)
+        row["verified_by_oracle"] = True
+    out["cfg3_proof_2^%d" % log_n] = row
+    del mine
+    torch.cuda.empty_cache()
+    # ---- configs[4]: the order batch split across the ranks
+    n_total = args.orders
+    n_loc = n_total // world
+    orders, r, s_, px, expect, _bad, _msgs, _nk, _sb = aux_bench.signed_orders(ctx, n_loc, 1005 + rank)
+    ctx.limit_order_verify(orders, r, s_, px)
+    barrier()
+    t0 = time.perf_counter()
+    st = ctx.limit_order_verify(orders, r, s_, px)
+    k_ms = ctx.last_kernel_ms
+    barrier()
+    wall = max_over_ranks(1e3 * (time.perf_counter() - t0))
+    k_ms = max_over_ranks(k_ms)
+    ok = max_over_ranks(0.0 if np.array_equal(st, expect) else 1.0) == 0.0
+    out["cfg4_orders_split"] = {"n": n_loc * world, "per_gpu": n_loc, "n_gpus": world, "ms": k_ms, "e2e_ms": wall,
+                                "orders_per_s": n_loc * world / (k_ms * 1e-3), "e2e_orders_per_s": n_loc * world / (wall * 1e-3),
+                                "statuses_as_expected": ok, "parallelism": "independent units, contiguous n/G split, no collective"}
+    return out if rank == 0 else None
+
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -240,6 +306,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the aux object (BASELINE configs 0, 1, 4 after the timed region)")
+    ap.add_argument("--aux-log-n", dest="aux_log_n", type=int, default=22, help="N > 1: size of the configs[3] proof in aux")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle verification of one proof")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -347,6 +414,7 @@ def main():
         e2e = {"ms_per_step": float(t.item()) / args.steps, "h2d_bytes_per_step": 25 * n * 32,   # summed over ranks
                "d2h_bytes_per_step": len(pr2) if pr2 is not None else 0}
 
+    line = None
     if rank == 0:
         muls, per_stage = proof_muls(cfg)
         peaks = {}
@@ -436,6 +504,25 @@ def main():
                                                 n_orders=args.orders, hbm_gbs=peak)
             except Exception as e:          # the headline line must survive a failure of the side measurements
                 line["aux"] = {"error": repr(e)[:500]}
+    if world > 1 and not args.no_aux:
+        # BASELINE.json configs[3] (2^22 proof) and [4] (order batch split) at this N, after the timed region.  A watchdog
+        # makes sure the headline line is printed even if a rank gets stuck in a collective of the side measurement.
+        def give_up():
+            if rank == 0:
+                line["aux"] = {"error": "multi-GPU aux timed out"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+        dog = threading.Timer(300.0, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            aux_multi = multi_gpu_aux(ctx, pv, args, rank, world, dev, barrier)
+        except Exception as e:
+            aux_multi = {"error": repr(e)[:500]}
+        dog.cancel()
+        if rank == 0:
+            line["aux"] = aux_multi
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

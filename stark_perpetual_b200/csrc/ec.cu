@@ -57,7 +57,10 @@ __device__ __forceinline__ void load_canon(const uint64_t* src, uint32_t (&x)[8]
 #ifndef PEDERSEN_MIN_CTAS
 #define PEDERSEN_MIN_CTAS 1
 #endif
-__global__ void __launch_bounds__(128, PEDERSEN_MIN_CTAS) k_pedersen_chain(const uint64_t* __restrict__ elems, int chain_len,
+#ifndef PEDERSEN_THREADS
+#define PEDERSEN_THREADS 128
+#endif
+__global__ void __launch_bounds__(PEDERSEN_THREADS, PEDERSEN_MIN_CTAS) k_pedersen_chain(const uint64_t* __restrict__ elems, int chain_len,
                                                         uint64_t* __restrict__ out, uint8_t* __restrict__ status,
                                                         size_t n, const APoint* __restrict__ cp,
                                                         uint64_t* __restrict__ out_y = nullptr,
@@ -129,7 +132,7 @@ __global__ void k_limbs_to_be32(const uint64_t* __restrict__ in, uint8_t* __rest
 int spg_pedersen_chain_device(spg_ctx* ctx, const uint64_t* elems, int chain_len, uint64_t* out, uint8_t* status,
                               size_t n, uint64_t* out_y = nullptr, const uint64_t* second = nullptr) {
   if (n == 0) return SPG_OK;
-  const int threads = 128;
+  const int threads = PEDERSEN_THREADS;
   k_pedersen_chain<<<(unsigned)((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
       elems, chain_len, out, status, n, (const APoint*)ctx->const_points, out_y, second);
   SPG_LAUNCH_CHECK();

@@ -135,6 +135,38 @@ def order_dict(o, i):
     return d
 
 
+def signed_orders(ctx, n, seed, n_keys=1024):
+    """n synthetic limit orders, signed on the device (spg_limit_order_msg_batch + spg_sign_batch) with n_keys distinct keys,
+    1 % of them corrupted afterwards (a flipped bit of r, s, the key or an order field).  Returns (orders, r, s, pub_x,
+    expected statuses, corrupted indices, message hashes, n_keys, bad-status count of the signing calls)."""
+    from conftest import rand_felts
+    orders = synthetic_orders(n, seed)
+    privs = rand_felts(n_keys, seed + 72)
+    privs[:, 3] &= np.uint64(0x03ffffffffffffff)
+    privs[:, 0] |= np.uint64(1)
+    pubs, _ = ctx.private_to_stark_key(privs)
+    kidx = np.arange(n) % n_keys
+    msgs, mst = ctx.limit_order_msg(orders)
+    r, s, sst = ctx.sign(msgs, privs[kidx])
+    px = pubs[kidx].copy()
+    g = np.random.Generator(np.random.PCG64(seed + 94))
+    bad = g.choice(n, size=max(1, n // 100), replace=False)
+    expect = np.ones(n, dtype=np.uint8)
+    for k, i in enumerate(bad):
+        which = k % 4
+        bit = np.uint64(1) << np.uint64(int(g.integers(0, 60)))
+        if which == 0:
+            r[i, 0] ^= bit
+        elif which == 1:
+            s[i, 0] ^= bit
+        elif which == 2:
+            px[i, 0] ^= bit
+        else:
+            orders["amount_collateral"][i] ^= bit
+        expect[i] = 0
+    return orders, r, s, px, expect, bad, msgs, n_keys, int((sst != 0).sum()) + int((mst != 0).sum())
+
+
 def measure(ctx, sm_mhz=1965.0, with_reference=True, n_orders=65536, hbm_gbs=6452.8):
     from conftest import rand_felts
     from oracle.pedersen import pedersen_hash as o_pedersen
@@ -170,31 +202,7 @@ def measure(ctx, sm_mhz=1965.0, with_reference=True, n_orders=65536, hbm_gbs=645
         del v
     # ---- configs[4]: n_orders limit orders; (a) validly signed on the device with 1 % corrupted, (b) random signatures
     n = n_orders
-    orders = synthetic_orders(n, 1005)
-    n_keys = 1024
-    privs = rand_felts(n_keys, 77)
-    privs[:, 3] &= np.uint64(0x03ffffffffffffff)
-    privs[:, 0] |= np.uint64(1)
-    pubs, _ = ctx.private_to_stark_key(privs)
-    kidx = np.arange(n) % n_keys
-    msgs, mst = ctx.limit_order_msg(orders)
-    r, s, sst = ctx.sign(msgs, privs[kidx])
-    px = pubs[kidx].copy()
-    g = np.random.Generator(np.random.PCG64(99))
-    bad = g.choice(n, size=max(1, n // 100), replace=False)
-    expect = np.ones(n, dtype=np.uint8)
-    for k, i in enumerate(bad):                      # flip one bit of r, s, the key or an order field (-> another message)
-        which = k % 4
-        bit = np.uint64(1) << np.uint64(int(g.integers(0, 60)))
-        if which == 0:
-            r[i, 0] ^= bit
-        elif which == 1:
-            s[i, 0] ^= bit
-        elif which == 2:
-            px[i, 0] ^= bit
-        else:
-            orders["amount_collateral"][i] ^= bit
-        expect[i] = 0
+    orders, r, s, px, expect, bad, msgs, n_keys, sign_bad = signed_orders(ctx, n, 1005)
     st, e2e_ms = _timed(lambda: ctx.limit_order_verify(orders, r, s, px), reps=3)
     k_ms = ctx.last_kernel_ms
     pm, pr = float(_popcounts(msgs[:2048]).mean()), float(_popcounts(r[:2048]).mean())
@@ -204,7 +212,7 @@ def measure(ctx, sm_mhz=1965.0, with_reference=True, n_orders=65536, hbm_gbs=645
            "muls_per_order": muls_valid, "field_mul_per_s": n * muls_valid / (k_ms * 1e-3),
            "frac_of_int_ceiling": n * muls_valid / (k_ms * 1e-3) / ceil,
            "status_counts": {int(a): int(b) for a, b in zip(*np.unique(st, return_counts=True))},
-           "statuses_as_expected": bool(np.array_equal(st, expect)), "sign_bad_status": int((sst != 0).sum()) + int((mst != 0).sum())}
+           "statuses_as_expected": bool(np.array_equal(st, expect)), "sign_bad_status": sign_bad}
     aux["cfg4_orders_valid_mix"] = row
     rr, ss = rand_felts(n, 32), rand_felts(n, 33)
     for a in (rr, ss):
