@@ -436,7 +436,7 @@ def main():
                 "stage_ms": {s: round(float(v), 4) for s, v in zip(STAGES, stage_ms)},
                 "algorithmic_muls_per_step": muls,
                 "gpu_launches": launches_per_step * args.steps, "clocks": clocks}
-        # dominant kernel: k_ntt_pass (all launches of the two LDE stages).  SURVEY.md section 8(d): the compulsory HBM traffic
+        # dominant kernel: k_ntt_tile (all launches of the two LDE stages).  SURVEY.md section 8(d): the compulsory HBM traffic
         # of a size-N transform is 64 N bytes (read once, write once), of the blowup-8 LDE 32 N C (1 + 8); a transform of
         # 2^log_n > 2^10 points takes two launches (passes), so one launch is charged half a transform: 32 N bytes per
         # column.  `frac` is that figure; `per_pass` charges every launch the 64 N bytes it really moves (two-pass
@@ -450,7 +450,7 @@ def main():
             ach = alg_bytes / (ntt_ms * 1e-3) / 1e9
             traffic, traffic_src = None, None
             try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_ntt_pass"]
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_ntt_tile"]
                 if log_n == 20:
                     traffic = tj["dram_bytes_per_launch"]
                     traffic_src = "static: profiles/ncu_traffic.json (%s)" % tj.get("source", "ncu --set full capture of this kernel")
@@ -461,7 +461,7 @@ def main():
             # (32 lanes/clk/SM, measured: profiles/r1g_microbench_imad.json); a multiplication needs 64 of them
             sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
             imad_peak = 148 * 32 * sm_mhz * 1e6
-            line["roofline"] = {"bound": "hbm", "kernel": "k_ntt_pass", "achieved": ach, "peak": peak, "unit": "GB/s",
+            line["roofline"] = {"bound": "hbm", "kernel": "k_ntt_tile", "achieved": ach, "peak": peak, "unit": "GB/s",
                                 "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                                 "algorithmic_bytes_per_launch": alg_bytes / n_launch,
                                 "per_pass": {"bytes_per_launch": pass_bytes / n_launch,

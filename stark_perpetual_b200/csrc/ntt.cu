@@ -141,13 +141,13 @@ __global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
   out[col * n + spg_bitrev((unsigned)r, (int)log_n)] = in[i];
 }
 
-// diag_table[(c << log_r) | k] = omega_{2^26}^(+- k * (c * ec + e0)) for the pass P (k = bit-reversed row), optionally
-// times row_factor[bitrev_R(k)] (the LDE folds the per-tile part of its g^k scaling into the inverse transform's table)
+// diag_table[(c << log_r) | r] = omega_{2^26}^(+- bitrev_R(r) * (c * ec + e0)) for the pass P, optionally times
+// row_factor[r] (the LDE folds the per-tile part of its g^k scaling into the inverse transform's table)
 __global__ void k_build_diag_table(NttPass P, Fp* __restrict__ table, const Fp* __restrict__ row_factor) {
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ((size_t)1 << (P.log_r + P.log_s))) return;
   Fp v = NttTile<NTT_LOG_WS, NTT_LOG_EPT>::diag_entry(P, idx);
-  if (row_factor) v = fp_mul(v, row_factor[spg_bitrev((unsigned)(idx & ((1ull << P.log_r) - 1)), P.log_r)]);
+  if (row_factor) v = fp_mul(v, row_factor[idx & ((1ull << P.log_r) - 1)]);
   table[idx] = fp_reduce(v);
 }
 

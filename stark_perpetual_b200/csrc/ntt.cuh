@@ -44,7 +44,8 @@ struct NttPass {
   const Fp* scale_lo;          // R entries
   const Fp* scale_hi;          // B entries
   int final_pass;              // last pass of the transform: store canonical values (otherwise any lazy representative)
-  // optional direct table of the diagonal factor: diag_table[(c << log_r) | bitrev_R(r)]
+  // optional direct table of the diagonal factor: diag_table[(c << log_r) | r]   (ROW order, so that a warp's consecutive
+  // rows read consecutive entries -- coalesced)
   // = omega_{2^26}^(+- bitrev_R(r) * (c * ec + e0)) [* an extra per-row factor folded in by the LDE, see lde.cu]; saves the
   // two-level lookup's multiplication (null: use uniA/uniB).  The contiguous pass of a coset transform has c = 0: its
   // table holds just 2^log_r entries.
@@ -130,9 +131,9 @@ struct NttTile {
     return fp_mul_lazy(P.uniA[hi], P.uniB[lo]);
   }
 
-  // entry idx = (c << log_r) | k of the direct diagonal table of pass P (k = bit-reversed row)
+  // entry idx = (c << log_r) | r of the direct diagonal table of pass P
   static SPG_HD Fp diag_entry(const NttPass& P, unsigned long long idx) {
-    const unsigned long long k = idx & ((1ull << P.log_r) - 1), c = idx >> P.log_r;
+    const unsigned long long k = spg_bitrev((unsigned)(idx & ((1ull << P.log_r) - 1)), P.log_r), c = idx >> P.log_r;
     unsigned long long E = k * (c * P.ec + P.e0);
     if (P.inverse) E = (0ull - E);
     return uni_pow(P, E);
@@ -145,7 +146,7 @@ struct NttTile {
     if (P.use_diag) {
       unsigned long long k = spg_bitrev((unsigned)r, P.log_r);
       if (P.diag_table) {
-        x = fp_mul_lazy(x, P.diag_table[((unsigned long long)c << P.log_r) | k]);
+        x = fp_mul_lazy(x, P.diag_table[((unsigned long long)c << P.log_r) | (unsigned)r]);
       } else {
         unsigned long long E = k * ((unsigned long long)c * P.ec + P.e0);
         if (P.inverse) E = (0ull - E);

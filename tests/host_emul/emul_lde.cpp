@@ -96,7 +96,7 @@ int main(int argc, char** argv) {
     std::vector<Fp> t((size_t)1 << (P.log_r + P.log_s));
     for (size_t idx = 0; idx < t.size(); idx++) {
       Fp v = Tile::diag_entry(P, idx);
-      if (row_factor) v = fp_mul(v, row_factor[spg_bitrev((unsigned)(idx & (((size_t)1 << P.log_r) - 1)), P.log_r)]);
+      if (row_factor) v = fp_mul(v, row_factor[idx & (((size_t)1 << P.log_r) - 1)]);
       t[idx] = fp_reduce(v);
     }
     return t;
