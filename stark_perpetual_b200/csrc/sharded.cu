@@ -323,7 +323,18 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     uint64_t three[4] = {3, 0, 0, 0}, off[4];
     const Fp g = spg_host_from_u64(three);
     spg_host_to_u64(fp_inv(fp_mul(fp_mul(g, g), g)), off);
-    if ((rc = spg_lde_coeffs_device(ctx, hev, log_n, 4, off, h_coef, /*mont=*/0))) return rc;
+    if (world == 1) {
+      if ((rc = spg_lde_coeffs_device(ctx, hev, log_n, 4, off, h_coef, /*mont=*/0))) return rc;
+    } else {
+      // the four chunk columns are interpolated by four (or two) different ranks and broadcast: 32 MB per column at 2^20
+      // against a replicated 4-column inverse transform
+      for (int m = rank; m < 4; m += world)
+        if ((rc = spg_lde_coeffs_device(ctx, hev + (size_t)m * n, log_n, 1, off, h_coef + (size_t)m * n, /*mont=*/0))) return rc;
+      SPG_NCCL(g_nccl.GroupStart());
+      for (int m = 0; m < 4; m++)
+        if ((rc = bcast(ctx, h_coef + (size_t)m * n, n * sizeof(Fp), m % world, S))) return rc;
+      SPG_NCCL(g_nccl.GroupEnd());
+    }
     if ((rc = spg_lde_cosets_device(ctx, h_coef, log_n, 4, SPG_LOG_BLOWUP, first, cs, h_lde))) return rc;
   }
   spg_stage_end(ctx, ST_HLDE);
