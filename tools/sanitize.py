@@ -38,6 +38,27 @@ def main():
     ostark.verify(proof, min_queries=8)
     out, st = ctx.pedersen_hash2(ints_to_limbs([1, 2]), ints_to_limbs([3, 4]))
     assert limbs_to_ints(out) == [pedersen_hash(1, 3), pedersen_hash(2, 4)]
+    # round-2 kernels: the C++ sharded prover with a one-rank communicator, math_utils ops, state trees, hash chain
+    tr10 = pv.witness(10, 1, x0, ys)
+    outs = limbs_to_ints(tr10.reshape(25, 1024, 4)[[5 * l for l in range(5)], 1023])
+    ctx.comm_init(0, 1)
+    assert ctx.prove_sharded(tr10, 10, 1, x0, outs, 8) == proof
+    if big:
+        one = rand_felts(1 << 20, 9)
+        assert np.array_equal(ctx.lde(one, 20, 1, 3)[:1 << 20], clib.lde(one, 20, 1, 3)[:1 << 20])     # k_ntt_tile, both passes, TMA load
+    g = [int(v, 16) for v in ("1ef15c18599971b7beced415a40f0c7deacfd9b0d1819e03d723d8bc943cfca", "5668060aa49730b7be4801df46ec62de53ecd11abe43a32873000c36e8dc1f")]
+    xy = ints_to_limbs(g).reshape(1, 8)
+    o2, st2 = ctx.ec_op(2, np.tile(xy, (3, 1)), ints_to_limbs([5, 2**200 + 3, 1]))
+    assert not st2.any() and np.array_equal(o2[2], xy[0])
+    pk = ints_to_limbs([7, 9])
+    h, st3 = ctx.position_hash(pk, np.array([1, -2], dtype=np.int64), np.array([0, 1, 1], dtype=np.uint64),
+                               np.array([[5, 0]], dtype=np.uint64), np.array([3], dtype=np.int64), np.array([-4], dtype=np.int64))
+    assert not st3.any()
+    sib = ctx.merkle_update_siblings(6, [3, 9, 10])
+    pr, nr, st4, _ = ctx.merkle_multi_update(6, [3, 9, 10], rand_felts(3, 1), rand_felts(3, 2), rand_felts(len(sib), 3))
+    assert st4 == 0
+    oc, st5 = ctx.hash_chain_rfold(rand_felts(6, 4), 3)
+    assert not st5.any()
     print("sanitize workload OK")
 
 
