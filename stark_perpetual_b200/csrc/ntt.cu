@@ -81,8 +81,11 @@ __device__ __forceinline__ void ntt_tile_steps(FpHalf* ws, const FpHalf* tws, in
 // LDG path in DESIGN.md section 3.
 __device__ __forceinline__ uint32_t spg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#ifndef NTT_TILE_MIN_CTAS
+#define NTT_TILE_MIN_CTAS 4       // CTAs per SM of the 2^10 tile: 4 = 64 registers (measured against 3 = 80: DESIGN.md section 3)
+#endif
 template <bool DIT, int LOG_R, bool TMA_IN>
-__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? 4 : 2) k_ntt_tile(NttPass P) {
+__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2) k_ntt_tile(NttPass P) {
   typedef NttTileCT<LOG_R> T;
   extern __shared__ uint4 smem_raw[];
   FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
