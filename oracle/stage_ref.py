@@ -30,6 +30,11 @@ FILES = [
     "services/perpetual/public/perpetual_messages.py", "services/perpetual/public/perpetual_messages_test.py",
     "services/perpetual/public/perpetual_messages_precomputed.json",
     "services/perpetual/public/stark_cli.py", "services/perpetual/public/stark_cli_test.py",
+    # the program-hash test (row f-2): run unchanged against compat's hash_program on a synthetic compiled program
+    "starkware/cairo/__init__.py", "starkware/cairo/bootloaders/__init__.py",
+    "starkware/cairo/bootloaders/program_hash_test_utils.py",
+    "services/perpetual/cairo/__init__.py", "services/perpetual/cairo/program_hash_test.py",
+    "services/perpetual/cairo/program_hash.json",
 ]
 # fixtures the Bazel test rule places beside stark_cli_test.py
 BESIDE_CLI_TEST = [

@@ -131,3 +131,38 @@ def test_reference_tests_run_unchanged(ctx, test_file):
                          env=env, capture_output=True, text=True, cwd=ROOT, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout, out.stdout[-2000:]
+
+
+def test_reference_program_hash_test_runs_unchanged(ctx, tmp_path):
+    """Row f-2: the reference's program_hash_test.py + program_hash_test_utils.py (:7-21), byte for byte, against compat's
+    compute_program_hash_chain (libspg underneath).  The compiled perpetual program cannot be produced here (no Cairo
+    compiler), so the test directory gets a SYNTHETIC compiled-program JSON and the hash the oracle restatement gives for it;
+    a wrong expected hash must make the reference's assertion fire."""
+    import random
+    import shutil
+    from oracle import hash_chain as ohc
+    src = refenv.ref_src()
+    if src is None or not os.path.exists(os.path.join(src, "services", "perpetual", "cairo", "program_hash_test.py")):
+        staged = os.path.join(ROOT, "oracle", "_ref", "src")
+        if not os.path.exists(os.path.join(staged, "services", "perpetual", "cairo", "program_hash_test.py")):
+            pytest.skip("reference program-hash test not staged")
+        src = staged
+    rng = random.Random(99)
+    builtins = ["output", "pedersen", "range_check", "ecdsa", "bitwise"]
+    data = [rng.randrange(P) for _ in range(300)]
+    work = tmp_path / "services" / "perpetual" / "cairo"
+    work.mkdir(parents=True)
+    shutil.copyfile(os.path.join(src, "services", "perpetual", "cairo", "program_hash_test.py"), work / "program_hash_test.py")
+    (work / "perpetual_cairo_compiled.json").write_text(json.dumps(
+        {"builtins": builtins, "data": [hex(v) for v in data], "identifiers": {"__main__.main": {"pc": 42, "type": "function"}},
+         "prime": hex(P)}))
+    want = ohc.compute_program_hash_chain(builtins, 42, data)
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, COMPAT, src]))
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "--import-mode=importlib", "--rootdir", str(work),
+           "-c", "/dev/null", str(work / "program_hash_test.py")]
+    for expected, ok in ((hex(want), True), (hex(want ^ 1), False)):
+        (work / "program_hash.json").write_text(json.dumps({"program_hash": expected}, indent=4) + "\n")
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, cwd=ROOT, timeout=600)
+        assert (out.returncode == 0) == ok, out.stdout[-2000:] + out.stderr[-1000:]
+        if not ok:
+            assert "Wrong program hash" in out.stdout

@@ -159,3 +159,36 @@ def test_stage_driver_equals_monolithic_prover(ctx, log_n, chain_log):
     got = pv.prove_sharded_device(block, log_n, chain_log, x0, outs, n_queries=9)
     assert got == want
     stark.verify(got, min_queries=9)
+
+
+def test_file_level_prover_cli(ctx, tmp_path):
+    """python -m stark_perpetual_b200.cpu_air_prover with the flag set of the prover CLI that follows cairo-run in the
+    reference's build (cairo_cmake_rules.cmake:72-110): files in, proof file out, accepted by the oracle verifier."""
+    import json
+    import os
+    import subprocess
+    import sys
+    log_n, chain_log = 10, 1
+    x0, ys = make_inputs(log_n, 123)
+    ys_limbs(ys).astype("<u8").tofile(tmp_path / "ys.bin")
+    (tmp_path / "public.json").write_text(json.dumps({"log_n": log_n, "chain_log": chain_log, "x0": [hex(v) for v in x0]}))
+    (tmp_path / "private.json").write_text(json.dumps({"ys_path": str(tmp_path / "ys.bin")}))
+    (tmp_path / "params.json").write_text(json.dumps({"n_queries": 30}))
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    out = subprocess.run([sys.executable, "-m", "stark_perpetual_b200.cpu_air_prover", "--out_file", str(tmp_path / "proof.bin"),
+                          "--private_input_file", str(tmp_path / "private.json"), "--public_input_file", str(tmp_path / "public.json"),
+                          "--parameter_file", str(tmp_path / "params.json")], cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    proof = (tmp_path / "proof.bin").read_bytes()
+    st = stark.verify(proof)
+    pub = json.loads((tmp_path / "proof.bin.public.json").read_text())
+    assert st["x0"] == x0 and [hex(v) for v in st["outs"]] == pub["outs"]
+    # the trace-file form gives the same proof
+    tr = ctx.pedersen_chain_trace(log_n, chain_log, x0, ys_limbs(ys))
+    tr.astype("<u8").tofile(tmp_path / "trace.bin")
+    (tmp_path / "private2.json").write_text(json.dumps({"trace_path": str(tmp_path / "trace.bin")}))
+    out = subprocess.run([sys.executable, "-m", "stark_perpetual_b200.cpu_air_prover", "--out_file", str(tmp_path / "proof2.bin"),
+                          "--private_input_file", str(tmp_path / "private2.json"), "--public_input_file", str(tmp_path / "public.json")],
+                         cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert (tmp_path / "proof2.bin").read_bytes() == proof
