@@ -77,7 +77,7 @@ int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int 
   const size_t per_cta_min = INV_THREADS;
   int ch = 1;
   if (n > per_cta_min * 16) {
-    const int groups = (n_a % 3 == 0) ? n_a / 3 : n_a;
+    const int groups = (n_a % 3 == 0) ? n_a / 3 : (n_a % 2 == 0) ? n_a / 2 : n_a;
     const double slots = (double)ctx->sm_count * 3;
     for (int waves = 1; waves <= 64; waves++) {
       const double tiles_f = waves * slots / ((double)nj * groups);
@@ -92,6 +92,9 @@ int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int 
   if (n_a % 3 == 0) {
     dim3 grid(tiles, (unsigned)nj, (unsigned)(n_a / 3));
     k_inv_x_minus<3><<<grid, INV_THREADS, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
+  } else if (n_a % 2 == 0) {
+    dim3 grid(tiles, (unsigned)nj, (unsigned)(n_a / 2));
+    k_inv_x_minus<2><<<grid, INV_THREADS, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
   } else {
     dim3 grid(tiles, (unsigned)nj, (unsigned)n_a);
     k_inv_x_minus<1><<<grid, INV_THREADS, 0, ctx->stream>>>(log_n, j0, jstep, nj, d_A, out, ch, host_gen(), ctx->uniA, ctx->uniB);
@@ -101,14 +104,17 @@ int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int 
 }
 
 // ------------------------------------------------------------------ DEEP quotient
+// Q(x) = (A(x) - K0) / (x - z) + (gamma^25 A(x) - K1) / (x - z w) + (C(x) - K2) / (x - z^4),  A = sum_c gamma^c T_c,
+// C = sum_m gamma^(50+m) H_m.  Only TWO inverse tables are needed: the points of a coset are x_i = x_0 w^i, so
+// x_i - z w = w (x_{i-1} - z) and 1 / (x_i - z w) = w^-1 / (x_{i-1} - z) -- the previous row of the first table; the
+// factor w^-1 is folded into the constants (G1 = gamma^25 / w, K1' = K1 / w).  inv2: [2][n_cosets][N] = 1/(x - z), 1/(x - z^4).
 __global__ void __launch_bounds__(256) k_deep(unsigned log_n, const Fp* __restrict__ t_lde, const Fp* __restrict__ h_lde,
-                                              const Fp* __restrict__ inv3, const Fp* __restrict__ gamma,
+                                              const Fp* __restrict__ inv2, const Fp* __restrict__ gamma,
                                               const Fp* __restrict__ K, Fp* __restrict__ out, int n_cosets) {
   const size_t n = (size_t)1 << log_n;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n_cosets * n) return;
   const size_t j = idx >> log_n, i = idx & (n - 1);
-  // sum_c gamma^(25+c) T_c = gamma^25 * sum_c gamma^c T_c: one pass over the 25 columns serves both quotients.
   // Lazy accumulation (fp.cuh): products are below 2p, twelve of them are summed before a partial reduction.
   Fp a = fp_zero(), c = fp_zero();
   const Fp* tp = t_lde + (j * SPG_AIR_COLS << log_n) + i;
@@ -118,21 +124,39 @@ __global__ void __launch_bounds__(256) k_deep(unsigned log_n, const Fp* __restri
     if (col % 12 == 11) a = fp_partial(a);
   }
   a = fp_partial(a);
-  Fp b = fp_mul(a, gamma[SPG_AIR_COLS]);
+  Fp b = fp_mul(a, gamma[SPG_AIR_COLS]);             // gamma^25 / w
   const Fp* hp = h_lde + (j * 4 << log_n) + i;
 #pragma unroll
   for (int m = 0; m < 4; m++) c = fp_add_raw(c, fp_mul_lazy(hp[(size_t)m << log_n], gamma[2 * SPG_AIR_COLS + m]));
   c = fp_partial(c);
   a = fp_sub(a, K[0]); b = fp_sub(b, K[1]); c = fp_sub(c, K[2]);
-  const Fp i1 = inv3[idx], i2 = inv3[idx + (size_t)n_cosets * n], i3 = inv3[idx + 2 * (size_t)n_cosets * n];
+  const Fp i1 = inv2[idx], i2 = inv2[(j << log_n) + ((i + n - 1) & (n - 1))], i3 = inv2[idx + (size_t)n_cosets * n];
   Fp q = fp_add(fp_add(fp_mul(a, i1), fp_mul(b, i2)), fp_mul(c, i3));
   out[idx] = fp_reduce(q);
 }
 
-int spg_deep_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, const Fp* inv3, const Fp* d_gamma,
-                    const Fp* d_K, Fp* out, int n_cosets) {
+// The whole DEEP stage on n_cosets consecutive cosets starting at first_coset: constants on the host, two batched
+// inverse tables, the quotient kernel.  z, gamma, oods[54]: Montgomery; inv_scratch: 2 n_cosets N felts; d_small: >= 64.
+int spg_deep_stage_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, int first_coset, int n_cosets,
+                          const Fp& z, const Fp& gamma, const Fp* oods, Fp* inv_scratch, Fp* d_small, Fp* out) {
+  const int C = SPG_AIR_COLS;
+  const Fp wn = spg_host_root_of_unity((int)log_n), wn_inv = fp_inv(wn), z4 = fp_sqr(fp_sqr(z));
+  Fp gp[SPG_N_OODS + 5];
+  gp[0] = fp_one();
+  for (int k = 1; k < SPG_N_OODS; k++) gp[k] = fp_mul(gp[k - 1], gamma);
+  Fp K[3] = {fp_zero(), fp_zero(), fp_zero()};
+  for (int c = 0; c < C; c++) { K[0] = fp_add(K[0], fp_mul(gp[c], oods[c])); K[1] = fp_add(K[1], fp_mul(gp[C + c], oods[C + c])); }
+  for (int m = 0; m < 4; m++) K[2] = fp_add(K[2], fp_mul(gp[2 * C + m], oods[2 * C + m]));
+  gp[C] = fp_mul(gp[C], wn_inv);                      // the kernel uses gamma[25] only as the factor of the second quotient
+  gp[SPG_N_OODS] = K[0]; gp[SPG_N_OODS + 1] = fp_mul(K[1], wn_inv); gp[SPG_N_OODS + 2] = K[2];
+  gp[SPG_N_OODS + 3] = z; gp[SPG_N_OODS + 4] = z4;
+  SPG_CUDA(cudaMemcpyAsync(d_small, gp, sizeof(gp), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));       // gp is a stack object
+  int rc = spg_inv_x_minus_device(ctx, log_n, first_coset, 1, n_cosets, d_small + SPG_N_OODS + 3, 2, inv_scratch);
+  if (rc) return rc;
   const size_t total = (size_t)n_cosets << log_n;
-  k_deep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_lde, h_lde, inv3, d_gamma, d_K, out, n_cosets);
+  k_deep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_lde, h_lde, inv_scratch, d_small, d_small + SPG_N_OODS, out,
+                                                                   n_cosets);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }

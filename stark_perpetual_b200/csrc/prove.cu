@@ -168,22 +168,9 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
   }
   // ---- 4. DEEP quotient
   const Fp gamma = ch.draw_felt();
-  {
-    Fp gp[SPG_N_OODS + 6];
-    gp[0] = fp_one();
-    for (int k = 1; k < SPG_N_OODS; k++) gp[k] = fp_mul(gp[k - 1], gamma);
-    Fp K[3] = {fp_zero(), fp_zero(), fp_zero()};
-    for (int c = 0; c < C; c++) { K[0] = fp_add(K[0], fp_mul(gp[c], oods[c])); K[1] = fp_add(K[1], fp_mul(gp[C + c], oods[C + c])); }
-    for (int m = 0; m < 4; m++) K[2] = fp_add(K[2], fp_mul(gp[2 * C + m], oods[2 * C + m]));
-    gp[SPG_N_OODS] = K[0]; gp[SPG_N_OODS + 1] = K[1]; gp[SPG_N_OODS + 2] = K[2];
-    gp[SPG_N_OODS + 3] = z; gp[SPG_N_OODS + 4] = zw; gp[SPG_N_OODS + 5] = z4;
-    SPG_CUDA(cudaMemcpyAsync(d_small, gp, sizeof(gp), cudaMemcpyHostToDevice, ctx->stream));
-    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    spg_stage_begin(ctx, ST_DEEP);
-    if ((rc = spg_inv_x_minus_device(ctx, log_n, 0, 1, 8, d_small + SPG_N_OODS + 3, 3, inv3))) return rc;
-    if ((rc = spg_deep_device(ctx, log_n, t_lde, h_lde, inv3, d_small, d_small + SPG_N_OODS, layer0))) return rc;
-    spg_stage_end(ctx, ST_DEEP);
-  }
+  spg_stage_begin(ctx, ST_DEEP);
+  if ((rc = spg_deep_stage_device(ctx, log_n, t_lde, h_lde, 0, 8, z, gamma, oods, inv3, d_small, layer0))) return rc;
+  spg_stage_end(ctx, ST_DEEP);
   // ---- 5. FRI
   std::vector<uint8_t> fri_roots;
   {

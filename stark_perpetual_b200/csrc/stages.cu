@@ -62,27 +62,13 @@ extern "C" int spg_stage_deep(spg_ctx* ctx, unsigned log_n, const uint64_t* t_ld
   SPG_LOCK(ctx);
   SPG_ARG(ctx && t_lde && h_lde && z && gamma && oods && inv_scratch && out, "spg_stage_deep: null");
   SPG_CUDA(cudaSetDevice(ctx->device));
-  const int C = SPG_AIR_COLS;
   const Fp zz = spg_host_from_u64(z), gm = spg_host_from_u64(gamma);
-  const Fp zw = fp_mul(zz, spg_host_root_of_unity((int)log_n)), z4 = fp_sqr(fp_sqr(zz));
-  Fp gp[SPG_N_OODS + 6], o[SPG_N_OODS];
+  Fp o[SPG_N_OODS];
   for (int k = 0; k < SPG_N_OODS; k++) o[k] = spg_host_from_u64(oods + 4 * k);
-  gp[0] = fp_one();
-  for (int k = 1; k < SPG_N_OODS; k++) gp[k] = fp_mul(gp[k - 1], gm);
-  Fp K[3] = {fp_zero(), fp_zero(), fp_zero()};
-  for (int c = 0; c < C; c++) { K[0] = fp_add(K[0], fp_mul(gp[c], o[c])); K[1] = fp_add(K[1], fp_mul(gp[C + c], o[C + c])); }
-  for (int m = 0; m < 4; m++) K[2] = fp_add(K[2], fp_mul(gp[2 * C + m], o[2 * C + m]));
-  gp[SPG_N_OODS] = K[0]; gp[SPG_N_OODS + 1] = K[1]; gp[SPG_N_OODS + 2] = K[2];
-  gp[SPG_N_OODS + 3] = zz; gp[SPG_N_OODS + 4] = zw; gp[SPG_N_OODS + 5] = z4;
   void* ds;
-  SPG_CUDA(spg_scratch(ctx, 6, sizeof(gp), &ds));
-  SPG_CUDA(cudaMemcpyAsync(ds, gp, sizeof(gp), cudaMemcpyHostToDevice, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  Fp* d_small = (Fp*)ds;
-  int rc = spg_inv_x_minus_device(ctx, log_n, first_coset, 1, n_cosets, d_small + SPG_N_OODS + 3, 3, (Fp*)inv_scratch);
-  if (rc) return rc;
-  return spg_deep_device(ctx, log_n, (const Fp*)t_lde, (const Fp*)h_lde, (const Fp*)inv_scratch, d_small,
-                         d_small + SPG_N_OODS, (Fp*)out, n_cosets);
+  SPG_CUDA(spg_scratch(ctx, 6, 64 * sizeof(Fp), &ds));
+  return spg_deep_stage_device(ctx, log_n, (const Fp*)t_lde, (const Fp*)h_lde, first_coset, n_cosets, zz, gm, o, (Fp*)inv_scratch,
+                               (Fp*)ds, (Fp*)out);
 }
 
 // fold layer `layer_index` (0 = the DEEP quotient, rows = 2^log_rows per coset) by 8 with challenge beta
