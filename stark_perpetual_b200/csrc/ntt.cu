@@ -1,5 +1,7 @@
 // NTT passes as CUDA kernels + the pass planner + the spg_ntt entry point.
 // (SURVEY.md section 8 row p1 / BASELINE.json configs[1]; conventions in DESIGN.md.)
+#include <cuda.h>
+
 #include "common.h"
 #include "ntt.cuh"
 
@@ -74,25 +76,26 @@ __device__ __forceinline__ void ntt_tile_steps(FpHalf* ws, const FpHalf* tws, in
   }
 }
 
-// TMA_IN (contiguous passes, log_s = 0; default, SPG_NTT_TMA=0 selects the per-thread LDG path): the tile's 2^LOG_R x 32 bytes are fetched by ONE
-// bulk asynchronous copy (cp.async.bulk global -> shared, completion on an mbarrier) into the workspace area in linear
-// element order; each thread then takes its four elements out of shared memory, applies the load-phase factor and, after
-// a CTA barrier, writes them back in the planar swizzled layout the butterflies use.  Measured against the per-thread
-// LDG path in DESIGN.md section 3.
+// TMA staging of the tile (default; SPG_NTT_TMA=0 selects the per-thread LDG path).  The tile's 2^LOG_R x 32 bytes are
+// fetched by the copy engine into the workspace area in LINEAR element order while the threads stage the twiddles; each
+// thread then takes its four elements out of shared memory, applies the load-phase factor and, after a CTA barrier,
+// writes them back in the planar swizzled layout the butterflies use.
+//   TMA_MODE 1  contiguous pass (log_s = 0): ONE cp.async.bulk of 32 KB, completion on an mbarrier;
+//   TMA_MODE 2  strided pass (log_s = LOG_R, B = 1): the tile is column c of an [R][S] matrix of 32-byte elements --
+//               four cp.async.bulk.tensor.4d copies of a {32 B x 1 x 256 rows x 1} box through a tensor map over
+//               (word, c, r, column), in place of 2048 per-lane 32-byte loads 32 KB apart (32 L1 wavefronts each).
+// Measured against the per-thread path in DESIGN.md section 3.
 __device__ __forceinline__ uint32_t spg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-#ifndef NTT_TILE_MIN_CTAS
-#define NTT_TILE_MIN_CTAS 4       // CTAs per SM of the 2^10 tile: 4 = 64 registers (measured against 3 = 80: DESIGN.md section 3)
-#endif
-template <bool DIT, int LOG_R, bool TMA_IN>
-__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2) k_ntt_tile(NttPass P) {
+template <bool DIT, int LOG_R, int TMA_MODE>
+__device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMap* tmap) {
   typedef NttTileCT<LOG_R> T;
   extern __shared__ uint4 smem_raw[];
   FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
   FpHalf* tws = ws + 2 * T::R;
   const int tid = threadIdx.x;
   const unsigned cta = blockIdx.x, col = blockIdx.y;
-  if (TMA_IN) {
+  if (TMA_MODE != 0) {
     __shared__ __align__(8) unsigned long long mbar;
     const uint32_t mb = spg_smem_u32(&mbar);
     constexpr uint32_t BYTES = (uint32_t)T::R * 32u;
@@ -102,10 +105,18 @@ __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_C
     }
     __syncthreads();
     if (tid == 0) {
-      const Fp* src = P.in + col * P.in_col_stride + ((unsigned long long)cta << LOG_R);
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(BYTES) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(spg_smem_u32(ws)), "l"(src), "r"(BYTES), "r"(mb) : "memory");
+      if (TMA_MODE == 1) {
+        const Fp* src = P.in + col * P.in_col_stride + ((unsigned long long)cta << LOG_R);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(spg_smem_u32(ws)), "l"(src), "r"(BYTES), "r"(mb) : "memory");
+      } else {
+#pragma unroll
+        for (int q = 0; q < T::R / 256; q++)
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(spg_smem_u32(ws) + (uint32_t)q * 8192u), "l"(tmap), "r"(mb), "r"(0), "r"((int)cta), "r"(q * 256), "r"((int)col)
+                       : "memory");
+      }
     }
     T::stage_twiddles(P, tws, tid);          // overlaps the copy
     {
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_C
     for (int j = 0; j < 4; j++) {
       const int r = T::io_row(tid, j);
       x[j] = lin[r];
-      if (DIT) x[j] = T::G::apply_factors(P, x[j], cta, r, 0);
+      if (DIT) x[j] = (TMA_MODE == 1) ? T::G::apply_factors(P, x[j], cta, r, 0) : T::G::apply_factors(P, x[j], 0, r, cta);
     }
     __syncthreads();                         // every element has left the linear image before the swizzled one overwrites it
 #pragma unroll
@@ -134,6 +145,43 @@ __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_C
   ntt_tile_steps<DIT, LOG_R, 0>(ws, tws, tid);
 #pragma unroll
   for (int j = 0; j < 4; j++) T::template store<DIT>(P, ws, cta, col, T::io_row(tid, j));
+}
+
+#ifndef NTT_TILE_MIN_CTAS
+#define NTT_TILE_MIN_CTAS 4       // CTAs per SM of the 2^10 tile: 4 = 64 registers (measured against 3 = 80: DESIGN.md section 3)
+#endif
+template <bool DIT, int LOG_R, bool TMA_IN>
+__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2) k_ntt_tile(NttPass P) {
+  ntt_tile_body<DIT, LOG_R, TMA_IN ? 1 : 0>(P, nullptr);
+}
+template <bool DIT, int LOG_R>
+__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2)
+    k_ntt_tile_tmap(NttPass P, const __grid_constant__ CUtensorMap tmap) {
+  ntt_tile_body<DIT, LOG_R, 2>(P, &tmap);
+}
+
+// tensor map over the input of a strided whole-workspace pass (B = 1): dims (innermost first) 8 words, S columns, R rows,
+// ncols trace columns; box {8, 1, 256, 1}.  Returns false when the driver entry point is unavailable.
+typedef CUresult (*spg_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_strided_tmap(const NttPass& P, size_t ncols, CUtensorMap* out) {
+  static spg_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (spg_encode_tiled_fn)p;
+  }
+  if (!fn) return false;
+  const cuuint64_t S = 1ull << P.log_s, R = 1ull << P.log_r;
+  const cuuint64_t dims[4] = {8, S, R, (cuuint64_t)ncols};
+  const cuuint64_t strides[3] = {32, S * 32, (cuuint64_t)P.in_col_stride * 32};       // bytes, dims 1..3
+  const cuuint32_t box[4] = {8, 1, 256, 1}, estr[4] = {1, 1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)P.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 __global__ void k_bitrev(const Fp* in, Fp* out, unsigned log_n, size_t ncols) {
@@ -190,6 +238,8 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
     attr_set = true;
   }
   NttPass passes[8];
@@ -211,9 +261,14 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     dim3 grid((unsigned)ctas, (unsigned)ncols);
     if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
       const int smem_ct = (1 << log_ws) * 48;
+      CUtensorMap tmap;
       if (log_ws == 11) {
         if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
         else k_ntt_tile<false, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
+      } else if (ctx->ntt_tma_strided && P.log_s == P.log_r && (int)log_n == 2 * P.log_r && make_strided_tmap(P, ncols, &tmap)) {
+        // strided pass: tensor-map TMA gathers the tile's 1024 rows
+        if (dit) k_ntt_tile_tmap<true, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap);
+        else k_ntt_tile_tmap<false, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap);
       } else if (ctx->ntt_tma_in && P.log_s == 0) {      // bulk asynchronous copy (TMA) of the contiguous tile
         if (dit) k_ntt_tile<true, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
         else k_ntt_tile<false, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
