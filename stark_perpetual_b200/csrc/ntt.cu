@@ -90,14 +90,15 @@ __device__ __forceinline__ uint32_t spg_smem_u32(const void* p) { return (uint32
 template <bool DIT, int LOG_R, int TMA_MODE>
 __device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMap* tmap) {
   typedef NttTileCT<LOG_R> T;
-  extern __shared__ uint4 smem_raw[];
+  extern __shared__ __align__(128) uint4 smem_raw[];
   FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
   FpHalf* tws = ws + 2 * T::R;
   const int tid = threadIdx.x;
   const unsigned cta = blockIdx.x, col = blockIdx.y;
   if (TMA_MODE != 0) {
-    __shared__ __align__(8) unsigned long long mbar;
-    const uint32_t mb = spg_smem_u32(&mbar);
+    // the mbarrier lives behind the twiddles in dynamic shared memory: the workspace must stay 128-byte aligned for the
+    // tensor copies (static shared memory would be placed in front of it)
+    const uint32_t mb = spg_smem_u32(tws + 2 * T::HW);
     constexpr uint32_t BYTES = (uint32_t)T::R * 32u;
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
@@ -232,14 +233,14 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, NTT_LOG_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_LOG_WS) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
     attr_set = true;
   }
   NttPass passes[8];
@@ -260,7 +261,7 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     const size_t ctas = ((size_t)1 << log_n) >> (P.log_r + P.log_g);
     dim3 grid((unsigned)ctas, (unsigned)ncols);
     if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
-      const int smem_ct = (1 << log_ws) * 48;
+      const int smem_ct = (1 << log_ws) * 48 + 16;
       CUtensorMap tmap;
       if (log_ws == 11) {
         if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
