@@ -96,9 +96,8 @@ __device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMa
   const int tid = threadIdx.x;
   const unsigned cta = blockIdx.x, col = blockIdx.y;
   if (TMA_MODE != 0) {
-    // the mbarrier lives behind the twiddles in dynamic shared memory: the workspace must stay 128-byte aligned for the
-    // tensor copies (static shared memory would be placed in front of it)
-    const uint32_t mb = spg_smem_u32(tws + 2 * T::HW);
+    __shared__ __align__(8) unsigned long long mbar;     // static: placed in front of the 128-byte aligned dynamic area
+    const uint32_t mb = spg_smem_u32(&mbar);
     constexpr uint32_t BYTES = (uint32_t)T::R * 32u;
     if (tid == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
@@ -153,8 +152,57 @@ __device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMa
 #endif
 template <bool DIT, int LOG_R, bool TMA_IN>
 __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2) k_ntt_tile(NttPass P) {
-  ntt_tile_body<DIT, LOG_R, TMA_IN ? 1 : 0>(P, nullptr);
+  typedef NttTileCT<LOG_R> T;
+  extern __shared__ uint4 smem_raw[];
+  FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
+  FpHalf* tws = ws + 2 * T::R;
+  const int tid = threadIdx.x;
+  const unsigned cta = blockIdx.x, col = blockIdx.y;
+  if (TMA_IN) {
+    __shared__ __align__(8) unsigned long long mbar;
+    const uint32_t mb = spg_smem_u32(&mbar);
+    constexpr uint32_t BYTES = (uint32_t)T::R * 32u;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const Fp* src = P.in + col * P.in_col_stride + ((unsigned long long)cta << LOG_R);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(BYTES) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(spg_smem_u32(ws)), "l"(src), "r"(BYTES), "r"(mb) : "memory");
+    }
+    T::stage_twiddles(P, tws, tid);          // overlaps the copy
+    {
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(mb) : "memory");
+    }
+    Fp x[4];
+    const Fp* lin = reinterpret_cast<const Fp*>(ws);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = T::io_row(tid, j);
+      x[j] = lin[r];
+      if (DIT) x[j] = T::G::apply_factors(P, x[j], cta, r, 0);
+    }
+    __syncthreads();                         // every element has left the linear image before the swizzled one overwrites it
+#pragma unroll
+    for (int j = 0; j < 4; j++) T::ws_put(ws, T::G::swz(T::io_row(tid, j)), x[j]);
+  } else {
+    T::stage_twiddles(P, tws, tid);
+#pragma unroll
+    for (int j = 0; j < 4; j++) T::template load<DIT>(P, ws, cta, col, T::io_row(tid, j));
+  }
+  __syncthreads();
+  ntt_tile_steps<DIT, LOG_R, 0>(ws, tws, tid);
+#pragma unroll
+  for (int j = 0; j < 4; j++) T::template store<DIT>(P, ws, cta, col, T::io_row(tid, j));
 }
+
+// the strided-pass variant: same tile, gathered through a tensor map (ntt_tile_body<., ., 2>)
 template <bool DIT, int LOG_R>
 __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2)
     k_ntt_tile_tmap(NttPass P, const __grid_constant__ CUtensorMap tmap) {
@@ -233,14 +281,14 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, NTT_LOG_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_LOG_WS) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48 + 16));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48 + 16));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48 + 16));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
     attr_set = true;
   }
   NttPass passes[8];
@@ -261,7 +309,7 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     const size_t ctas = ((size_t)1 << log_n) >> (P.log_r + P.log_g);
     dim3 grid((unsigned)ctas, (unsigned)ncols);
     if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
-      const int smem_ct = (1 << log_ws) * 48 + 16;
+      const int smem_ct = (1 << log_ws) * 48;
       CUtensorMap tmap;
       if (log_ws == 11) {
         if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
