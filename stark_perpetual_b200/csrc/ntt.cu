@@ -88,7 +88,7 @@ __device__ __forceinline__ void ntt_tile_steps(FpHalf* ws, const FpHalf* tws, in
 __device__ __forceinline__ uint32_t spg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <bool DIT, int LOG_R, int TMA_MODE>
-__device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMap* tmap) {
+__device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMap* tmap, const CUtensorMap* tmap_out) {
   typedef NttTileCT<LOG_R> T;
   extern __shared__ __align__(128) uint4 smem_raw[];
   FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
@@ -143,6 +143,34 @@ __device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMa
   }
   __syncthreads();
   ntt_tile_steps<DIT, LOG_R, 0>(ws, tws, tid);
+  if (TMA_MODE == 2 && tmap_out) {
+    // strided store through the tensor map: final values go back to shared memory in linear order, then four tensor copies
+    // write the tile's rows (in place of 2048 per-lane 32-byte stores 32 KB apart)
+    Fp y[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int r = T::io_row(tid, j);
+      y[j] = T::ws_at(ws, T::G::swz(r));
+      if (!DIT) y[j] = T::G::apply_factors(P, y[j], 0, r, cta);
+      if (P.final_pass) y[j] = fp_reduce_full(y[j]);
+    }
+    __syncthreads();                         // the swizzled image has been read by everyone
+    Fp* lin = reinterpret_cast<Fp*>(ws);
+#pragma unroll
+    for (int j = 0; j < 4; j++) lin[T::io_row(tid, j)] = y[j];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+      for (int q = 0; q < T::R / 256; q++)
+        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                     ::"l"(tmap_out), "r"(spg_smem_u32(ws) + (uint32_t)q * 8192u), "r"(0), "r"((int)cta), "r"(q * 256), "r"((int)col)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; j++) T::template store<DIT>(P, ws, cta, col, T::io_row(tid, j));
 }
@@ -205,8 +233,8 @@ __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_C
 // the strided-pass variant: same tile, gathered through a tensor map (ntt_tile_body<., ., 2>)
 template <bool DIT, int LOG_R>
 __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2)
-    k_ntt_tile_tmap(NttPass P, const __grid_constant__ CUtensorMap tmap) {
-  ntt_tile_body<DIT, LOG_R, 2>(P, &tmap);
+    k_ntt_tile_tmap(NttPass P, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, int tma_store) {
+  ntt_tile_body<DIT, LOG_R, 2>(P, &tmap, tma_store ? &tmap_out : nullptr);
 }
 
 // tensor map over the input of a strided whole-workspace pass (B = 1): dims (innermost first) 8 words, S columns, R rows,
@@ -214,7 +242,7 @@ __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_C
 typedef CUresult (*spg_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static bool make_strided_tmap(const NttPass& P, size_t ncols, CUtensorMap* out) {
+static bool make_strided_tmap(const NttPass& P, size_t ncols, CUtensorMap* out, bool for_output = false) {
   static spg_encode_tiled_fn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -227,9 +255,9 @@ static bool make_strided_tmap(const NttPass& P, size_t ncols, CUtensorMap* out) 
   if (!fn) return false;
   const cuuint64_t S = 1ull << P.log_s, R = 1ull << P.log_r;
   const cuuint64_t dims[4] = {8, S, R, (cuuint64_t)ncols};
-  const cuuint64_t strides[3] = {32, S * 32, (cuuint64_t)P.in_col_stride * 32};       // bytes, dims 1..3
+  const cuuint64_t strides[3] = {32, S * 32, (cuuint64_t)(for_output ? P.out_col_stride : P.in_col_stride) * 32};   // bytes, dims 1..3
   const cuuint32_t box[4] = {8, 1, 256, 1}, estr[4] = {1, 1, 1, 1};
-  return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, (void*)P.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, for_output ? (void*)P.out : (void*)P.in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -310,14 +338,16 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     dim3 grid((unsigned)ctas, (unsigned)ncols);
     if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
       const int smem_ct = (1 << log_ws) * 48;
-      CUtensorMap tmap;
+      CUtensorMap tmap, tmap_out;
       if (log_ws == 11) {
         if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
         else k_ntt_tile<false, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-      } else if (ctx->ntt_tma_strided && P.log_s == P.log_r && (int)log_n == 2 * P.log_r && make_strided_tmap(P, ncols, &tmap)) {
-        // strided pass: tensor-map TMA gathers the tile's 1024 rows
-        if (dit) k_ntt_tile_tmap<true, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap);
-        else k_ntt_tile_tmap<false, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap);
+      } else if (ctx->ntt_tma_strided && P.log_s == P.log_r && (int)log_n == 2 * P.log_r && make_strided_tmap(P, ncols, &tmap) &&
+                 make_strided_tmap(P, ncols, &tmap_out, true)) {
+        // strided pass: tensor-map TMA gathers (and, unless SPG_NTT_TMA2D_STORE=0, scatters) the tile's 1024 rows
+        const int st = ctx->ntt_tma_store ? 1 : 0;
+        if (dit) k_ntt_tile_tmap<true, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
+        else k_ntt_tile_tmap<false, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
       } else if (ctx->ntt_tma_in && P.log_s == 0) {      // bulk asynchronous copy (TMA) of the contiguous tile
         if (dit) k_ntt_tile<true, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
         else k_ntt_tile<false, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
