@@ -315,6 +315,10 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
+    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
     attr_set = true;
@@ -339,13 +343,22 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
       const int smem_ct = (1 << log_ws) * 48;
       CUtensorMap tmap, tmap_out;
+      const bool tma2d = ctx->ntt_tma_strided && P.log_s == P.log_r && (int)log_n == 2 * P.log_r && make_strided_tmap(P, ncols, &tmap) &&
+                         make_strided_tmap(P, ncols, &tmap_out, true);
+      const int st = ctx->ntt_tma_store ? 1 : 0;
       if (log_ws == 11) {
-        if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-        else k_ntt_tile<false, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-      } else if (ctx->ntt_tma_strided && P.log_s == P.log_r && (int)log_n == 2 * P.log_r && make_strided_tmap(P, ncols, &tmap) &&
-                 make_strided_tmap(P, ncols, &tmap_out, true)) {
-        // strided pass: tensor-map TMA gathers (and, unless SPG_NTT_TMA2D_STORE=0, scatters) the tile's 1024 rows
-        const int st = ctx->ntt_tma_store ? 1 : 0;
+        if (tma2d) {
+          if (dit) k_ntt_tile_tmap<true, 11><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
+          else k_ntt_tile_tmap<false, 11><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
+        } else if (ctx->ntt_tma_in && P.log_s == 0) {
+          if (dit) k_ntt_tile<true, 11, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
+          else k_ntt_tile<false, 11, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        } else {
+          if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
+          else k_ntt_tile<false, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
+        }
+      } else if (tma2d) {
+        // strided pass: tensor-map TMA gathers and (unless SPG_NTT_TMA2D_STORE=0) scatters the tile's rows
         if (dit) k_ntt_tile_tmap<true, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
         else k_ntt_tile_tmap<false, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
       } else if (ctx->ntt_tma_in && P.log_s == 0) {      // bulk asynchronous copy (TMA) of the contiguous tile
