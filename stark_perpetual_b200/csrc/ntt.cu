@@ -16,7 +16,8 @@
 #define NTT_LOG_EPT 2
 #endif
 
-int spg_ntt_tile_log_ws(unsigned log_n) { return (log_n == 21 || log_n == 22) ? 11 : NTT_LOG_WS; }
+// 2^18 (BASELINE configs[1]) takes a 2^9 workspace so that both of its passes are whole-workspace tiles (k_ntt_tile)
+int spg_ntt_tile_log_ws(unsigned log_n) { return (log_n == 21 || log_n == 22) ? 11 : log_n == 18 ? 9 : NTT_LOG_WS; }
 
 // Synchronisation between the phases of a pass.  When the pass uses the whole workspace for one column (log_g = 0,
 // log_r = LOG_WS) and every thread owns exactly one butterfly group per step, a step with sh + w <= 5 + LOG_EPT only
@@ -178,8 +179,10 @@ __device__ __forceinline__ void ntt_tile_body(const NttPass& P, const CUtensorMa
 #ifndef NTT_TILE_MIN_CTAS
 #define NTT_TILE_MIN_CTAS 4       // CTAs per SM of the 2^10 tile: 4 = 64 registers (measured against 3 = 80: DESIGN.md section 3)
 #endif
+// resident CTAs per SM asked of ptxas: 32 warps per SM (64 registers per thread) for every tile size
+#define NTT_TILE_CTAS(LOG_R) ((LOG_R) == 10 ? NTT_TILE_MIN_CTAS : (LOG_R) == 9 ? 8 : 2)
 template <bool DIT, int LOG_R, bool TMA_IN>
-__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2) k_ntt_tile(NttPass P) {
+__global__ void __launch_bounds__((1 << LOG_R) / 4, NTT_TILE_CTAS(LOG_R)) k_ntt_tile(NttPass P) {
   typedef NttTileCT<LOG_R> T;
   extern __shared__ uint4 smem_raw[];
   FpHalf* ws = reinterpret_cast<FpHalf*>(smem_raw);
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_C
 
 // the strided-pass variant: same tile, gathered through a tensor map (ntt_tile_body<., ., 2>)
 template <bool DIT, int LOG_R>
-__global__ void __launch_bounds__((1 << LOG_R) / 4, LOG_R == 10 ? NTT_TILE_MIN_CTAS : 2)
+__global__ void __launch_bounds__((1 << LOG_R) / 4, NTT_TILE_CTAS(LOG_R))
     k_ntt_tile_tmap(NttPass P, const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, int tma_store) {
   ntt_tile_body<DIT, LOG_R, 2>(P, &tmap, tma_store ? &tmap_out : nullptr);
 }
@@ -296,6 +299,33 @@ int spg_ntt_build_diag_table(spg_ctx* ctx, unsigned log_n, int inverse, int dit,
   return SPG_OK;
 }
 
+// launch of the compile-time tile for one pass: tensor-map kernel for strided passes, bulk-copy kernel for contiguous ones,
+// per-thread loads when TMA is switched off
+template <int LOG_R>
+static void launch_tile(spg_ctx* ctx, const NttPass& P, dim3 grid, int dit, bool tma2d, const CUtensorMap& tin, const CUtensorMap& tout) {
+  const int threads = (1 << LOG_R) / 4, smem = (1 << LOG_R) * 48, st = ctx->ntt_tma_store ? 1 : 0;
+  if (tma2d) {
+    if (dit) k_ntt_tile_tmap<true, LOG_R><<<grid, threads, smem, ctx->stream>>>(P, tin, tout, st);
+    else k_ntt_tile_tmap<false, LOG_R><<<grid, threads, smem, ctx->stream>>>(P, tin, tout, st);
+  } else if (ctx->ntt_tma_in && P.log_s == 0) {
+    if (dit) k_ntt_tile<true, LOG_R, true><<<grid, threads, smem, ctx->stream>>>(P);
+    else k_ntt_tile<false, LOG_R, true><<<grid, threads, smem, ctx->stream>>>(P);
+  } else {
+    if (dit) k_ntt_tile<true, LOG_R, false><<<grid, threads, smem, ctx->stream>>>(P);
+    else k_ntt_tile<false, LOG_R, false><<<grid, threads, smem, ctx->stream>>>(P);
+  }
+}
+template <int LOG_R>
+static cudaError_t tile_attrs() {
+  const int smem = (1 << LOG_R) * 48;
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); };
+  set((const void*)k_ntt_tile<false, LOG_R, false>); set((const void*)k_ntt_tile<true, LOG_R, false>);
+  set((const void*)k_ntt_tile<false, LOG_R, true>); set((const void*)k_ntt_tile<true, LOG_R, true>);
+  set((const void*)k_ntt_tile_tmap<false, LOG_R>); set((const void*)k_ntt_tile_tmap<true, LOG_R>);
+  return e;
+}
+
 int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t ncols, size_t in_stride,
                    size_t out_stride, int inverse, int dit, unsigned long long coset_exp,
                    const Fp* scale_lo, const Fp* scale_hi, const Fp* diag_table, const Fp* diag_table0) {
@@ -309,18 +339,7 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, NTT_LOG_WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << NTT_LOG_WS) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
     SPG_CUDA(cudaFuncSetAttribute(k_ntt_pass<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 32));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<false, 11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile<true, 11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 11) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<false, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
-    SPG_CUDA(cudaFuncSetAttribute(k_ntt_tile_tmap<true, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 << 10) * 48));
+    SPG_CUDA(tile_attrs<9>()); SPG_CUDA(tile_attrs<10>()); SPG_CUDA(tile_attrs<11>());
     attr_set = true;
   }
   NttPass passes[8];
@@ -335,39 +354,19 @@ int spg_ntt_device(spg_ctx* ctx, const Fp* in, Fp* out, unsigned log_n, size_t n
   } else if (np == 2 && !dit && inverse && diag_table) {
     passes[0].diag_table = diag_table;
   }
-  const int smem = (1 << log_ws) * (int)sizeof(Fp), threads = (1 << log_ws) >> NTT_LOG_EPT;
+  const int gen_ws = log_ws == 9 ? NTT_LOG_WS : log_ws;     // the generic kernel exists for the 2^10 and 2^11 workspaces
+  const int smem = (1 << gen_ws) * (int)sizeof(Fp), threads = (1 << gen_ws) >> NTT_LOG_EPT;
   for (int pi = 0; pi < np; pi++) {
     const NttPass& P = passes[pi];
     const size_t ctas = ((size_t)1 << log_n) >> (P.log_r + P.log_g);
     dim3 grid((unsigned)ctas, (unsigned)ncols);
     if (!ctx->ntt_generic_only && P.log_r == log_ws && P.log_g == 0) {     // the compile-time tile: whole-workspace tiles
-      const int smem_ct = (1 << log_ws) * 48;
       CUtensorMap tmap, tmap_out;
       const bool tma2d = ctx->ntt_tma_strided && P.log_s == P.log_r && (int)log_n == 2 * P.log_r && make_strided_tmap(P, ncols, &tmap) &&
                          make_strided_tmap(P, ncols, &tmap_out, true);
-      const int st = ctx->ntt_tma_store ? 1 : 0;
-      if (log_ws == 11) {
-        if (tma2d) {
-          if (dit) k_ntt_tile_tmap<true, 11><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
-          else k_ntt_tile_tmap<false, 11><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
-        } else if (ctx->ntt_tma_in && P.log_s == 0) {
-          if (dit) k_ntt_tile<true, 11, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
-          else k_ntt_tile<false, 11, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
-        } else {
-          if (dit) k_ntt_tile<true, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-          else k_ntt_tile<false, 11, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-        }
-      } else if (tma2d) {
-        // strided pass: tensor-map TMA gathers and (unless SPG_NTT_TMA2D_STORE=0) scatters the tile's rows
-        if (dit) k_ntt_tile_tmap<true, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
-        else k_ntt_tile_tmap<false, NTT_LOG_WS><<<grid, threads, smem_ct, ctx->stream>>>(P, tmap, tmap_out, st);
-      } else if (ctx->ntt_tma_in && P.log_s == 0) {      // bulk asynchronous copy (TMA) of the contiguous tile
-        if (dit) k_ntt_tile<true, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
-        else k_ntt_tile<false, NTT_LOG_WS, true><<<grid, threads, smem_ct, ctx->stream>>>(P);
-      } else {
-        if (dit) k_ntt_tile<true, NTT_LOG_WS, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-        else k_ntt_tile<false, NTT_LOG_WS, false><<<grid, threads, smem_ct, ctx->stream>>>(P);
-      }
+      if (log_ws == 11) launch_tile<11>(ctx, P, grid, dit, tma2d, tmap, tmap_out);
+      else if (log_ws == 9) launch_tile<9>(ctx, P, grid, dit, tma2d, tmap, tmap_out);
+      else launch_tile<NTT_LOG_WS>(ctx, P, grid, dit, tma2d, tmap, tmap_out);
     } else if (log_ws == 11) {
       if (dit) k_ntt_pass<true, 11><<<grid, threads, smem, ctx->stream>>>(P);
       else k_ntt_pass<false, 11><<<grid, threads, smem, ctx->stream>>>(P);
