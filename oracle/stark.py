@@ -1,4 +1,5 @@
-"""STARK prover + verifier for the Pedersen hash-chain AIR, plain Python ints.  TEST INFRASTRUCTURE.
+"""STARK prover + verifier, plain Python ints: the protocol (AIR-generic: prove_air / verify) and the Pedersen hash-chain
+AIR; the second AIR (ECDSA builtin) lives in stark_ecdsa.py.  TEST INFRASTRUCTURE.
 
 PARITY UNPINNED: the reference repository contains no prover, verifier or AIR; the
 protocol below is this repo's own (DESIGN.md "Protocol").  What IS pinned by the reference is the
@@ -163,6 +164,9 @@ class Air:
     """Constraint evaluation at an arbitrary point x (given current / next row values and the periodic
     values at x) -- used on the LDE domain by the prover and at the OODS point by the verifier."""
 
+    kind = 1                                   # proof header VERSION field
+    n_alpha = LANES * N_CONSTRAINTS
+
     def __init__(self, log_n, chain_log, x0, outs):
         self.log_n, self.n = log_n, 1 << log_n
         self.chain_log = chain_log
@@ -207,6 +211,29 @@ class Air:
         for cx, cy in zip(reversed(self.px_coef), reversed(self.py_coef)):
             hx, hy = (hx * u + cx) % P, (hy * u + cy) % P
         return hx, hy
+
+    # ---- hooks of the AIR-generic prover / verifier below (the ECDSA-builtin AIR of stark_ecdsa.py has the same set)
+    def seed(self, n_queries):
+        return public_seed(self.log_n, self.chain_log, n_queries, self.x0, self.outs)
+
+    def header(self, n_queries, n_folds):
+        return b"".join([MAGIC, self.kind.to_bytes(4, "little"), self.log_n.to_bytes(4, "little"),
+                         self.chain_log.to_bytes(4, "little"), n_queries.to_bytes(4, "little"), n_folds.to_bytes(4, "little")]
+                        + [ser(v) for v in self.x0] + [ser(v) for v in self.outs])
+
+    def periodic_lde(self):
+        """-> per(j, i): the periodic columns' values at LDE point (coset j, row i)"""
+        px512, py512 = periodic_points()
+        g512 = pow(GEN, self.n // 512, P)
+        px_lde = ontt.lde(px512, LOG_BLOWUP, g512)                        # [j][i mod 512]
+        py_lde = ontt.lde(py512, LOG_BLOWUP, g512)
+        return lambda j, i: (px_lde[j][i % 512], py_lde[j][i % 512])
+
+    def composition_per(self, cur, nxt, per, iz, alpha_pows):
+        return self.composition(cur, nxt, per[0], per[1], iz, alpha_pows)
+
+    def statement(self):
+        return {"log_n": self.log_n, "chain_log": self.chain_log, "x0": self.x0, "outs": self.outs}
 
     def composition(self, cur, nxt, px, py, iz, alpha_pows):
         """cur / nxt: 25 values at x and x * w_N; returns CP(x)."""
@@ -290,9 +317,15 @@ def prove(log_n, chain_log, x0, ys, n_queries=30, corrupt=None):
 
 
 def prove_trace(log_n, chain_log, x0, outs, cols, n_queries=30, debug=None):
+    return prove_air(Air(log_n, chain_log, x0, outs), cols, n_queries, debug)
+
+
+def prove_air(air, cols, n_queries=30, debug=None):
+    """The protocol for any AIR object with the hook set of class Air (25 columns, mask {x, x w_N}, composition degree
+    < 4N): the Pedersen hash chain above, the ECDSA builtin of stark_ecdsa.py."""
+    log_n = air.log_n
     n = 1 << log_n
-    air = Air(log_n, chain_log, x0, outs)
-    ch = Channel(public_seed(log_n, chain_log, n_queries, x0, outs))
+    ch = Channel(air.seed(n_queries))
     wn = root_of_unity(log_n)
     # 1. trace LDE + commitment
     lde_cols = [ontt.lde(c, LOG_BLOWUP, GEN) for c in cols]               # [c][j][i]
@@ -302,11 +335,8 @@ def prove_trace(log_n, chain_log, x0, outs, cols, n_queries=30, debug=None):
     ch.absorb(t_levels[-1][0])
     # 2. composition on the cosets j = 0, 2, 4, 6  (= the coset g <w_4N>)
     alpha = ch.draw_felt()
-    apows = [pow(alpha, k, P) for k in range(LANES * N_CONSTRAINTS)]
-    px512, py512 = periodic_points()
-    g512 = pow(GEN, n // 512, P)
-    px_lde = ontt.lde(px512, LOG_BLOWUP, g512)                            # [j][i mod 512]
-    py_lde = ontt.lde(py512, LOG_BLOWUP, g512)
+    apows = [pow(alpha, k, P) for k in range(air.n_alpha)]
+    per = air.periodic_lde()
     cp = [0] * (4 * n)                                                    # index e' = j/2 + 4 i
     for j in range(0, 8, 2):
         for i in range(n):
@@ -314,7 +344,7 @@ def prove_trace(log_n, chain_log, x0, outs, cols, n_queries=30, debug=None):
             cur = [t_table[j][c][i] for c in range(N_COLS)]
             nxt = [t_table[j][c][(i + 1) % n] for c in range(N_COLS)]
             iz = air.inv_zerofiers(x)
-            cp[j // 2 + 4 * i] = air.composition(cur, nxt, px_lde[j][i % 512], py_lde[j][i % 512], iz, apows)
+            cp[j // 2 + 4 * i] = air.composition_per(cur, nxt, per(j, i), iz, apows)
     # interpolate CP on g <w_4N>, split into 4 chunks of degree < N
     coef = ontt.ntt(cp, inverse=True)
     ginv = inv(GEN)
@@ -387,9 +417,7 @@ def prove_trace(log_n, chain_log, x0, outs, cols, n_queries=30, debug=None):
         debug["betas"] = betas
         debug["last_coef"] = last_coef
     # 6. queries
-    out = [MAGIC, VERSION.to_bytes(4, "little"), log_n.to_bytes(4, "little"), chain_log.to_bytes(4, "little"),
-           n_queries.to_bytes(4, "little"), (len(sizes) - 1).to_bytes(4, "little")]
-    out += [ser(v) for v in x0] + [ser(v) for v in outs]
+    out = [air.header(n_queries, len(sizes) - 1)]
     out += [t_levels[-1][0], h_levels[-1][0]] + [ser(v) for v in oods]
     out += [lv[-1][0] for lv in fri_levels] + [ser(v) for v in last_coef]
     for _ in range(n_queries):
@@ -440,10 +468,17 @@ def verify(proof, min_queries=MIN_QUERIES):
     The query count is read from the proof header; proofs with fewer than `min_queries` queries are rejected
     (blowup 8, no grinding: each query is worth 3 bits)."""
     rd = _Reader(proof)
-    if rd.take(4) != MAGIC or rd.u32() != VERSION:
+    if rd.take(4) != MAGIC:
+        raise ProofError("bad header")
+    kind = rd.u32()
+    if kind not in (VERSION, 2):
         raise ProofError("bad header")
     log_n, chain_log, n_queries, n_folds = rd.u32(), rd.u32(), rd.u32(), rd.u32()
-    if not (9 <= log_n <= 23) or 512 << chain_log > 1 << log_n or n_queries < 1:
+    if not (9 <= log_n <= 23) or n_queries < 1:
+        raise ProofError("bad parameters")
+    if kind == VERSION and 512 << chain_log > 1 << log_n:
+        raise ProofError("bad parameters")
+    if kind == 2 and chain_log != 0:
         raise ProofError("bad parameters")
     if n_queries < min_queries:
         raise ProofError("proof carries %d queries, fewer than the %d required" % (n_queries, min_queries))
@@ -451,25 +486,31 @@ def verify(proof, min_queries=MIN_QUERIES):
     if n_folds != len(sizes) - 1:
         raise ProofError("bad layer count")
     n = 1 << log_n
-    x0 = [rd.felt() for _ in range(LANES)]
-    outs = [rd.felt() for _ in range(LANES)]
+    if kind == VERSION:
+        x0 = [rd.felt() for _ in range(LANES)]
+        outs = [rd.felt() for _ in range(LANES)]
+        air = Air(log_n, chain_log, x0, outs)
+    else:                                          # the ECDSA-builtin AIR: public anchors (msg, key, r) of instance 0
+        from .stark_ecdsa import EcdsaAir
+        try:
+            air = EcdsaAir(log_n, [rd.felt() for _ in range(3)])
+        except ValueError as e:
+            raise ProofError(str(e))
     root_t, root_h = rd.take(32), rd.take(32)
     oods = [rd.felt() for _ in range(54)]
     fri_roots = [rd.take(32) for _ in range(n_folds)]
     last_coef = [rd.felt() for _ in range(sizes[-1])]
-    air = Air(log_n, chain_log, x0, outs)
     wn = root_of_unity(log_n)
-    ch = Channel(public_seed(log_n, chain_log, n_queries, x0, outs))
+    ch = Channel(air.seed(n_queries))
     ch.absorb(root_t)
     alpha = ch.draw_felt()
-    apows = [pow(alpha, k, P) for k in range(LANES * N_CONSTRAINTS)]
+    apows = [pow(alpha, k, P) for k in range(air.n_alpha)]
     ch.absorb(root_h)
     z = ch.draw_felt()
     zw, z4 = z * wn % P, pow(z, 4, P)
     ch.absorb(b"".join(ser(v) for v in oods))
     # composition consistency at z
-    pxz, pyz = air.periodic_at(z)
-    cpz = air.composition(oods[:25], oods[25:50], pxz, pyz, air.inv_zerofiers(z), apows)
+    cpz = air.composition_per(oods[:25], oods[25:50], air.periodic_at(z), air.inv_zerofiers(z), apows)
     if cpz != sum(pow(z, m, P) * oods[50 + m] for m in range(4)) % P:
         raise ProofError("composition polynomial mismatch at the out-of-domain point")
     gamma = ch.draw_felt()
@@ -529,4 +570,6 @@ def verify(proof, min_queries=MIN_QUERIES):
                 raise ProofError("FRI last layer mismatch")
     if rd.o != len(proof):
         raise ProofError("trailing bytes")
-    return {"log_n": log_n, "chain_log": chain_log, "x0": x0, "outs": outs, "n_queries": n_queries}
+    st = air.statement()
+    st["n_queries"] = n_queries
+    return st
