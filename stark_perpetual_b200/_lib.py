@@ -55,6 +55,9 @@ def _load():
             "spg_pedersen_chain_trace": (C.c_int, [vp, C.c_uint, C.c_uint, vp, vp, vp, C.c_int]),
             "spg_air_eval": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, vp, vp, vp, C.c_int]),
             "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
+            "spg_ecdsa_air_trace": (C.c_int, [vp, C.c_uint, vp, vp, vp, vp, vp, vp, C.c_int]),
+            "spg_air_eval_ecdsa": (C.c_int, [vp, vp, C.c_uint, vp, vp, vp, C.c_int]),
+            "spg_prove_ecdsa": (C.c_int, [vp, vp, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_ecdsa_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_private_to_stark_key_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_sign_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
@@ -518,6 +521,41 @@ class Context:
                                         C.byref(ln), flags))
         return buf[:ln.value].tobytes()
 
+    # ---- second AIR: the ECDSA builtin (csrc/air_ecdsa.cu; CPU twin oracle/stark_ecdsa.py) ----
+    def ecdsa_air_trace(self, log_n, msgs, r, w, key_x, key_y):
+        """One `verify` call per 256-row block (signature.py:243-260): msgs / r / w / key_x / key_y are (2^log_n / 256, 4)
+        uint64 canonical arrays (w = s^-1 mod the curve order, key point on the curve).  -> trace (25 * 2^log_n, 4).
+        SpgError where the reference asserts (scalar range, x collision) or returns False."""
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in (msgs, r, w, key_x, key_y)]
+        nb = (1 << log_n) >> 8
+        assert all(a.shape[0] == nb for a in arrs)
+        out = np.empty((25 << log_n, 4), dtype=np.uint64)
+        self._check(self._lib.spg_ecdsa_air_trace(self._h, log_n, *[_ptr(a) for a in arrs], _ptr(out), 0))
+        return out
+
+    def air_eval_ecdsa(self, trace, log_n, pub3, alpha):
+        tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
+        assert tr.shape[0] == 25 << log_n
+        pa, aa = ints_to_limbs(pub3), ints_to_limbs([alpha])
+        cp = np.empty((4 << log_n, 4), dtype=np.uint64)
+        self._check(self._lib.spg_air_eval_ecdsa(self._h, _ptr(tr), log_n, _ptr(pa), _ptr(aa), _ptr(cp), 0))
+        return cp
+
+    def prove_ecdsa(self, trace, log_n, pub3, n_queries=30, device_ptr=None):
+        """Proof that every block of `trace` is a verifying signature; pub3 = (msg_hash, key x, r) of signature 0."""
+        pa = ints_to_limbs(pub3)
+        assert pa.shape[0] == 3
+        if device_ptr is None:
+            tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
+            assert tr.shape[0] == 25 << log_n
+            tp, flags = _ptr(tr), 0
+        else:
+            tp, flags = C.c_void_p(device_ptr), SPG_DEVICE_PTRS
+        cap = 64 + 64 * 32 + 64 * 32 + 128 * 32 + n_queries * (8 * 29 + 8 * 8 + 10 * 24) * 32 + 65536
+        buf = np.empty(cap, dtype=np.uint8)
+        ln = C.c_size_t(0)
+        self._check(self._lib.spg_prove_ecdsa(self._h, tp, log_n, _ptr(pa), n_queries, _ptr(buf), cap, C.byref(ln), flags))
+        return buf[:ln.value].tobytes()
 
     # ---- multi-GPU (one process per GPU) ----
     def comm_unique_id(self):

@@ -7,16 +7,30 @@
 #include <string.h>
 
 #include "prove_common.h"
+#include "ecdsa_air_point.cuh"
 
+// which AIR a proof is for: the protocol around it is the same (25 columns, mask {x, x w_N}, 4 composition chunks)
+struct AirSpec {
+  int kind = 1;                         // proof header VERSION: 1 = Pedersen hash chain, 2 = ECDSA builtin
+  unsigned chain_log = 0;               // kind 1
+  const uint64_t* x0_canon = nullptr;   // kind 1: the 5 lane seeds
+  Fp pub3[3];                           // kind 2: msg_hash, key x, r of signature 0 (Montgomery)
+};
+#define SPG_MAX_ALPHA (SPG_AIR_LANES * SPG_AIR_NCONSTR)
+static_assert(SPG_EAIR_NALPHA <= SPG_MAX_ALPHA && SPG_EAIR_COLS == SPG_AIR_COLS, "both AIRs share the protocol's shape");
 
 // d_trace: [25][N] canonical felts on the device.  Appends the proof to `proof`.
 // h_trace (optional): the same trace in HOST memory; it is then uploaded into d_trace in column chunks on a
 // second stream while the LDE of the chunks already on the device runs (every column's transforms depend on that
 // column only), so the host->device copy of the end-to-end path hides behind the first stage.
-static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigned chain_log, const uint64_t* x0_canon,
-                        unsigned n_queries, std::vector<uint8_t>& proof, const Fp* h_trace = nullptr) {
+static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const AirSpec& air, unsigned n_queries,
+                        std::vector<uint8_t>& proof, const Fp* h_trace = nullptr) {
+  const unsigned chain_log = air.chain_log;
+  const uint64_t* x0_canon = air.x0_canon;
+  const bool pedersen = air.kind == 1;
+  const int n_alpha = pedersen ? SPG_MAX_ALPHA : SPG_EAIR_NALPHA;
   SPG_ARG(log_n >= 9 && log_n + SPG_LOG_BLOWUP <= SPG_UNI_LOG, "spg_prove: log_n must be in [9, 23]");
-  SPG_ARG(9 + chain_log <= log_n, "spg_prove: chain_log");
+  SPG_ARG(!pedersen || 9 + chain_log <= log_n, "spg_prove: chain_log");
   SPG_ARG(n_queries >= 1 && n_queries <= 1024, "spg_prove: n_queries");
   const size_t n = (size_t)1 << log_n;
   const int C = SPG_AIR_COLS;
@@ -54,7 +68,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
   const int n_chunks = 6, chunk_begin[7] = {0, 1, 5, 10, 15, 20, 25};
   static_assert(SPG_AIR_COLS == 25, "chunk table");
   if (h_trace) {
-    for (int l = 0; l < SPG_AIR_LANES; l++) h_last[l] = h_trace[((size_t)(5 * l) << log_n) + (n - 1)];
+    for (int l = 0; l < SPG_AIR_LANES; l++) h_last[l] = h_trace[((size_t)(5 * l) << log_n) + (n - 1)];   // (unused by kind 2)
     if (!ctx->copy_stream) {
       SPG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
       for (auto& e : ctx->copy_ev) SPG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -69,26 +83,33 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
                                cudaMemcpyHostToDevice, ctx->copy_stream));
       SPG_CUDA(cudaEventRecord(ctx->copy_ev[k], ctx->copy_stream));
     }
-  } else {
+  } else if (pedersen) {
     for (int l = 0; l < SPG_AIR_LANES; l++)
       SPG_CUDA(cudaMemcpyAsync(&h_last[l], d_trace + ((size_t)(5 * l) << log_n) + (n - 1), sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   AirPublic pub;
-  for (int l = 0; l < SPG_AIR_LANES; l++) {
-    pub.x0[l] = spg_host_from_u64(x0_canon + 4 * l);
-    uint64_t w[4]; fp_to_u64(h_last[l], w);
-    pub.outs[l] = spg_host_from_u64(w);
-  }
   std::vector<uint8_t> seed;
-  put_u32(seed, log_n); put_u32(seed, chain_log); put_u32(seed, n_queries);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.x0[l]);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.outs[l]);
-  Channel ch(seed);
   proof.insert(proof.end(), {'S', 'P', 'G', 'P'});
-  put_u32(proof, 1); put_u32(proof, log_n); put_u32(proof, chain_log); put_u32(proof, n_queries); put_u32(proof, (uint32_t)n_folds);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.x0[l]);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.outs[l]);
+  put_u32(proof, (uint32_t)air.kind); put_u32(proof, log_n); put_u32(proof, chain_log); put_u32(proof, n_queries); put_u32(proof, (uint32_t)n_folds);
+  if (pedersen) {
+    for (int l = 0; l < SPG_AIR_LANES; l++) {
+      pub.x0[l] = spg_host_from_u64(x0_canon + 4 * l);
+      uint64_t w[4]; fp_to_u64(h_last[l], w);
+      pub.outs[l] = spg_host_from_u64(w);
+    }
+    put_u32(seed, log_n); put_u32(seed, chain_log); put_u32(seed, n_queries);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.x0[l]);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.outs[l]);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.x0[l]);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.outs[l]);
+  } else {                                   // oracle/stark_ecdsa.py EcdsaAir.seed / .header
+    const char* tag = "ecdsa-builtin";
+    seed.insert(seed.end(), tag, tag + 13);
+    put_u32(seed, log_n); put_u32(seed, n_queries);
+    for (int k = 0; k < 3; k++) { put_fp(seed, air.pub3[k]); put_fp(proof, air.pub3[k]); }
+  }
+  Channel ch(seed);
 
   int rc;
   uint8_t root[32];
@@ -114,11 +135,13 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
   put_bytes(proof, root, 32);
   // ---- 2. composition polynomial on cosets 0, 2, 4, 6; chunk split; chunk LDE; commitment
   const Fp alpha = ch.draw_felt();
-  Fp apows[SPG_AIR_LANES * SPG_AIR_NCONSTR];
+  Fp apows[SPG_MAX_ALPHA];
   apows[0] = fp_one();
-  for (int k = 1; k < SPG_AIR_LANES * SPG_AIR_NCONSTR; k++) apows[k] = fp_mul(apows[k - 1], alpha);
+  for (int k = 1; k < n_alpha; k++) apows[k] = fp_mul(apows[k - 1], alpha);
   spg_stage_begin(ctx, ST_AIR);
-  if ((rc = spg_air_eval_device(ctx, log_n, chain_log, t_lde, pub, apows, cp))) return rc;
+  if (pedersen) rc = spg_air_eval_device(ctx, log_n, chain_log, t_lde, pub, apows, cp);
+  else rc = spg_eair_eval_device(ctx, log_n, t_lde, air.pub3, apows, cp);
+  if (rc) return rc;
   if ((rc = spg_cp_split_device(ctx, log_n, cp, hev))) return rc;
   spg_stage_end(ctx, ST_AIR);
   spg_stage_begin(ctx, ST_HLDE);
@@ -155,7 +178,8 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, unsigne
   }
   {
     // self-check: the composition recomputed on the host from the trace values at z must equal sum z^m H_m(z^4)
-    const Fp lhs = spg_air_composition_at_host(log_n, chain_log, pub, apows, z, oods, oods + C, ctx->h_const_points);
+    const Fp lhs = pedersen ? spg_air_composition_at_host(log_n, chain_log, pub, apows, z, oods, oods + C, ctx->h_const_points)
+                            : spg_eair_composition_at_host(ctx, log_n, air.pub3, apows, z, oods, oods + C);
     Fp rhs = fp_zero(), zp = fp_one();
     for (int m = 0; m < 4; m++) { rhs = fp_add(rhs, fp_mul(zp, oods[2 * C + m])); zp = fp_mul(zp, z); }
     if (!fp_eq(lhs, rhs)) { ctx->err = "trace does not satisfy the AIR (composition mismatch at the out-of-domain point)"; return SPG_E_PROOF; }
@@ -275,7 +299,9 @@ extern "C" int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, un
     h_trace = (const Fp*)trace;       // uploaded chunk by chunk inside prove_device, overlapped with the LDE
   }
   std::vector<uint8_t> proof;
-  int rc = prove_device(ctx, d_trace, log_n, chain_log, x0, n_queries, proof, h_trace);
+  AirSpec air;
+  air.kind = 1; air.chain_log = chain_log; air.x0_canon = x0;
+  int rc = prove_device(ctx, d_trace, log_n, air, n_queries, proof, h_trace);
   if (rc) return rc;
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -283,6 +309,46 @@ extern "C" int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, un
   *proof_len = proof.size();
   if (proof_out) {
     SPG_ARG(proof_cap >= proof.size(), "spg_prove: proof buffer too small (call with proof_out = NULL for the size)");
+    memcpy(proof_out, proof.data(), proof.size());
+  }
+  return SPG_OK;
+}
+
+// The same protocol over the ECDSA-builtin AIR (air_ecdsa.cu): trace [25][N] canonical felts as spg_ecdsa_air_trace writes
+// it, pub3 = (msg_hash, key x, r) of signature 0 (canonical).  Proof header VERSION = 2; verifier: oracle/stark.py verify.
+extern "C" int spg_prove_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* pub3, unsigned n_queries,
+                               uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags) {
+  SPG_LOCK(ctx);
+  SPG_ARG(ctx && trace && pub3 && proof_len, "spg_prove_ecdsa: null");
+  SPG_ARG(log_n >= 9 && log_n <= 23, "spg_prove_ecdsa: log_n must be in [9, 23]");
+  SPG_CUDA(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)1 << log_n, bytes = (size_t)SPG_AIR_COLS * n * 32;
+  const Fp* d_trace = (const Fp*)trace;
+  SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  const Fp* h_trace = nullptr;
+  if (!(flags & SPG_DEVICE_PTRS)) {
+    void* p;
+    SPG_CUDA(spg_scratch(ctx, 2, bytes, &p));
+    d_trace = (const Fp*)p;
+    h_trace = (const Fp*)trace;
+  }
+  AirSpec air;
+  air.kind = 2;
+  for (int k = 0; k < 3; k++) {
+    uint32_t lim[8];
+    for (int q = 0; q < 4; q++) { lim[2 * q] = (uint32_t)pub3[4 * k + q]; lim[2 * q + 1] = (uint32_t)(pub3[4 * k + q] >> 32); }
+    SPG_ARG(!spg_canon_geq_p(lim), "spg_prove_ecdsa: public value >= p");
+    air.pub3[k] = spg_host_from_u64(pub3 + 4 * k);
+  }
+  std::vector<uint8_t> proof;
+  int rc = prove_device(ctx, d_trace, log_n, air, n_queries, proof, h_trace);
+  if (rc) return rc;
+  SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1); ctx->last_ms = ms;
+  *proof_len = proof.size();
+  if (proof_out) {
+    SPG_ARG(proof_cap >= proof.size(), "spg_prove_ecdsa: proof buffer too small (call with proof_out = NULL for the size)");
     memcpy(proof_out, proof.data(), proof.size());
   }
   return SPG_OK;
