@@ -504,6 +504,10 @@ def main():
                                                 n_orders=args.orders, hbm_gbs=peak)
             except Exception as e:          # the headline line must survive a failure of the side measurements
                 line["aux"] = {"error": repr(e)[:500]}
+            try:                            # the second AIR (ECDSA builtin) at the headline trace size: 4096 signatures, one proof
+                line["aux"]["ecdsa_air_2^%d" % args.log_n] = aux_bench.ecdsa_air(ctx, args.log_n, args.queries)
+            except Exception as e:
+                line["aux"]["ecdsa_air_error"] = repr(e)[:500]
     if world > 1 and not args.no_aux:
         # BASELINE.json configs[3] (2^22 proof) and [4] (order batch split) at this N, after the timed region.  A watchdog
         # makes sure the headline line is printed even if a rank gets stuck in a collective of the side measurement.

@@ -83,6 +83,15 @@ static int ensure_eair_tables(spg_ctx* ctx, unsigned log_n) {
 }
 
 // ------------------------------------------------------------------ composition evaluation
+// loaders handed to ecdsa_air_point: cell k of the row, group g's inverse zerofier
+struct EairCells {
+  const Fp* __restrict__ p; unsigned log_n;
+  __device__ __forceinline__ Fp operator[](int k) const { return p[(size_t)k << log_n]; }
+};
+struct EairZerofiers {
+  const Fp* __restrict__ izt; const Fp* __restrict__ anchor;
+  __device__ __forceinline__ Fp operator[](int g) const { return g < 6 ? izt[(size_t)g * 4 * SPG_EAIR_BLOCK] : *anchor; }
+};
 __global__ void __launch_bounds__(128) k_air_eval_ecdsa(unsigned log_n, const Fp* __restrict__ t_lde,
                                                         const EcdsaAirConsts* __restrict__ K, const Fp* __restrict__ izt,
                                                         const Fp* __restrict__ plde, const Fp* __restrict__ ianchor,
@@ -94,14 +103,8 @@ __global__ void __launch_bounds__(128) k_air_eval_ecdsa(unsigned log_n, const Fp
   const size_t in = (i + 1) & (n - 1);
   const int B = SPG_EAIR_BLOCK;
   const Fp* base = t_lde + ((j - first_coset) * SPG_EAIR_COLS << log_n);
-  Fp c[SPG_EAIR_COLS], nx[SPG_EAIR_COLS];
-#pragma unroll
-  for (int k = 0; k < SPG_EAIR_COLS; k++) { c[k] = base[((size_t)k << log_n) + i]; nx[k] = base[((size_t)k << log_n) + in]; }
-  Fp iz[SPG_EAIR_NGROUPS];
-  const size_t zi = jj * B + (i & (B - 1));
-#pragma unroll
-  for (int g = 0; g < 6; g++) iz[g] = izt[(size_t)g * 4 * B + zi];
-  iz[6] = ianchor[(jj << log_n) + i];
+  const EairCells c = {base + i, log_n}, nx = {base + in, log_n};
+  const EairZerofiers iz = {izt + jj * B + (i & (B - 1)), ianchor + (jj << log_n) + i};
   const Fp gx = plde[(j * 2 + 0) * B + (i & (B - 1))], gy = plde[(j * 2 + 1) * B + (i & (B - 1))];
   cp[idx] = ecdsa_air_point(c, nx, gx, gy, *K, iz);
 }

@@ -51,9 +51,11 @@ SPG_HD Fp eair_double(const Fp* a, const Fp& QX, const Fp& QY, const Fp& QXn, co
   return fp_add(fp_add(fp_mul(a[0], d1), fp_mul(a[1], d2)), fp_mul(a[2], d3));
 }
 
-// c / n: the 25 cells at x and at x w_N; (gx, gy): lane A's periodic point at x; iz[7]: inverse zerofiers of the groups.
-// Returns the composition value (Montgomery, canonical).
-SPG_HD Fp ecdsa_air_point(const Fp* c, const Fp* n, const Fp& gx, const Fp& gy, const EcdsaAirConsts& K, const Fp* iz) {
+// c / n: the 25 cells at x and at x w_N (anything indexable: an array on the host, a loader over the LDE table on the
+// device, so that a cell is fetched where it is used and only one lane's cells are live at a time); (gx, gy): lane A's
+// periodic point at x; iz[7]: inverse zerofiers of the groups.  Returns the composition value (Montgomery, canonical).
+template <class Cells, class Zerofiers>
+SPG_HD Fp ecdsa_air_point(const Cells& c, const Cells& n, const Fp& gx, const Fp& gy, const EcdsaAirConsts& K, const Zerofiers& iz) {
   const Fp* a = K.alpha;
   const Fp one = fp_one();
   // lane A                                                                                   alpha 0 .. 9

@@ -167,6 +167,46 @@ def signed_orders(ctx, n, seed, n_keys=1024):
     return orders, r, s, px, expect, bad, msgs, n_keys, int((sst != 0).sum()) + int((mst != 0).sum())
 
 
+def ecdsa_air(ctx, log_n=20, n_queries=30, verify=True):
+    """The second AIR at the headline trace size: 2^log_n / 256 signatures made on the device, their `verify` walks as a
+    25-column trace (spg_ecdsa_air_trace), one proof (spg_prove_ecdsa), checked by the oracle's verifier."""
+    import random
+    import torch
+    from stark_perpetual_b200._lib import ints_to_limbs, limbs_to_ints
+    from stark_perpetual_b200.ecdsa_air import air_inputs
+    count = (1 << log_n) >> 8
+    rng = random.Random(2026)
+    privs = [rng.randrange(1, 1 << 250) for _ in range(count)]
+    msgs = [rng.randrange(1, 1 << 251) for _ in range(count)]
+    kx, ky, st = ctx.private_to_stark_key(ints_to_limbs(privs), want_y=True)
+    r, s_, st2 = ctx.sign(ints_to_limbs(msgs), ints_to_limbs(privs))
+    assert not st.any() and not st2.any()
+    ri, si = limbs_to_ints(r), limbs_to_ints(s_)
+    keys = list(zip(limbs_to_ints(kx), limbs_to_ints(ky)))
+    m_, r_, w_, kx_, ky_ = air_inputs(msgs, ri, si, keys)
+    trace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx_, ky_)
+    trace_ms = ctx.last_kernel_ms
+    pub = [msgs[0], keys[0][0], ri[0]]
+    d_trace = torch.from_numpy(trace.view(np.int64)).cuda()
+    best, stages = 1e30, None
+    for _ in range(4):
+        proof = ctx.prove_ecdsa(None, log_n, pub, n_queries, device_ptr=d_trace.data_ptr())
+        if ctx.last_kernel_ms < best:
+            best, stages = ctx.last_kernel_ms, [round(ctx.stage_ms(k), 3) for k in range(9)]
+    t0 = time.perf_counter()
+    proof_h = ctx.prove_ecdsa(trace, log_n, pub, n_queries)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    row = {"log_n": log_n, "signatures": count, "trace_ms": trace_ms, "proof_ms": best, "e2e_ms": e2e_ms,
+           "signatures_per_s": count / (best * 1e-3), "proof_bytes": len(proof), "same_proof_from_host_trace": proof_h == proof,
+           "stage_ms": dict(zip(["lde_trace", "merkle_trace", "air_composition", "lde_chunks", "merkle_chunks", "oods_eval",
+                                 "deep_quotient", "fri", "queries"], stages))}
+    if verify:
+        from oracle import stark
+        row["verified_by_oracle"] = stark.verify(proof)["air"] == "ecdsa"
+    del d_trace
+    return row
+
+
 def measure(ctx, sm_mhz=1965.0, with_reference=True, n_orders=65536, hbm_gbs=6452.8):
     from conftest import rand_felts
     from oracle.pedersen import pedersen_hash as o_pedersen
