@@ -289,18 +289,21 @@ int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, unsigned chai
  * The reference has no AIR; what it pins is the computation each 256-row block of this trace encodes, one `verify` call
  * (src/starkware/crypto/signature/signature.py:243-260: zG, rQ, w(zG + rQ) by mimic_ec_mult_air, :176-190, then
  * r == ec_add(wB, -shift).x), with every assertion of those loops held by an inverse cell.
+ * Public input of the statement: the message hash and the key's x of every signature (the two cells the Cairo ECDSA builtin
+ * exposes); r and w are witness.
  * spg_ecdsa_air_trace: msg, r, w, key_x, key_y = [2^log_n / 256] canonical felts each (w = s^-1 mod the curve order, as
  *   verify computes it at :219; the key as a curve point) -> trace_out [25][2^log_n] canonical.  SPG_E_ARG where the
  *   reference asserts (scalar outside [1, 2^251), key off the curve, x collision) or verify() is False.
  * spg_air_eval_ecdsa: composition polynomial of such a trace on the cosets 0, 2, 4, 6 -> cp_out [4][2^log_n] canonical
- *   (parity entry point; pub3 = msg_hash, key x, r of signature 0 -- the public anchors; alpha canonical; host pointers).
- * spg_prove_ecdsa: the protocol of spg_prove over this AIR; proof header VERSION = 2. */
+ *   (parity entry point; msgs, key_x = the public input, [2^log_n / 256] canonical each; alpha canonical; host pointers).
+ * spg_prove_ecdsa: the protocol of spg_prove over this AIR; proof header VERSION = 2 followed by the public input
+ *   (msg, key x per signature).  msgs / key_x are host arrays whatever `flags` says about the trace. */
 int spg_ecdsa_air_trace(spg_ctx* ctx, unsigned log_n, const uint64_t* msg, const uint64_t* r, const uint64_t* w,
                         const uint64_t* key_x, const uint64_t* key_y, uint64_t* trace_out, int flags);
-int spg_air_eval_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* pub3, const uint64_t* alpha,
-                       uint64_t* cp_out, int flags);
-int spg_prove_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* pub3, unsigned n_queries,
-                    uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
+int spg_air_eval_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* msgs, const uint64_t* key_x,
+                       const uint64_t* alpha, uint64_t* cp_out, int flags);
+int spg_prove_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* msgs, const uint64_t* key_x,
+                    unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
 
 /* ---- multi-GPU prover: one process per GPU, NCCL called from inside libspg (DESIGN.md "Multi-GPU") ----------------------
  * spg_comm_unique_id: rank 0 obtains a 128-byte NCCL id and hands it to the other ranks by any means (the Python host side

@@ -490,10 +490,10 @@ def verify(proof, min_queries=MIN_QUERIES):
         x0 = [rd.felt() for _ in range(LANES)]
         outs = [rd.felt() for _ in range(LANES)]
         air = Air(log_n, chain_log, x0, outs)
-    else:                                          # the ECDSA-builtin AIR: public anchors (msg, key, r) of instance 0
+    else:                                          # the ECDSA-builtin AIR: public (msg_hash, key x) of every block
         from .stark_ecdsa import EcdsaAir
         try:
-            air = EcdsaAir(log_n, [rd.felt() for _ in range(3)])
+            air = EcdsaAir(log_n, [(rd.felt(), rd.felt()) for _ in range(n >> 8)])
         except ValueError as e:
             raise ProofError(str(e))
     root_t, root_h = rd.take(32), rd.take(32)

@@ -19,8 +19,10 @@ sum BEFORE step t, (QX, QY) the doubled point 2^t Q (lane A: periodic columns 2^
 addition / doubling of step t, I = 1 / (PX - QX) (the `partial_sum[0] != point[0]` assertion).  T1 carries r of the
 block's signature, T2 the r of the signature lane C is finishing; V1, V2 (row 0) invert the scalars (`0 < m`).
 Scalars are unpacked into 251 bits (M = 0 on rows 251..255: `assert m == 0` after N_ELEMENT_BITS_ECDSA steps).
-Public input: (msg_hash, key x, r) of signature 0 -- anchors at row 0; the other instances' cells are what a memory
-argument would bind (the Cairo layout's job; out of scope).
+Public input: the list of (msg_hash, key x) of every signature -- the two cells the Cairo ECDSA builtin exposes; (r, w) stay
+witness.  The lists enter as two polynomials of degree < N/256 interpolating them over the block-start rows
+(x^(N/256) = 1), compared with the cells M_A and QX_B on exactly those rows; the verifier evaluates them at the
+out-of-domain point itself.
 """
 from .params import ALPHA, BETA, EC_GEN, FIELD_PRIME as P, MINUS_SHIFT_POINT, N_ELEMENT_BITS_ECDSA, SHIFT_POINT, root_of_unity
 from .curve import ec_add, ec_double
@@ -34,7 +36,7 @@ NBITS = N_ELEMENT_BITS_ECDSA                      # 251 steps per scalar
  BM, BPX, BPY, BQX, BQY, BSA, BSD, BI,
  CM, CPX, CPY, CQX, CQY, CSA, CSD, CI,
  T1, T2, V1, V2) = range(N_COLS)
-N_ALPHA = 53
+N_ALPHA = 52
 KIND = 2
 assert ALPHA == 1
 
@@ -124,13 +126,18 @@ class EcdsaAir:
     n_alpha = N_ALPHA
 
     def __init__(self, log_n, pub):
-        """pub = (msg_hash, key x, r) of signature 0"""
+        """pub = [(msg_hash, key x)] of the N/256 signatures"""
         if log_n < 9:
             raise ValueError("log_n too small")
         self.log_n, self.n = log_n, 1 << log_n
-        self.pub = [v % P for v in pub]
-        if not (0 < self.pub[0] < 1 << NBITS and 0 < self.pub[2] < 1 << NBITS):
+        self.pub = [(m % P, k % P) for m, k in pub]
+        if len(self.pub) != self.n // BLOCK:
+            raise ValueError("public input must list one (msg_hash, key) pair per block")
+        if not all(0 < m < 1 << NBITS for m, _k in self.pub):
             raise ValueError("public scalar out of range")              # signature.py:219-227
+        # the public columns: F(w_nb^b) = value of block b, as polynomials in x of degree < nb
+        self.fm_coef = ontt.ntt([m for m, _k in self.pub], inverse=True)
+        self.fk_coef = ontt.ntt([k for _m, k in self.pub], inverse=True)
         self.w256 = root_of_unity(8)
         gx, gy = doubled_generator()
         self.gx, self.gy = gx, gy
@@ -139,27 +146,33 @@ class EcdsaAir:
     # ---- protocol hooks (same set as stark.Air)
     def seed(self, n_queries):
         return (b"ecdsa-builtin" + self.log_n.to_bytes(4, "little") + n_queries.to_bytes(4, "little")
-                + b"".join(ser(v) for v in self.pub))
+                + b"".join(ser(m) + ser(k) for m, k in self.pub))
 
     def header(self, n_queries, n_folds):
         return b"".join([stark.MAGIC, self.kind.to_bytes(4, "little"), self.log_n.to_bytes(4, "little"), (0).to_bytes(4, "little"),
-                         n_queries.to_bytes(4, "little"), n_folds.to_bytes(4, "little")] + [ser(v) for v in self.pub])
+                         n_queries.to_bytes(4, "little"), n_folds.to_bytes(4, "little")] + [ser(m) + ser(k) for m, k in self.pub])
 
     def statement(self):
-        return {"log_n": self.log_n, "air": "ecdsa", "msg0": self.pub[0], "key0": self.pub[1], "r0": self.pub[2]}
+        return {"log_n": self.log_n, "air": "ecdsa", "msgs": [m for m, _k in self.pub], "keys": [k for _m, k in self.pub]}
 
     def periodic_lde(self):
         g256 = pow(stark.GEN, self.n // BLOCK, P)
         gx_lde = ontt.lde(self.gx, stark.LOG_BLOWUP, g256)              # [j][i mod 256]
         gy_lde = ontt.lde(self.gy, stark.LOG_BLOWUP, g256)
-        return lambda j, i: (gx_lde[j][i % BLOCK], gy_lde[j][i % BLOCK])
+        pad = [0] * (self.n - len(self.pub))
+        fm_lde = ontt.lde(ontt.ntt(self.fm_coef + pad), stark.LOG_BLOWUP, stark.GEN)     # [j][i]: F at the LDE points
+        fk_lde = ontt.lde(ontt.ntt(self.fk_coef + pad), stark.LOG_BLOWUP, stark.GEN)
+        return lambda j, i: (gx_lde[j][i % BLOCK], gy_lde[j][i % BLOCK], fm_lde[j][i], fk_lde[j][i])
 
     def periodic_at(self, x):
         u = pow(x, self.n // BLOCK, P)
         hx = hy = 0
         for cx, cy in zip(reversed(self.gx_coef), reversed(self.gy_coef)):
             hx, hy = (hx * u + cx) % P, (hy * u + cy) % P
-        return hx, hy
+        fm = fk = 0
+        for cm, ck in zip(reversed(self.fm_coef), reversed(self.fk_coef)):
+            fm, fk = (fm * x + cm) % P, (fk * x + ck) % P
+        return hx, hy, fm, fk
 
     def inv_zerofiers(self, x):
         u = pow(x, self.n // BLOCK, P)
@@ -177,7 +190,6 @@ class EcdsaAir:
             "first": inv(u - 1),                   # t = 0
             "last": inv(e_last),                   # t = 255
             "thold": e_last * iz_all % P,          # every row but t = 255
-            "anchor": inv(x - 1),                  # row 0 of the trace
         }
 
     @staticmethod
@@ -200,7 +212,7 @@ class EcdsaAir:
         return (a[0] * d1 + a[1] * d2 + a[2] * d3) % P
 
     def composition_per(self, cur, nxt, per, iz, a):
-        gx, gy = per
+        gx, gy, fm, fk = per
         sx, sy = SHIFT_POINT
         c, n = cur, nxt
         # ---- lane A: z G, shift -S, point = periodic (gx, gy)                                  alpha 0 .. 9
@@ -234,16 +246,15 @@ class EcdsaAir:
         first += a[45] * (c[T1] - c[BM]) + a[46] * (c[V1] * c[AM] % P * c[BM] - 1) + a[47] * (c[V2] * c[CM] - 1)
         # ---- carriers hold inside a block                                                      alpha 48, 49
         thold = a[48] * (n[T1] - c[T1]) + a[49] * (n[T2] - c[T2])
-        # ---- public anchors, row 0 of the trace                                                alpha 50 .. 52
-        anchor = a[50] * (c[AM] - self.pub[0]) + a[51] * (c[BQX] - self.pub[1]) + a[52] * (c[BM] - self.pub[2])
+        # ---- public input on the block-start rows: the message and the key's x                 alpha 50, 51
+        first += a[50] * (c[AM] - fm) + a[51] * (c[BQX] - fk)
         acc = (step % P * iz["step"] + hold % P * iz["hold"] + zero % P * iz["zero"] + first % P * iz["first"]
-               + last % P * iz["last"] + thold % P * iz["thold"] + anchor % P * iz["anchor"])
+               + last % P * iz["last"] + thold % P * iz["thold"])
         return acc % P
 
 
 def public_of(sigs):
-    z, r, w, key = sigs[0]
-    return [z, key[0], r]
+    return [(z, key[0]) for z, _r, _w, key in sigs]
 
 
 def prove(log_n, sigs, n_queries=30, corrupt=None, debug=None):

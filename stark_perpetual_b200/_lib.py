@@ -56,8 +56,8 @@ def _load():
             "spg_air_eval": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, vp, vp, vp, C.c_int]),
             "spg_prove": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_ecdsa_air_trace": (C.c_int, [vp, C.c_uint, vp, vp, vp, vp, vp, vp, C.c_int]),
-            "spg_air_eval_ecdsa": (C.c_int, [vp, vp, C.c_uint, vp, vp, vp, C.c_int]),
-            "spg_prove_ecdsa": (C.c_int, [vp, vp, C.c_uint, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
+            "spg_air_eval_ecdsa": (C.c_int, [vp, vp, C.c_uint, vp, vp, vp, vp, C.c_int]),
+            "spg_prove_ecdsa": (C.c_int, [vp, vp, C.c_uint, vp, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_ecdsa_verify_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_private_to_stark_key_batch": (C.c_int, [vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
             "spg_sign_batch": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_size_t, C.c_int]),
@@ -533,28 +533,33 @@ class Context:
         self._check(self._lib.spg_ecdsa_air_trace(self._h, log_n, *[_ptr(a) for a in arrs], _ptr(out), 0))
         return out
 
-    def air_eval_ecdsa(self, trace, log_n, pub3, alpha):
+    def air_eval_ecdsa(self, trace, log_n, msgs, key_x, alpha):
         tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
         assert tr.shape[0] == 25 << log_n
-        pa, aa = ints_to_limbs(pub3), ints_to_limbs([alpha])
+        ma = np.ascontiguousarray(msgs, dtype=np.uint64).reshape(-1, 4)
+        ka = np.ascontiguousarray(key_x, dtype=np.uint64).reshape(-1, 4)
+        assert ma.shape[0] == ka.shape[0] == (1 << log_n) >> 8
+        aa = ints_to_limbs([alpha])
         cp = np.empty((4 << log_n, 4), dtype=np.uint64)
-        self._check(self._lib.spg_air_eval_ecdsa(self._h, _ptr(tr), log_n, _ptr(pa), _ptr(aa), _ptr(cp), 0))
+        self._check(self._lib.spg_air_eval_ecdsa(self._h, _ptr(tr), log_n, _ptr(ma), _ptr(ka), _ptr(aa), _ptr(cp), 0))
         return cp
 
-    def prove_ecdsa(self, trace, log_n, pub3, n_queries=30, device_ptr=None):
-        """Proof that every block of `trace` is a verifying signature; pub3 = (msg_hash, key x, r) of signature 0."""
-        pa = ints_to_limbs(pub3)
-        assert pa.shape[0] == 3
+    def prove_ecdsa(self, trace, log_n, msgs, key_x, n_queries=30, device_ptr=None):
+        """Proof that block b of `trace` is a verifying signature on msgs[b] under the key with x = key_x[b], for every b;
+        msgs, key_x: (2^log_n / 256, 4) uint64 canonical (host) -- the public input, carried in the proof header."""
+        ma = np.ascontiguousarray(msgs, dtype=np.uint64).reshape(-1, 4)
+        ka = np.ascontiguousarray(key_x, dtype=np.uint64).reshape(-1, 4)
+        assert ma.shape[0] == ka.shape[0] == (1 << log_n) >> 8
         if device_ptr is None:
             tr = np.ascontiguousarray(trace, dtype=np.uint64).reshape(-1, 4)
             assert tr.shape[0] == 25 << log_n
             tp, flags = _ptr(tr), 0
         else:
             tp, flags = C.c_void_p(device_ptr), SPG_DEVICE_PTRS
-        cap = 64 + 64 * 32 + 64 * 32 + 128 * 32 + n_queries * (8 * 29 + 8 * 8 + 10 * 24) * 32 + 65536
+        cap = 64 + 64 * 32 + 64 * 32 + 128 * 32 + n_queries * (8 * 29 + 8 * 8 + 10 * 24) * 32 + 65536 + 64 * ma.shape[0]
         buf = np.empty(cap, dtype=np.uint8)
         ln = C.c_size_t(0)
-        self._check(self._lib.spg_prove_ecdsa(self._h, tp, log_n, _ptr(pa), n_queries, _ptr(buf), cap, C.byref(ln), flags))
+        self._check(self._lib.spg_prove_ecdsa(self._h, tp, log_n, _ptr(ma), _ptr(ka), n_queries, _ptr(buf), cap, C.byref(ln), flags))
         return buf[:ln.value].tobytes()
 
     # ---- multi-GPU (one process per GPU) ----

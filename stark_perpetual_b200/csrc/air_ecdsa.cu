@@ -15,8 +15,8 @@ static Fp eh_small(uint64_t v) { uint64_t w[4] = {v, 0, 0, 0}; return spg_host_f
 static int ensure_eair_tables(spg_ctx* ctx, unsigned log_n) {
   if (ctx->eair_log_n == (int)log_n) return SPG_OK;
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(ctx->eair_izt); cudaFree(ctx->eair_plde); cudaFree(ctx->eair_ianchor);
-  ctx->eair_izt = ctx->eair_plde = ctx->eair_ianchor = nullptr;
+  cudaFree(ctx->eair_izt); cudaFree(ctx->eair_plde);
+  ctx->eair_izt = ctx->eair_plde = nullptr;
   ctx->eair_log_n = -1;
   const size_t n = (size_t)1 << log_n;
   const int B = SPG_EAIR_BLOCK;
@@ -70,14 +70,7 @@ static int ensure_eair_tables(spg_ctx* ctx, unsigned log_n) {
   spg_host_to_u64(g256, off);
   int rc = spg_lde_device(ctx, dp.as<Fp>(), 8, 2, SPG_LOG_BLOWUP, off, ctx->eair_plde, dcoef.as<Fp>(), 0);
   if (rc) return rc;
-  // 1 / (x - 1) on cosets 0, 2, 4, 6 (the public anchors of row 0)
-  DevBuf d1;
-  SPG_CUDA(d1.alloc(ctx, sizeof(Fp)));
-  SPG_CUDA(cudaMemcpyAsync(d1.p, &one, sizeof(Fp), cudaMemcpyHostToDevice, ctx->stream));
-  SPG_CUDA(cudaMalloc((void**)&ctx->eair_ianchor, 4 * n * sizeof(Fp)));
-  rc = spg_inv_x_minus_device(ctx, log_n, 0, 2, 4, d1.as<Fp>(), 1, ctx->eair_ianchor);
-  if (rc) return rc;
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));      // `one` and pcols are host objects
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));      // pcols is a host object
   ctx->eair_log_n = (int)log_n;
   return SPG_OK;
 }
@@ -89,12 +82,12 @@ struct EairCells {
   __device__ __forceinline__ Fp operator[](int k) const { return p[(size_t)k << log_n]; }
 };
 struct EairZerofiers {
-  const Fp* __restrict__ izt; const Fp* __restrict__ anchor;
-  __device__ __forceinline__ Fp operator[](int g) const { return g < 6 ? izt[(size_t)g * 4 * SPG_EAIR_BLOCK] : *anchor; }
+  const Fp* __restrict__ izt;
+  __device__ __forceinline__ Fp operator[](int g) const { return izt[(size_t)g * 4 * SPG_EAIR_BLOCK]; }
 };
 __global__ void __launch_bounds__(128) k_air_eval_ecdsa(unsigned log_n, const Fp* __restrict__ t_lde,
                                                         const EcdsaAirConsts* __restrict__ K, const Fp* __restrict__ izt,
-                                                        const Fp* __restrict__ plde, const Fp* __restrict__ ianchor,
+                                                        const Fp* __restrict__ plde, const Fp* __restrict__ pub_lde,
                                                         Fp* __restrict__ cp, int first_coset, int jj0, int n_even) {
   const size_t n = (size_t)1 << log_n;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -104,20 +97,62 @@ __global__ void __launch_bounds__(128) k_air_eval_ecdsa(unsigned log_n, const Fp
   const int B = SPG_EAIR_BLOCK;
   const Fp* base = t_lde + ((j - first_coset) * SPG_EAIR_COLS << log_n);
   const EairCells c = {base + i, log_n}, nx = {base + in, log_n};
-  const EairZerofiers iz = {izt + jj * B + (i & (B - 1)), ianchor + (jj << log_n) + i};
+  const EairZerofiers iz = {izt + jj * B + (i & (B - 1))};
   const Fp gx = plde[(j * 2 + 0) * B + (i & (B - 1))], gy = plde[(j * 2 + 1) * B + (i & (B - 1))];
-  cp[idx] = ecdsa_air_point(c, nx, gx, gy, *K, iz);
+  const Fp* pl = pub_lde + (((jj - jj0) * 2) << log_n) + i;          // public columns on coset 2 jj: [jj - jj0][2][N]
+  cp[idx] = ecdsa_air_point(c, nx, gx, gy, pl[0], pl[n], *K, iz);
 }
 
-static void eair_consts(spg_ctx* ctx, const Fp* pub3, const Fp* alpha_pows, EcdsaAirConsts& K) {
+static void eair_consts(spg_ctx* ctx, const Fp* alpha_pows, EcdsaAirConsts& K) {
   for (int k = 0; k < SPG_EAIR_NALPHA; k++) K.alpha[k] = alpha_pows[k];
   K.shift_x = ctx->h_const_points[0]; K.shift_y = ctx->h_const_points[1];
   K.minus_shift_y = fp_reduce(fp_neg(K.shift_y));
   K.beta = spg_host_from_u64(SPG_BETA);
-  for (int k = 0; k < 3; k++) K.pub[k] = pub3[k];
 }
 
-int spg_eair_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* pub3, const Fp* h_alpha_pows, Fp* cp,
+// The public columns.  d_pub: [2][N/256] canonical (message hashes, keys' x), device.  coef_small [2][N/256] receives the
+// interpolants' coefficients c_k g^k (Montgomery, bit-reversed: what spg_lde_coeffs writes); pub_lde [n_even][2][N] their
+// values on the cosets 2 jj, jj in [jj0, jj0 + n_even).  A polynomial of degree < N/256 over the size-N domain is the same
+// coefficient vector zero-padded, and in bit-reversed order coefficient k of the small transform sits at position 256 q of
+// the big one (q its small position): one strided copy, then the ordinary coset transforms.
+int spg_eair_public_device(spg_ctx* ctx, unsigned log_n, const Fp* d_pub, Fp* coef_small, Fp* pub_lde, int jj0, int n_even) {
+  const size_t n = (size_t)1 << log_n, nb = n >> 8;
+  int rc = spg_lde_coeffs_device(ctx, d_pub, log_n - 8, 2, nullptr, coef_small, /*mont=*/1);
+  if (rc) return rc;
+  DevBuf pad;
+  SPG_CUDA(pad.alloc(ctx, 2 * n * sizeof(Fp)));
+  SPG_CUDA(cudaMemsetAsync(pad.p, 0, 2 * n * sizeof(Fp), ctx->stream));
+  for (int c = 0; c < 2; c++)
+    SPG_CUDA(cudaMemcpy2DAsync(pad.as<Fp>() + c * n, SPG_EAIR_BLOCK * sizeof(Fp), coef_small + c * nb, sizeof(Fp), sizeof(Fp), nb,
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int e = 0; e < n_even; e++)
+    if ((rc = spg_lde_cosets_device(ctx, pad.as<Fp>(), log_n, 2, SPG_LOG_BLOWUP, 2 * (size_t)(jj0 + e), 1, pub_lde + ((size_t)e * 2 << log_n))))
+      return rc;
+  return SPG_OK;
+}
+
+// the two public polynomials at an out-of-domain point z (host Horner over the bit-reversed coefficients): out[0] = F_msg(z),
+// out[1] = F_key(z)
+int spg_eair_public_at_host(spg_ctx* ctx, unsigned log_n, const Fp* d_coef_small, const Fp& z, Fp* out) {
+  const unsigned lb = log_n - 8;
+  const size_t nb = (size_t)1 << lb;
+  std::vector<Fp> cf(2 * nb);
+  SPG_CUDA(cudaMemcpyAsync(cf.data(), d_coef_small, cf.size() * sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  const Fp y = fp_mul(z, fp_inv(eh_small(3)));       // the coefficients carry g^k
+  Fp pw = fp_one();
+  out[0] = out[1] = fp_zero();
+  for (size_t k = 0; k < nb; k++) {
+    size_t q = 0;
+    for (unsigned b = 0; b < lb; b++) q |= ((k >> b) & 1) << (lb - 1 - b);
+    out[0] = fp_add(out[0], fp_mul(cf[q], pw));
+    out[1] = fp_add(out[1], fp_mul(cf[nb + q], pw));
+    pw = fp_mul(pw, y);
+  }
+  return SPG_OK;
+}
+
+int spg_eair_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* pub_lde, const Fp* h_alpha_pows, Fp* cp,
                          int first_coset, int jj0, int n_even) {
   if (n_even <= 0) return SPG_OK;
   SPG_ARG(2 * jj0 >= first_coset && jj0 + n_even <= 4, "ecdsa air eval: coset range");
@@ -125,34 +160,32 @@ int spg_eair_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp
   int rc = ensure_eair_tables(ctx, log_n);
   if (rc) return rc;
   EcdsaAirConsts K;
-  eair_consts(ctx, pub3, h_alpha_pows, K);
+  eair_consts(ctx, h_alpha_pows, K);
   void* dk;
   SPG_CUDA(spg_scratch(ctx, 7, sizeof(EcdsaAirConsts) + 4096, &dk));
   SPG_CUDA(cudaMemcpyAsync(dk, &K, sizeof(K), cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));   // K is a stack object
   const size_t total = (size_t)n_even << log_n;
   k_air_eval_ecdsa<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(log_n, t_lde, (const EcdsaAirConsts*)dk, ctx->eair_izt,
-                                                                            ctx->eair_plde, ctx->eair_ianchor, cp, first_coset,
-                                                                            jj0, n_even);
+                                                                            ctx->eair_plde, pub_lde, cp, first_coset, jj0, n_even);
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }
 
 // ------------------------------------------------------------------ host evaluation at one point (prover self-check)
-Fp spg_eair_composition_at_host(spg_ctx* ctx, unsigned log_n, const Fp* pub3, const Fp* alpha_pows, const Fp& z, const Fp* tz,
-                                const Fp* tzw) {
+Fp spg_eair_composition_at_host(spg_ctx* ctx, unsigned log_n, const Fp* pub_z /*F_msg(z), F_key(z)*/, const Fp* alpha_pows,
+                                const Fp& z, const Fp* tz, const Fp* tzw) {
   const uint64_t n = 1ull << log_n;
   const int B = SPG_EAIR_BLOCK;
   const Fp one = fp_one();
   EcdsaAirConsts K;
-  eair_consts(ctx, pub3, alpha_pows, K);
+  eair_consts(ctx, alpha_pows, K);
   const Fp u = fp_pow_u64(z, n >> 8), w256 = spg_host_root_of_unity(8);
   const Fp iz_all = fp_inv(fp_sub(fp_pow_u64(z, n), one));
   Fp t4 = one;
   for (int t = SPG_EAIR_BITS; t < B - 1; t++) t4 = fp_mul(t4, fp_sub(u, fp_pow_u64(w256, t)));
   const Fp el = fp_sub(u, fp_pow_u64(w256, B - 1)), t5 = fp_mul(t4, el);
-  Fp iz[SPG_EAIR_NGROUPS] = {fp_mul(t5, iz_all), fp_inv(t4), fp_inv(t5), fp_inv(fp_sub(u, one)), fp_inv(el), fp_mul(el, iz_all),
-                             fp_inv(fp_sub(z, one))};
+  Fp iz[SPG_EAIR_NGROUPS] = {fp_mul(t5, iz_all), fp_inv(t4), fp_inv(t5), fp_inv(fp_sub(u, one)), fp_inv(el), fp_mul(el, iz_all)};
   // periodic columns at z: Lagrange over the 256-th roots, L_r(u) = (u^256 - 1) w^r / (256 (u - w^r)), one batch inversion
   Fp gx = fp_zero(), gy = fp_zero();
   {
@@ -173,7 +206,7 @@ Fp spg_eair_composition_at_host(spg_ctx* ctx, unsigned log_n, const Fp* pub3, co
       }
     }
   }
-  return ecdsa_air_point(tz, tzw, gx, gy, K, iz);
+  return ecdsa_air_point(tz, tzw, gx, gy, pub_z[0], pub_z[1], K, iz);
 }
 
 // ------------------------------------------------------------------ witness generation
@@ -369,29 +402,32 @@ extern "C" int spg_ecdsa_air_trace(spg_ctx* ctx, unsigned log_n, const uint64_t*
 }
 
 // composition polynomial of an ECDSA-AIR trace on the cosets j = 0, 2, 4, 6 (parity entry point for the AIR stage):
-// trace [25][N] canonical -> cp [4][N] canonical; pub3 = (msg_hash, key x, r) of signature 0, alpha: canonical.
-extern "C" int spg_air_eval_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* pub3, const uint64_t* alpha,
-                                  uint64_t* cp_out, int flags) {
+// trace [25][N] canonical -> cp [4][N] canonical; msgs, key_x [N/256] canonical = the public input; alpha canonical.
+extern "C" int spg_air_eval_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* msgs, const uint64_t* key_x,
+                                  const uint64_t* alpha, uint64_t* cp_out, int flags) {
   SPG_LOCK(ctx);
-  SPG_ARG(ctx && trace && pub3 && alpha && cp_out, "spg_air_eval_ecdsa: null");
+  SPG_ARG(ctx && trace && msgs && key_x && alpha && cp_out, "spg_air_eval_ecdsa: null");
   SPG_ARG(log_n >= 9 && log_n <= 23, "spg_air_eval_ecdsa: size");
   SPG_ARG(!(flags & SPG_DEVICE_PTRS), "spg_air_eval_ecdsa: host pointers only");
   SPG_CUDA(cudaSetDevice(ctx->device));
-  const size_t n = (size_t)1 << log_n;
+  const size_t n = (size_t)1 << log_n, nb = n >> 8;
   const int C = SPG_EAIR_COLS;
-  DevBuf dt, dl, dc, dcp;
+  DevBuf dt, dl, dc, dcp, dpub, dcs, dpl;
   SPG_CUDA(dt.alloc(ctx, C * n * 32)); SPG_CUDA(dl.alloc(ctx, 8 * C * n * 32)); SPG_CUDA(dc.alloc(ctx, C * n * 32));
-  SPG_CUDA(dcp.alloc(ctx, 4 * n * 32));
+  SPG_CUDA(dcp.alloc(ctx, 4 * n * 32)); SPG_CUDA(dpub.alloc(ctx, 2 * nb * 32)); SPG_CUDA(dcs.alloc(ctx, 2 * nb * 32));
+  SPG_CUDA(dpl.alloc(ctx, 8 * n * 32));
   SPG_CUDA(cudaMemcpyAsync(dt.p, trace, C * n * 32, cudaMemcpyHostToDevice, ctx->stream));
-  Fp pub[3], apows[SPG_EAIR_NALPHA];
-  for (int k = 0; k < 3; k++) pub[k] = spg_host_from_u64(pub3 + 4 * k);
+  SPG_CUDA(cudaMemcpyAsync(dpub.p, msgs, nb * 32, cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(dpub.as<Fp>() + nb, key_x, nb * 32, cudaMemcpyHostToDevice, ctx->stream));
+  Fp apows[SPG_EAIR_NALPHA];
   const Fp a = spg_host_from_u64(alpha);
   apows[0] = fp_one();
   for (int k = 1; k < SPG_EAIR_NALPHA; k++) apows[k] = fp_mul(apows[k - 1], a);
   int rc = spg_lde_device(ctx, dt.as<Fp>(), log_n, C, SPG_LOG_BLOWUP, nullptr, dl.as<Fp>(), dc.as<Fp>(), 1);
   if (rc) return rc;
   SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  rc = spg_eair_eval_device(ctx, log_n, dl.as<Fp>(), pub, apows, dcp.as<Fp>(), 0, 0, 4);
+  if ((rc = spg_eair_public_device(ctx, log_n, dpub.as<Fp>(), dcs.as<Fp>(), dpl.as<Fp>(), 0, 4))) return rc;
+  rc = spg_eair_eval_device(ctx, log_n, dl.as<Fp>(), dpl.as<Fp>(), apows, dcp.as<Fp>(), 0, 0, 4);
   if (rc) return rc;
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   rc = spg_from_mont_device(ctx, dcp.as<Fp>(), 4 * n);

@@ -75,7 +75,6 @@ struct spg_ctx {
   int eair_log_n = -1;
   Fp* eair_izt = nullptr;     // [6][4][256] block-periodic inverse zerofiers on cosets 0,2,4,6
   Fp* eair_plde = nullptr;    // [8][2][256] lane A's periodic point 2^t G on the LDE cosets
-  Fp* eair_ianchor = nullptr; // [4][N] 1 / (x - 1) on cosets 0,2,4,6
   // per-stage device milliseconds of the last pipeline call (spg_stage_ms)
   double stage_ms[16] = {0};
   cudaEvent_t stage_ev[16][2] = {{nullptr}};

@@ -100,7 +100,7 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
   for (auto& t : ctx->lde_tables) { cudaFree(t.lo); cudaFree(t.hi); cudaFree(t.inv_diag); }
   for (auto& t : ctx->diag_tables) { cudaFree(t.t); cudaFree(t.t0); }
   cudaFree(ctx->air_izt); cudaFree(ctx->air_plde); cudaFree(ctx->air_ilast);
-  cudaFree(ctx->eair_izt); cudaFree(ctx->eair_plde); cudaFree(ctx->eair_ianchor);
+  cudaFree(ctx->eair_izt); cudaFree(ctx->eair_plde);
   for (void* p : ctx->owned) cudaFree(p);
   for (void* p : ctx->scratch_p) cudaFree(p);
   for (auto& b : ctx->pool) cudaFree(b.p);

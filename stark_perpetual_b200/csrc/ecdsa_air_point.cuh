@@ -7,10 +7,10 @@
 #include "fp.cuh"
 
 #define SPG_EAIR_COLS 25
-#define SPG_EAIR_NALPHA 53
+#define SPG_EAIR_NALPHA 52
 #define SPG_EAIR_BLOCK 256
 #define SPG_EAIR_BITS 251          // N_ELEMENT_BITS_ECDSA, signature.py:47
-#define SPG_EAIR_NGROUPS 7         // step, hold, zero, first, last, thold, anchor
+#define SPG_EAIR_NGROUPS 6         // step, hold, zero, first, last, thold
 
 // column indices: lane A (z G, shift -S; the point 2^t G is periodic), lane B (r Q), lane C (w (zG + rQ)), carriers
 enum {
@@ -23,7 +23,6 @@ enum {
 struct EcdsaAirConsts {            // Montgomery form
   Fp alpha[SPG_EAIR_NALPHA];
   Fp shift_x, shift_y, minus_shift_y, beta;
-  Fp pub[3];                       // msg_hash, key x, r of signature 0
 };
 
 // the five step constraints every lane has: bit, addition slope, x, y, x-distinctness (signature.py:183-185)
@@ -53,9 +52,11 @@ SPG_HD Fp eair_double(const Fp* a, const Fp& QX, const Fp& QY, const Fp& QXn, co
 
 // c / n: the 25 cells at x and at x w_N (anything indexable: an array on the host, a loader over the LDE table on the
 // device, so that a cell is fetched where it is used and only one lane's cells are live at a time); (gx, gy): lane A's
-// periodic point at x; iz[7]: inverse zerofiers of the groups.  Returns the composition value (Montgomery, canonical).
+// periodic point at x; (fm, fk): the public columns at x (the polynomials through the message hashes / the keys' x over the
+// block-start rows); iz[6]: inverse zerofiers of the groups.  Returns the composition value (Montgomery, canonical).
 template <class Cells, class Zerofiers>
-SPG_HD Fp ecdsa_air_point(const Cells& c, const Cells& n, const Fp& gx, const Fp& gy, const EcdsaAirConsts& K, const Zerofiers& iz) {
+SPG_HD Fp ecdsa_air_point(const Cells& c, const Cells& n, const Fp& gx, const Fp& gy, const Fp& fm, const Fp& fk,
+                          const EcdsaAirConsts& K, const Zerofiers& iz) {
   const Fp* a = K.alpha;
   const Fp one = fp_one();
   // lane A                                                                                   alpha 0 .. 9
@@ -99,15 +100,13 @@ SPG_HD Fp ecdsa_air_point(const Cells& c, const Cells& n, const Fp& gx, const Fp
   first = fp_add(first, fp_mul(a[47], fp_sub(fp_mul(c[EA_V2], c[EA_CM]), one)));
   // carriers hold inside a block                                                               alpha 48, 49
   const Fp thold = fp_add(fp_mul(a[48], fp_sub(n[EA_T1], c[EA_T1])), fp_mul(a[49], fp_sub(n[EA_T2], c[EA_T2])));
-  // public anchors on row 0 of the trace                                                       alpha 50 .. 52
-  Fp anchor = fp_add(fp_mul(a[50], fp_sub(c[EA_AM], K.pub[0])), fp_mul(a[51], fp_sub(c[EA_BQX], K.pub[1])));
-  anchor = fp_add(anchor, fp_mul(a[52], fp_sub(c[EA_BM], K.pub[2])));
+  // public input on the block-start rows: the message hash and the key's x                     alpha 50, 51
+  first = fp_add(first, fp_add(fp_mul(a[50], fp_sub(c[EA_AM], fm)), fp_mul(a[51], fp_sub(c[EA_BQX], fk))));
   Fp acc = fp_mul(step, iz[0]);
   acc = fp_add(acc, fp_mul(hold, iz[1]));
   acc = fp_add(acc, fp_mul(zero, iz[2]));
   acc = fp_add(acc, fp_mul(first, iz[3]));
   acc = fp_add(acc, fp_mul(last, iz[4]));
   acc = fp_add(acc, fp_mul(thold, iz[5]));
-  acc = fp_add(acc, fp_mul(anchor, iz[6]));
   return fp_reduce(acc);
 }

@@ -14,7 +14,8 @@ struct AirSpec {
   int kind = 1;                         // proof header VERSION: 1 = Pedersen hash chain, 2 = ECDSA builtin
   unsigned chain_log = 0;               // kind 1
   const uint64_t* x0_canon = nullptr;   // kind 1: the 5 lane seeds
-  Fp pub3[3];                           // kind 2: msg_hash, key x, r of signature 0 (Montgomery)
+  const uint64_t* msgs_canon = nullptr; // kind 2: the public input, [N/256] message hashes ...
+  const uint64_t* keys_canon = nullptr; //         ... and [N/256] keys' x (canonical, host)
 };
 #define SPG_MAX_ALPHA (SPG_AIR_LANES * SPG_AIR_NCONSTR)
 static_assert(SPG_EAIR_NALPHA <= SPG_MAX_ALPHA && SPG_EAIR_COLS == SPG_AIR_COLS, "both AIRs share the protocol's shape");
@@ -107,7 +108,10 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
     const char* tag = "ecdsa-builtin";
     seed.insert(seed.end(), tag, tag + 13);
     put_u32(seed, log_n); put_u32(seed, n_queries);
-    for (int k = 0; k < 3; k++) { put_fp(seed, air.pub3[k]); put_fp(proof, air.pub3[k]); }
+    for (size_t b = 0; b < (n >> 8); b++) {
+      const Fp m = spg_host_from_u64(air.msgs_canon + 4 * b), k = spg_host_from_u64(air.keys_canon + 4 * b);
+      put_fp(seed, m); put_fp(seed, k); put_fp(proof, m); put_fp(proof, k);
+    }
   }
   Channel ch(seed);
 
@@ -139,8 +143,16 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
   apows[0] = fp_one();
   for (int k = 1; k < n_alpha; k++) apows[k] = fp_mul(apows[k - 1], alpha);
   spg_stage_begin(ctx, ST_AIR);
+  DevBuf e_pub, e_coef, e_lde;       // kind 2: the public columns (values, coefficients, cosets 0 2 4 6)
   if (pedersen) rc = spg_air_eval_device(ctx, log_n, chain_log, t_lde, pub, apows, cp);
-  else rc = spg_eair_eval_device(ctx, log_n, t_lde, air.pub3, apows, cp);
+  else {
+    const size_t nb = n >> 8;
+    SPG_CUDA(e_pub.alloc(ctx, 2 * nb * 32)); SPG_CUDA(e_coef.alloc(ctx, 2 * nb * 32)); SPG_CUDA(e_lde.alloc(ctx, 8 * n * 32));
+    SPG_CUDA(cudaMemcpyAsync(e_pub.p, air.msgs_canon, nb * 32, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(e_pub.as<Fp>() + nb, air.keys_canon, nb * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = spg_eair_public_device(ctx, log_n, e_pub.as<Fp>(), e_coef.as<Fp>(), e_lde.as<Fp>()))) return rc;
+    rc = spg_eair_eval_device(ctx, log_n, t_lde, e_lde.as<Fp>(), apows, cp);
+  }
   if (rc) return rc;
   if ((rc = spg_cp_split_device(ctx, log_n, cp, hev))) return rc;
   spg_stage_end(ctx, ST_AIR);
@@ -178,8 +190,10 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
   }
   {
     // self-check: the composition recomputed on the host from the trace values at z must equal sum z^m H_m(z^4)
+    Fp pub_z[2];
+    if (!pedersen && (rc = spg_eair_public_at_host(ctx, log_n, e_coef.as<Fp>(), z, pub_z))) return rc;
     const Fp lhs = pedersen ? spg_air_composition_at_host(log_n, chain_log, pub, apows, z, oods, oods + C, ctx->h_const_points)
-                            : spg_eair_composition_at_host(ctx, log_n, air.pub3, apows, z, oods, oods + C);
+                            : spg_eair_composition_at_host(ctx, log_n, pub_z, apows, z, oods, oods + C);
     Fp rhs = fp_zero(), zp = fp_one();
     for (int m = 0; m < 4; m++) { rhs = fp_add(rhs, fp_mul(zp, oods[2 * C + m])); zp = fp_mul(zp, z); }
     if (!fp_eq(lhs, rhs)) { ctx->err = "trace does not satisfy the AIR (composition mismatch at the out-of-domain point)"; return SPG_E_PROOF; }
@@ -315,11 +329,12 @@ extern "C" int spg_prove(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, un
 }
 
 // The same protocol over the ECDSA-builtin AIR (air_ecdsa.cu): trace [25][N] canonical felts as spg_ecdsa_air_trace writes
-// it, pub3 = (msg_hash, key x, r) of signature 0 (canonical).  Proof header VERSION = 2; verifier: oracle/stark.py verify.
-extern "C" int spg_prove_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* pub3, unsigned n_queries,
-                               uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags) {
+// it; msgs, key_x = the public input, [N/256] canonical felts each (host).  Proof header VERSION = 2, followed by the
+// public input; verifier: oracle/stark.py verify.
+extern "C" int spg_prove_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log_n, const uint64_t* msgs, const uint64_t* key_x,
+                               unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags) {
   SPG_LOCK(ctx);
-  SPG_ARG(ctx && trace && pub3 && proof_len, "spg_prove_ecdsa: null");
+  SPG_ARG(ctx && trace && msgs && key_x && proof_len, "spg_prove_ecdsa: null");
   SPG_ARG(log_n >= 9 && log_n <= 23, "spg_prove_ecdsa: log_n must be in [9, 23]");
   SPG_CUDA(cudaSetDevice(ctx->device));
   const size_t n = (size_t)1 << log_n, bytes = (size_t)SPG_AIR_COLS * n * 32;
@@ -333,13 +348,13 @@ extern "C" int spg_prove_ecdsa(spg_ctx* ctx, const uint64_t* trace, unsigned log
     h_trace = (const Fp*)trace;
   }
   AirSpec air;
-  air.kind = 2;
-  for (int k = 0; k < 3; k++) {
-    uint32_t lim[8];
-    for (int q = 0; q < 4; q++) { lim[2 * q] = (uint32_t)pub3[4 * k + q]; lim[2 * q + 1] = (uint32_t)(pub3[4 * k + q] >> 32); }
-    SPG_ARG(!spg_canon_geq_p(lim), "spg_prove_ecdsa: public value >= p");
-    air.pub3[k] = spg_host_from_u64(pub3 + 4 * k);
-  }
+  air.kind = 2; air.msgs_canon = msgs; air.keys_canon = key_x;
+  for (size_t b = 0; b < (n >> 8); b++)
+    for (const uint64_t* v : {msgs + 4 * b, key_x + 4 * b}) {
+      uint32_t lim[8];
+      for (int q = 0; q < 4; q++) { lim[2 * q] = (uint32_t)v[q]; lim[2 * q + 1] = (uint32_t)(v[q] >> 32); }
+      SPG_ARG(!spg_canon_geq_p(lim), "spg_prove_ecdsa: public value >= p");
+    }
   std::vector<uint8_t> proof;
   int rc = prove_device(ctx, d_trace, log_n, air, n_queries, proof, h_trace);
   if (rc) return rc;

@@ -66,11 +66,14 @@ Fp spg_air_composition_at_host(unsigned log_n, unsigned chain_log, const AirPubl
 int spg_pedersen_trace_device(spg_ctx* ctx, unsigned log_n, unsigned chain_log, const Fp* d_x0_canon /*[5]*/,
                               const Fp* d_ys_canon /*[5][N/512]*/, Fp* trace /*[25][N] canonical*/, uint8_t* d_status);
 
-// ---- air_ecdsa.cu: the ECDSA-builtin AIR (same protocol slots as the Pedersen hash-chain AIR; pub3 = msg_hash, key x, r of
-// signature 0, Montgomery)
-int spg_eair_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* pub3, const Fp* h_alpha_pows /*[53]*/, Fp* cp,
+// ---- air_ecdsa.cu: the ECDSA-builtin AIR (same protocol slots as the Pedersen hash-chain AIR).  Public input: the message
+// hashes and the keys' x of all N/256 signatures, as two polynomials over the block-start rows.
+int spg_eair_public_device(spg_ctx* ctx, unsigned log_n, const Fp* d_pub /*[2][N/256] canonical*/, Fp* coef_small /*[2][N/256]*/,
+                           Fp* pub_lde /*[n_even][2][N]*/, int jj0 = 0, int n_even = 4);
+int spg_eair_public_at_host(spg_ctx* ctx, unsigned log_n, const Fp* d_coef_small, const Fp& z, Fp* out /*[2]*/);
+int spg_eair_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* pub_lde, const Fp* h_alpha_pows /*[52]*/, Fp* cp,
                          int first_coset = 0, int jj0 = 0, int n_even = 4);
-Fp spg_eair_composition_at_host(spg_ctx* ctx, unsigned log_n, const Fp* pub3, const Fp* alpha_pows, const Fp& z, const Fp* tz,
-                                const Fp* tzw);
+Fp spg_eair_composition_at_host(spg_ctx* ctx, unsigned log_n, const Fp* pub_z /*[2]*/, const Fp* alpha_pows, const Fp& z,
+                                const Fp* tz, const Fp* tzw);
 int spg_eair_trace_device(spg_ctx* ctx, unsigned log_n, const Fp* msg, const Fp* rr, const Fp* ww, const Fp* kx, const Fp* ky,
                           Fp* trace, uint32_t* d_status);

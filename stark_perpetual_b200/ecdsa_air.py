@@ -29,7 +29,8 @@ def air_inputs(msgs, r, s, keys):
 
 
 def prove_signatures(msgs, r, s, keys, n_queries=30, ctx=None):
-    """Proof that all len(msgs) = 2^k >= 2 signatures verify.  Returns (proof bytes, log_n)."""
+    """Proof that all len(msgs) = 2^k >= 2 signatures verify; the statement (public input, carried by the proof) is the
+    list of (msg_hash, key x).  Returns (proof bytes, log_n)."""
     ctx = ctx or get_context()
     n = len(msgs)
     if n < 2 or n & (n - 1):
@@ -37,4 +38,4 @@ def prove_signatures(msgs, r, s, keys, n_queries=30, ctx=None):
     log_n = (n * BLOCK).bit_length() - 1
     m_, r_, w_, kx, ky = air_inputs(msgs, r, s, keys)
     trace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx, ky)
-    return ctx.prove_ecdsa(trace, log_n, [msgs[0], keys[0][0], r[0]], n_queries), log_n
+    return ctx.prove_ecdsa(trace, log_n, m_, kx, n_queries), log_n

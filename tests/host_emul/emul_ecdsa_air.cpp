@@ -1,6 +1,6 @@
 // CPU run of the ECDSA-builtin AIR's per-point code (csrc/ecdsa_air_point.cuh), compiled with g++.
-// stdin, per case (hex canonical values): gx gy shift_x shift_y beta, 3 public values, 53 alpha powers, 25 cells at x,
-// 25 cells at x w, 7 inverse zerofier values.  stdout: the composition value (canonical hex).
+// stdin, per case (hex canonical values): gx gy shift_x shift_y beta, the 2 public column values, 52 alpha powers, 25 cells
+// at x, 25 cells at x w, 6 inverse zerofier values.  stdout: the composition value (canonical hex).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -27,12 +27,13 @@ int main() {
     EcdsaAirConsts K;
     if (!read_felt(&gy) || !read_felt(&K.shift_x) || !read_felt(&K.shift_y) || !read_felt(&K.beta)) return 1;
     K.minus_shift_y = fp_neg(K.shift_y);
-    for (auto& p : K.pub) if (!read_felt(&p)) return 1;
+    Fp fm, fk;
+    if (!read_felt(&fm) || !read_felt(&fk)) return 1;
     for (auto& a : K.alpha) if (!read_felt(&a)) return 1;
     for (auto& v : cur) if (!read_felt(&v)) return 1;
     for (auto& v : nxt) if (!read_felt(&v)) return 1;
     for (auto& z : iz) if (!read_felt(&z)) return 1;
-    const Fp v = fp_from_mont(ecdsa_air_point(cur, nxt, gx, gy, K, iz));
+    const Fp v = fp_from_mont(ecdsa_air_point(cur, nxt, gx, gy, fm, fk, K, iz));
     uint64_t o[4];
     fp_to_u64(v, o);
     printf("%016llx%016llx%016llx%016llx\n", (unsigned long long)o[3], (unsigned long long)o[2], (unsigned long long)o[1],

@@ -51,16 +51,17 @@ def test_invalid_signature_has_no_trace(sigs2):
 def test_oracle_proof_roundtrip_and_tamper(sigs2):
     proof = se.prove(9, sigs2)
     st = stark.verify(proof)
-    assert st["air"] == "ecdsa" and st["msg0"] == sigs2[0][0] and st["key0"] == sigs2[0][3][0] and st["r0"] == sigs2[0][1]
+    assert st["air"] == "ecdsa" and st["msgs"] == [s[0] for s in sigs2] and st["keys"] == [s[3][0] for s in sigs2]
     # a constrained cell of every kind: scalar, partial sum, doubled point, slope, inverse, carrier, non-zero witness
     for col, row in ((se.AM, 3), (se.BPX, 300), (se.CQY, 17), (se.BSD, 250), (se.CI, 255), (se.T2, 400), (se.V1, 0), (se.ASA, 255)):
         with pytest.raises((ValueError, stark.ProofError)):
             stark.verify(se.prove(9, sigs2, corrupt=(col, row, 1)))
-    # the public anchors are bound: same proof under another statement
-    bad = bytearray(proof)
-    bad[24 + 31] ^= 1
-    with pytest.raises(stark.ProofError):
-        stark.verify(bytes(bad))
+    # every instance's public cells are bound: the same proof under another statement (message 0, key 1) is rejected
+    for off in (24 + 31, 24 + 3 * 32 + 31):
+        bad = bytearray(proof)
+        bad[off] ^= 1
+        with pytest.raises(stark.ProofError):
+            stark.verify(bytes(bad))
     with pytest.raises(stark.ProofError):
         stark.verify(se.prove(9, sigs2, n_queries=12))
 
@@ -70,7 +71,7 @@ def test_emulated_ecdsa_air_point_vs_oracle():
     rng = random.Random(77)
     exe = _build("emul_ecdsa_air")
     air = object.__new__(se.EcdsaAir)
-    names = ["step", "hold", "zero", "first", "last", "thold", "anchor"]
+    names = ["step", "hold", "zero", "first", "last", "thold"]
 
     def draw(mode):
         if mode == 0:
@@ -81,13 +82,12 @@ def test_emulated_ecdsa_air_point_vs_oracle():
     lines, want = [], []
     for case in range(200):
         mode = case if case < 2 else 2
-        gx, gy = draw(mode), draw(mode)
-        air.pub = [draw(mode) for _ in range(3)]
+        gx, gy, fm, fk = (draw(mode) for _ in range(4))
         alpha = [draw(mode) for _ in range(se.N_ALPHA)]
         cur, nxt = [draw(mode) for _ in range(25)], [draw(mode) for _ in range(25)]
-        iz = [draw(mode) for _ in range(7)]
-        want.append(air.composition_per(cur, nxt, (gx, gy), dict(zip(names, iz)), alpha))
-        vals = [gx, gy, SHIFT_POINT[0], SHIFT_POINT[1], BETA] + air.pub + alpha + cur + nxt + iz
+        iz = [draw(mode) for _ in range(6)]
+        want.append(air.composition_per(cur, nxt, (gx, gy, fm, fk), dict(zip(names, iz)), alpha))
+        vals = [gx, gy, SHIFT_POINT[0], SHIFT_POINT[1], BETA, fm, fk] + alpha + cur + nxt + iz
         lines.append(" ".join("%x" % v for v in vals))
     res = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-500:]

@@ -50,7 +50,8 @@ def test_trace_composition_and_proof_bit_exact(log_n):
     apows = [pow(alpha, k, P) for k in range(se.N_ALPHA)]
     lde_cols = [ontt.lde(c, stark.LOG_BLOWUP, stark.GEN) for c in want_cols]
     per = air.periodic_lde()
-    cp = _ints(ctx.air_eval_ecdsa(trace, log_n, pub, alpha))
+    ins = _inputs(sigs)
+    cp = _ints(ctx.air_eval_ecdsa(trace, log_n, ins[0], ins[3], alpha))
     step = 1 if log_n == 9 else 7
     for jj in range(4):
         j = 2 * jj
@@ -60,10 +61,10 @@ def test_trace_composition_and_proof_bit_exact(log_n):
             want = air.composition_per(cur, nxt, per(j, i), air.inv_zerofiers(stark.lde_point(log_n, j, i)), apows)
             assert cp[jj * n + i] == want, (jj, i)
     # whole proof
-    proof = ctx.prove_ecdsa(trace, log_n, pub, 30)
+    proof = ctx.prove_ecdsa(trace, log_n, ins[0], ins[3], 30)
     assert proof == stark.prove_air(air, want_cols, 30)
     st = stark.verify(proof)
-    assert st["air"] == "ecdsa" and st["r0"] == sigs[0][1]
+    assert st["air"] == "ecdsa" and st["msgs"] == [s[0] for s in sigs] and st["keys"] == [s[3][0] for s in sigs]
 
 
 def _gpu_signatures(ctx, count, seed):
@@ -90,7 +91,7 @@ def test_larger_batches_verify_under_the_oracle(log_n):
     proof, ln = prove_signatures(msgs, r, s, keys, ctx=ctx)
     assert ln == log_n
     st = stark.verify(proof)
-    assert st["log_n"] == log_n and st["msg0"] == msgs[0] and st["key0"] == keys[0][0] and st["r0"] == r[0]
+    assert st["log_n"] == log_n and st["msgs"] == msgs and st["keys"] == [k[0] for k in keys]
     # the witness rows follow the reference's verify: spot-check one signature against the oracle's own verify
     from oracle import ecdsa as oe
     assert oe.verify(msgs[3], r[3], s[3], keys[3])
@@ -108,13 +109,17 @@ def test_invalid_inputs_are_refused():
         with pytest.raises(SpgError):
             ctx.ecdsa_air_trace(9, *_inputs([sigs[0], bad]))
     # a tampered trace has no proof (the prover checks the composition at the out-of-domain point)
-    trace = ctx.ecdsa_air_trace(9, *_inputs(sigs))
+    ins = _inputs(sigs)
+    trace = ctx.ecdsa_air_trace(9, *ins)
     for col, row in ((se.BM, 0), (se.CPX, 300), (se.T2, 260), (se.CSA, 511)):
         t2 = trace.copy()
         t2[col * 512 + row, 0] ^= np.uint64(1)
         with pytest.raises(SpgError):
-            ctx.prove_ecdsa(t2, 9, se.public_of(sigs), 30)
-    # wrong public anchors
-    with pytest.raises(SpgError):
-        ctx.prove_ecdsa(trace, 9, [sigs[0][0], sigs[0][3][0], sigs[0][1] ^ 1], 30)
+            ctx.prove_ecdsa(t2, 9, ins[0], ins[3], 30)
+    # a public input that is not what the trace holds (message of signature 1, key of signature 0)
+    for which in (0, 3):
+        pub = [ins[0].copy(), ins[3].copy()]
+        pub[which == 3][1 if which == 0 else 0, 0] ^= np.uint64(1)
+        with pytest.raises(SpgError):
+            ctx.prove_ecdsa(trace, 9, pub[0], pub[1], 30)
     assert EC_ORDER > 0

@@ -186,15 +186,14 @@ def ecdsa_air(ctx, log_n=20, n_queries=30, verify=True):
     m_, r_, w_, kx_, ky_ = air_inputs(msgs, ri, si, keys)
     trace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx_, ky_)
     trace_ms = ctx.last_kernel_ms
-    pub = [msgs[0], keys[0][0], ri[0]]
     d_trace = torch.from_numpy(trace.view(np.int64)).cuda()
     best, stages = 1e30, None
     for _ in range(4):
-        proof = ctx.prove_ecdsa(None, log_n, pub, n_queries, device_ptr=d_trace.data_ptr())
+        proof = ctx.prove_ecdsa(None, log_n, m_, kx_, n_queries, device_ptr=d_trace.data_ptr())
         if ctx.last_kernel_ms < best:
             best, stages = ctx.last_kernel_ms, [round(ctx.stage_ms(k), 3) for k in range(9)]
     t0 = time.perf_counter()
-    proof_h = ctx.prove_ecdsa(trace, log_n, pub, n_queries)
+    proof_h = ctx.prove_ecdsa(trace, log_n, m_, kx_, n_queries)
     e2e_ms = (time.perf_counter() - t0) * 1e3
     row = {"log_n": log_n, "signatures": count, "trace_ms": trace_ms, "proof_ms": best, "e2e_ms": e2e_ms,
            "signatures_per_s": count / (best * 1e-3), "proof_bytes": len(proof), "same_proof_from_host_trace": proof_h == proof,
@@ -202,7 +201,8 @@ def ecdsa_air(ctx, log_n=20, n_queries=30, verify=True):
                                  "deep_quotient", "fri", "queries"], stages))}
     if verify:
         from oracle import stark
-        row["verified_by_oracle"] = stark.verify(proof)["air"] == "ecdsa"
+        st = stark.verify(proof)
+        row["verified_by_oracle"] = st["air"] == "ecdsa" and st["msgs"] == msgs and st["keys"] == [k[0] for k in keys]
     del d_trace
     return row
 
