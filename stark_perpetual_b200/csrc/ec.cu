@@ -83,13 +83,9 @@ __global__ void __launch_bounds__(PEDERSEN_THREADS, PEDERSEN_MIN_CTAS) k_pederse
     do {
       PedersenAcc a;
       a.init(cp[0]);
-      bool ok = pedersen_absorb(a, x, cp + 2);
-      if (k < chain_len) {
-        uint32_t y[8];
-        load_canon((second && k == 1) ? second + i * 4 : e + 4 * k, y);
-        ok = pedersen_absorb(a, y, cp + 2 + SPG_HASH_BITS) && ok;
-      }
-      if (!ok) { st = 2; break; }
+      uint32_t y[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (k < chain_len) load_canon((second && k == 1) ? second + i * 4 : e + 4 * k, y);
+      if (!pedersen_absorb_elems(a, x, y, k < chain_len ? 2 : 1, cp + 2)) { st = 2; break; }
       const Fp zi = fp_inv_chain(a.p.Z), zi2 = fp_sqr(zi);
       res = fp_from_mont(fp_mul(a.p.X, zi2));
       if (out_y) res_y = fp_from_mont(fp_mul(a.p.Y, fp_mul(zi2, zi)));     // pedersen_hash_as_point (signature.py:300)

@@ -162,14 +162,79 @@ SPG_HD bool pedersen_absorb(PedersenAcc& a, const uint32_t (&x)[8], const APoint
 }
 
 
+// ---- the same absorption as ONE stream of set bits over both elements (n_elems = 1: x only).
+// pedersen_absorb branches on the bit inside every step; in a warp some lane almost always has the bit set, so every step
+// pays the 13-multiplication addition although half the lanes idle through it.  Here a thread jumps from set bit to set
+// bit: the additions of a warp's lanes line up (k-th addition with k-th addition), and what differs per lane -- the
+// collision checks of the steps skipped over, one multiplication each (signature.py:313 runs on EVERY step) -- is a
+// short loop.  Same result, same "Unhashable input." detection, ~504 x 14 -> ~275 x 19 multiplications per warp and hash.
+SPG_HD uint32_t ped_word(const uint32_t (&x)[8], const uint32_t (&y)[8], int wi) {
+  uint32_t w = x[0];
+#pragma unroll
+  for (int k = 1; k < 8; k++) w = (wi == k) ? x[k] : w;
+#pragma unroll
+  for (int k = 0; k < 8; k++) w = (wi == 8 + k) ? y[k] : w;
+  return w;
+}
+SPG_HD int ped_ctz(uint32_t w) {
+#ifdef __CUDA_ARCH__
+  return __ffs((int)w) - 1;
+#else
+  return __builtin_ctz(w);
+#endif
+}
+SPG_HD bool pedersen_absorb_stream(PedersenAcc& a, const uint32_t (&x)[8], const uint32_t (&y)[8], int n_elems, const APoint* tab) {
+  bool ok = true;
+  const int total = SPG_HASH_BITS * n_elems, last_word = 8 * n_elems - 1;
+  int s = 0;                      // next step whose collision check is due
+  int wi = 0, base = 0;           // current word of the stream and the step index of its bit 0
+  uint32_t word = x[0];
+#pragma unroll 1
+  for (;;) {
+#pragma unroll 1
+    while (word == 0 && wi < last_word) {
+      wi++;
+      word = ped_word(x, y, wi);
+      base = (wi >> 3) * SPG_HASH_BITS + (wi & 7) * 32;
+    }
+    if (word == 0) break;
+    const int sb = base + ped_ctz(word);
+    word &= word - 1;
+    Fp u2 = fp_zero();
+#pragma unroll 1
+    for (; s <= sb; s++) {        // checks of the skipped steps and of step sb itself, all against the current sum
+      u2 = fp_mul(tab[s].x, a.zz);
+      if (fp_is_zero(fp_sub(u2, a.p.X))) ok = false;
+    }
+    a.p = ec_madd_nocheck(a.p, tab[sb], a.zzz, u2);
+    a.zz = fp_sqr(a.p.Z);
+    a.zzz = fp_mul(a.zz, a.p.Z);
+  }
+#pragma unroll 1
+  for (; s < total; s++)
+    if (fp_is_zero(fp_sub(fp_mul(tab[s].x, a.zz), a.p.X))) ok = false;
+  return ok;
+}
+#ifndef PEDERSEN_STREAM
+#define PEDERSEN_STREAM 1         // 0: the step-by-step absorption (A/B measurements)
+#endif
+// both elements (n_elems = 2) or x alone (n_elems = 1) into the accumulator
+SPG_HD bool pedersen_absorb_elems(PedersenAcc& a, const uint32_t (&x)[8], const uint32_t (&y)[8], int n_elems, const APoint* tab) {
+#if PEDERSEN_STREAM
+  return pedersen_absorb_stream(a, x, y, n_elems, tab);
+#else
+  bool ok = pedersen_absorb(a, x, tab);
+  if (n_elems > 1) ok = pedersen_absorb(a, y, tab + SPG_HASH_BITS) && ok;
+  return ok;
+#endif
+}
+
 // One pedersen_hash(x, y) (signature.py:296-318) of canonical operands already known to be < p; cp = the 506-point table.
 // Returns false on "Unhashable input." (signature.py:313); *out_canon receives the canonical hash.
 SPG_HD bool pedersen_hash2_one(const uint32_t (&x)[8], const uint32_t (&y)[8], const APoint* cp, Fp* out_canon) {
   PedersenAcc a;
   a.init(cp[0]);
-  bool ok = pedersen_absorb(a, x, cp + 2);
-  ok = pedersen_absorb(a, y, cp + 2 + SPG_HASH_BITS) && ok;
-  if (!ok) { *out_canon = fp_zero(); return false; }
+  if (!pedersen_absorb_elems(a, x, y, 2, cp + 2)) { *out_canon = fp_zero(); return false; }
   const Fp zi = fp_inv_chain(a.p.Z);
   *out_canon = fp_from_mont(fp_mul(a.p.X, fp_sqr(zi)));
   return true;

@@ -35,8 +35,15 @@ int main() {
     uint64_t out[4] = {0, 0, 0, 0};
     if (!st) {
       PedersenAcc acc; acc.init(pts[0]);
-      bool ok = pedersen_absorb(acc, x, pts.data() + 2);
-      ok = pedersen_absorb(acc, y, pts.data() + 2 + SPG_HASH_BITS) && ok;
+      // both forms of the absorption must agree: the step-by-step one and the set-bit stream the kernels run
+      PedersenAcc acc2 = acc;
+      bool ok2 = pedersen_absorb(acc2, x, pts.data() + 2);
+      ok2 = pedersen_absorb(acc2, y, pts.data() + 2 + SPG_HASH_BITS) && ok2;
+      bool ok = pedersen_absorb_stream(acc, x, y, 2, pts.data() + 2);
+      if (ok != ok2 || (ok && !(fp_eq(acc.p.X, acc2.p.X) && fp_eq(acc.p.Y, acc2.p.Y) && fp_eq(acc.p.Z, acc2.p.Z)))) {
+        fprintf(stderr, "stream / step absorption disagree\n");
+        return 3;
+      }
       if (!ok) st = 2;
       else {
         Fp zi = fp_inv_chain(acc.p.Z);
