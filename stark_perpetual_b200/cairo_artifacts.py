@@ -20,6 +20,9 @@ itself (tests/test_cairo_artifacts.py).  What is done with them here:
     consistency check of the witness for the largest builtin of a perpetual batch, and check the
     ECDSA instances against signatures supplied by the private input (spg_ecdsa_verify_batch).
 
+  * prove the ECDSA builtin segment with the repo's ECDSA-builtin AIR (`prove_ecdsa_builtin`): one proof whose public input
+    is the segment's (message, key) cells.
+
 The Cairo CPU / memory / range-check AIR itself is NOT implemented (DESIGN.md "Out of scope"): proving these traces needs
 the Cairo layout's constraint system, which is cairo-lang / Stone material and absent from the reference.
 """
@@ -194,6 +197,46 @@ def check_ecdsa_builtin(memory, pub, signatures, ctx=None):
     if bad.size:
         raise ValueError("ecdsa builtin instance %d does not verify (status %d)" % (int(bad[0]), int(st[bad[0]])))
     return n
+
+
+def prove_ecdsa_builtin(memory, pub, signatures, n_queries=30, ctx=None):
+    """One STARK proof (the ECDSA-builtin AIR, csrc/air_ecdsa.cu) that every instance of the ECDSA builtin segment carries
+    a verifying signature: the public input of the proof is exactly the segment's cells -- (message, key x) per instance --
+    so a verifier holding the memory file checks `statement["msgs"] / ["keys"]` against it.  signatures: {instance: (r, s)}
+    from the runner's private input.  The batch is padded to a power of two (>= 2) by repeating instance 0.
+    Returns (proof bytes, log_n, number of real instances)."""
+    from ._lib import ints_to_limbs, limbs_to_ints
+    from .ecdsa_air import BLOCK, air_inputs
+    ctx = ctx or get_context()
+    keys_x, msgs = ecdsa_instances(memory, pub)
+    n = keys_x.shape[0]
+    if n == 0:
+        raise ValueError("the ecdsa segment is empty")
+    if sorted(signatures) != list(range(n)):
+        raise ValueError("private input must carry one signature per ecdsa instance")
+    r = ints_to_limbs([signatures[i][0] for i in range(n)])
+    s = ints_to_limbs([signatures[i][1] for i in range(n)])
+    # the key's y: the builtin cell holds x only; verify() tries both roots (signature.py:229-241) -- keep the one that verifies
+    y, st = ctx.get_y_coordinate(keys_x)
+    if st.any():
+        raise ValueError("ecdsa builtin instance %d: the key is not on the curve" % int(np.nonzero(st)[0][0]))
+    ok = ctx.ecdsa_verify(msgs, r, s, keys_x, y) == 1
+    yi = limbs_to_ints(y)
+    yi = [v if good else FIELD_PRIME - v for v, good in zip(yi, ok)]
+    y = ints_to_limbs(yi)
+    bad = np.nonzero(ctx.ecdsa_verify(msgs, r, s, keys_x, y) != 1)[0]
+    if bad.size:
+        raise ValueError("ecdsa builtin instance %d does not verify" % int(bad[0]))
+    count = 2
+    while count < n:
+        count *= 2
+    idx = list(range(n)) + [0] * (count - n)
+    mi, ri, si, kx = (limbs_to_ints(a) for a in (msgs, r, s, keys_x))
+    m_, r_, w_, kx_, ky_ = air_inputs([mi[i] for i in idx], [ri[i] for i in idx], [si[i] for i in idx],
+                                      [(kx[i], yi[i]) for i in idx])
+    log_n = (count * BLOCK).bit_length() - 1
+    trace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx_, ky_)
+    return ctx.prove_ecdsa(trace, log_n, m_, kx_, n_queries), log_n, n
 
 
 def load(prefix):

@@ -14,6 +14,9 @@ for the AIR this repo implements (the Pedersen hash chain):
   public input   {"log_n": .., "chain_log": .., "x0": ["0x..", x5]}
   parameters     {"n_queries": 30}   (optional)
   prover config  {"device": 0}       (optional)
+For the second AIR (the ECDSA builtin) the public input names it:
+  public input   {"air": "ecdsa", "instances": [{"msg": "0x..", "key": "0x.."}, ...]}   -- a power of two (>= 2) of them
+  private input  {"signatures": [{"r": "0x..", "s": "0x..", "key_y": "0x.."}, ...]}      -- one per instance, in order
 Output: the proof bytes (format: DESIGN.md section 4) and, next to it, `<out_file>.public.json` with the public outputs.
 Traces of the Cairo layouts themselves are not provable here.
 """
@@ -38,6 +41,8 @@ def main(argv=None):
     prv = json.load(open(args.private_input_file))
     params = json.load(open(args.parameter_file)) if args.parameter_file else {}
     cfg = json.load(open(args.prover_config_file)) if args.prover_config_file else {}
+    if pub.get("air") == "ecdsa":
+        return _main_ecdsa(args, pub, prv, params, cfg)
     log_n, chain_log = int(pub["log_n"]), int(pub.get("chain_log", 0))
     x0 = [int(v, 16) if isinstance(v, str) else int(v) for v in pub["x0"]]
     if len(x0) != 5:
@@ -63,6 +68,30 @@ def main(argv=None):
     with open(args.out_file + ".public.json", "w") as f:
         json.dump({"log_n": log_n, "chain_log": chain_log, "x0": [hex(v) for v in x0], "outs": [hex(v) for v in outs],
                    "proof_bytes": len(proof)}, f)
+    return 0
+
+
+def _main_ecdsa(args, pub, prv, params, cfg):
+    from . import Context
+    from ._lib import SpgError
+    from .ecdsa_air import prove_signatures
+
+    def num(v):
+        return int(v, 16) if isinstance(v, str) else int(v)
+    inst, sigs = pub["instances"], prv["signatures"]
+    if len(inst) != len(sigs):
+        raise SystemExit("private input must carry one signature per instance")
+    ctx = Context(int(cfg.get("device", 0)))
+    try:
+        proof, log_n = prove_signatures([num(i["msg"]) for i in inst], [num(s["r"]) for s in sigs], [num(s["s"]) for s in sigs],
+                                        [(num(i["key"]), num(s["key_y"])) for i, s in zip(inst, sigs)],
+                                        int(params.get("n_queries", 30)), ctx=ctx)
+    except (ValueError, SpgError) as e:
+        raise SystemExit("ecdsa air: %s" % e)
+    with open(args.out_file, "wb") as f:
+        f.write(proof)
+    with open(args.out_file + ".public.json", "w") as f:
+        json.dump({"air": "ecdsa", "log_n": log_n, "instances": len(inst), "proof_bytes": len(proof)}, f)
     return 0
 
 

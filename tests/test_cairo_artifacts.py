@@ -89,3 +89,23 @@ def test_builtin_segments_recomputed_on_the_gpu(ctx, tmp_path):
     _t, memory, pub = ca.load(prefix)
     with pytest.raises(ValueError, match="instance 1"):
         ca.check_ecdsa_builtin(memory, pub, sigs, ctx)
+
+
+@pytest.mark.gpu
+def test_ecdsa_builtin_segment_is_proven(ctx, tmp_path):
+    """the ECDSA builtin segment of the artefacts -> one proof of the second AIR whose public input is the segment's cells"""
+    from oracle import stark
+    prefix, sigs = _make(tmp_path, n_sig=3)
+    _trace, memory, pub = ca.load(prefix)
+    proof, log_n, n = ca.prove_ecdsa_builtin(memory, pub, sigs, ctx=ctx)
+    assert (log_n, n) == (10, 3)                       # 3 instances padded to 4 blocks of 256 rows
+    st = stark.verify(proof)
+    keys, msgs = ca.ecdsa_instances(memory, pub)
+    from stark_perpetual_b200._lib import limbs_to_ints
+    assert st["air"] == "ecdsa" and st["msgs"][:3] == limbs_to_ints(msgs) and st["keys"][:3] == limbs_to_ints(keys)
+    assert st["msgs"][3] == st["msgs"][0] and st["keys"][3] == st["keys"][0]
+    (tmp_path / "c").mkdir()
+    prefix, sigs = _make(tmp_path / "c", corrupt=("ecdsa", 1))
+    _t, memory, pub = ca.load(prefix)
+    with pytest.raises(ValueError, match="instance 1"):
+        ca.prove_ecdsa_builtin(memory, pub, sigs, ctx=ctx)

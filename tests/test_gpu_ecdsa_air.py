@@ -123,3 +123,31 @@ def test_invalid_inputs_are_refused():
         with pytest.raises(SpgError):
             ctx.prove_ecdsa(trace, 9, pub[0], pub[1], 30)
     assert EC_ORDER > 0
+
+
+def test_file_level_prover_cli_ecdsa(tmp_path):
+    """the prover CLI (flag set of the one that follows cairo-run, cairo_cmake_rules.cmake:72-110) over the second AIR:
+    instances in the public input file, signatures in the private input file, proof file out"""
+    import json
+    import os
+    import subprocess
+    import sys
+    sigs = se.make_signatures(4, 31)
+    from oracle import ecdsa as oe
+    inst = [{"msg": hex(z), "key": hex(key[0])} for z, _r, _w, key in sigs]
+    prv = [{"r": hex(r), "s": hex(pow(w, -1, EC_ORDER)), "key_y": hex(key[1])} for _z, r, w, key in sigs]
+    assert oe.verify(sigs[0][0], sigs[0][1], int(prv[0]["s"], 16), sigs[0][3])
+    (tmp_path / "public.json").write_text(json.dumps({"air": "ecdsa", "instances": inst}))
+    (tmp_path / "private.json").write_text(json.dumps({"signatures": prv}))
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    cmd = [sys.executable, "-m", "stark_perpetual_b200.cpu_air_prover", "--out_file", str(tmp_path / "proof.bin"),
+           "--private_input_file", str(tmp_path / "private.json"), "--public_input_file", str(tmp_path / "public.json")]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    st = stark.verify((tmp_path / "proof.bin").read_bytes())
+    assert st["msgs"] == [s[0] for s in sigs] and st["keys"] == [s[3][0] for s in sigs] and st["log_n"] == 10
+    # a signature that does not verify: no proof, a message instead
+    prv[2]["r"] = hex(int(prv[2]["r"], 16) ^ 4)
+    (tmp_path / "private.json").write_text(json.dumps({"signatures": prv}))
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and "does not verify" in out.stderr
