@@ -151,3 +151,44 @@ def test_file_level_prover_cli_ecdsa(tmp_path):
     (tmp_path / "private.json").write_text(json.dumps({"signatures": prv}))
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode != 0 and "does not verify" in out.stderr
+
+
+@pytest.mark.parametrize("log_n,n_points", [(12, 256), (20, 1024)])
+def test_composition_at_sampled_points_headline_size(log_n, n_points):
+    """the constraint kernel at the bench's trace size (4096 signatures): composition values at sampled points of the four
+    even cosets against the twin's constraint code fed with the C oracle's LDE of the same trace, the twin's own public
+    and periodic columns and zerofiers"""
+    import random
+    from oracle import clib
+    ctx = _ctx()
+    n = 1 << log_n
+    count = n >> 8
+    msgs, r, s, keys = _gpu_signatures(ctx, count, 77)
+    from stark_perpetual_b200.ecdsa_air import air_inputs
+    m_, r_, w_, kx_, ky_ = air_inputs(msgs, r, s, keys)
+    trace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx_, ky_)
+    alpha = 0x3039 * 2**190 + 12345
+    cp = ctx.air_eval_ecdsa(trace, log_n, m_, kx_, alpha)                      # (4 N, 4)
+    rng = random.Random(5)
+    # the block-boundary rows carry most constraints' interesting cases: force some of them into the sample
+    rows = [rng.randrange(n) for _ in range(n_points - 64)] + [256 * rng.randrange(count) + t for t in (0, 250, 251, 255) for _ in range(16)]
+    pts = [(2 * rng.randrange(4), i) for i in rows]
+    want_pts = sorted({(j, i) for j, i in pts} | {(j, (i + 1) % n) for j, i in pts})
+    jj = np.array([p[0] for p in want_pts]); ii = np.array([p[1] for p in want_pts])
+    clib.use_all_cores()
+    t_vals = {pt: [0] * 25 for pt in want_pts}
+    tr = trace.reshape(25, n, 4)
+    for c0 in range(0, 25, 13):
+        step = min(13, 25 - c0)
+        lde = clib.lde(np.ascontiguousarray(tr[c0:c0 + step]).reshape(-1, 4), log_n, step, 3).reshape(8, step, n, 4)
+        for c in range(step):
+            for pt, v in zip(want_pts, _ints(np.ascontiguousarray(lde[jj, c, ii]))):
+                t_vals[pt][c0 + c] = v
+        del lde
+    air = se.EcdsaAir(log_n, list(zip(msgs, [k[0] for k in keys])))
+    apows = [pow(alpha, k, P) for k in range(se.N_ALPHA)]
+    got = _ints(np.ascontiguousarray(cp.reshape(4, n, 4)[np.array([p[0] // 2 for p in pts]), np.array([p[1] for p in pts])]))
+    for (j, i), g in zip(pts, got):
+        x = stark.lde_point(log_n, j, i)
+        want = air.composition_per(t_vals[(j, i)], t_vals[(j, (i + 1) % n)], air.periodic_at(x), air.inv_zerofiers(x), apows)
+        assert g == want, (j, i)
