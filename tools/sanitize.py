@@ -59,6 +59,14 @@ def main():
     assert st4 == 0
     oc, st5 = ctx.hash_chain_rfold(rand_felts(6, 4), 3)
     assert not st5.any()
+    # second AIR: witness kernels, public columns, constraint kernel, proof (2 signatures, 2^9 rows)
+    from oracle import stark_ecdsa as se
+    sigs = se.make_signatures(2, 5)
+    ins = [ints_to_limbs(v) for v in ([s_[0] for s_ in sigs], [s_[1] for s_ in sigs], [s_[2] for s_ in sigs],
+                                      [s_[3][0] for s_ in sigs], [s_[3][1] for s_ in sigs])]
+    tr9 = ctx.ecdsa_air_trace(9, *ins)
+    ep = ctx.prove_ecdsa(tr9, 9, ins[0], ins[3], 8)
+    assert ostark.verify(ep, min_queries=8)["air"] == "ecdsa"
     print("sanitize workload OK")
 
 
