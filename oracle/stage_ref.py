@@ -30,6 +30,8 @@ FILES = [
     "services/perpetual/public/perpetual_messages.py", "services/perpetual/public/perpetual_messages_test.py",
     "services/perpetual/public/perpetual_messages_precomputed.json",
     "services/perpetual/public/stark_cli.py", "services/perpetual/public/stark_cli_test.py",
+    # the config-hash script: run unchanged (by path) against compat's hash and the two definitions modules it imports
+    "services/perpetual/public/generate_perpetual_config_hash.py",
     # the program-hash test (row f-2): run unchanged against compat's hash_program on a synthetic compiled program
     "starkware/cairo/__init__.py", "starkware/cairo/bootloaders/__init__.py",
     "starkware/cairo/bootloaders/program_hash_test_utils.py",
