@@ -64,25 +64,25 @@ SPG_HD Fp ecdsa_air_point(const Cells& c, const Cells& n, const Fp& gx, const Fp
   Fp hold = fp_add(fp_mul(a[5], fp_sub(n[EA_APX], c[EA_APX])), fp_mul(a[6], fp_sub(n[EA_APY], c[EA_APY])));
   Fp zero = fp_mul(a[7], c[EA_AM]);
   Fp first = fp_add(fp_mul(a[8], fp_sub(c[EA_APX], K.shift_x)), fp_mul(a[9], fp_sub(c[EA_APY], K.minus_shift_y)));
-  // lane B                                                                                   alpha 10 .. 23
-  step = fp_add(step, eair_lane(a + 10, c[EA_BM], n[EA_BM], c[EA_BPX], c[EA_BPY], n[EA_BPX], n[EA_BPY], c[EA_BQX], c[EA_BQY],
-                                c[EA_BSA], c[EA_BI]));
-  step = fp_add(step, eair_double(a + 15, c[EA_BQX], c[EA_BQY], n[EA_BQX], n[EA_BQY], c[EA_BSD]));
-  hold = fp_add(hold, fp_add(fp_mul(a[18], fp_sub(n[EA_BPX], c[EA_BPX])), fp_mul(a[19], fp_sub(n[EA_BPY], c[EA_BPY]))));
-  zero = fp_add(zero, fp_mul(a[20], c[EA_BM]));
-  first = fp_add(first, fp_add(fp_mul(a[21], fp_sub(c[EA_BPX], K.shift_x)), fp_mul(a[22], fp_sub(c[EA_BPY], K.shift_y))));
-  {
-    const Fp x = c[EA_BQX];
-    const Fp curve = fp_sub(fp_sub(fp_sub(fp_sqr(c[EA_BQY]), fp_mul(fp_sqr(x), x)), x), K.beta);
-    first = fp_add(first, fp_mul(a[23], curve));
+  // lanes B (alpha 10 .. 23) and C (alpha 24 .. 36): the same eight columns and the same constraints at the same relative
+  // alpha positions, so ONE copy of the code serves both (the kernel is fetch-bound when everything is unrolled: a field
+  // multiplication is ~190 instructions and a point needs ~100 of them)
+#pragma unroll 1
+  for (int l = 0; l < 2; l++) {
+    const int cb = l ? EA_CM : EA_BM;
+    const Fp* al = a + (l ? 24 : 10);
+    const Fp M = c[cb], PX = c[cb + 1], PY = c[cb + 2], QX = c[cb + 3], QY = c[cb + 4];
+    const Fp PXn = n[cb + 1], PYn = n[cb + 2];
+    step = fp_add(step, eair_lane(al, M, n[cb], PX, PY, PXn, PYn, QX, QY, c[cb + 5], c[cb + 7]));
+    step = fp_add(step, eair_double(al + 5, QX, QY, n[cb + 3], n[cb + 4], c[cb + 6]));
+    hold = fp_add(hold, fp_add(fp_mul(al[8], fp_sub(PXn, PX)), fp_mul(al[9], fp_sub(PYn, PY))));
+    zero = fp_add(zero, fp_mul(al[10], M));
+    first = fp_add(first, fp_add(fp_mul(al[11], fp_sub(PX, K.shift_x)), fp_mul(al[12], fp_sub(PY, K.shift_y))));
+    if (l == 0) {                                     // the key is a curve point (lane B's row 0)
+      const Fp curve = fp_sub(fp_sub(fp_sub(fp_sqr(QY), fp_mul(fp_sqr(QX), QX)), QX), K.beta);
+      first = fp_add(first, fp_mul(al[13], curve));
+    }
   }
-  // lane C                                                                                   alpha 24 .. 36
-  step = fp_add(step, eair_lane(a + 24, c[EA_CM], n[EA_CM], c[EA_CPX], c[EA_CPY], n[EA_CPX], n[EA_CPY], c[EA_CQX], c[EA_CQY],
-                                c[EA_CSA], c[EA_CI]));
-  step = fp_add(step, eair_double(a + 29, c[EA_CQX], c[EA_CQY], n[EA_CQX], n[EA_CQY], c[EA_CSD]));
-  hold = fp_add(hold, fp_add(fp_mul(a[32], fp_sub(n[EA_CPX], c[EA_CPX])), fp_mul(a[33], fp_sub(n[EA_CPY], c[EA_CPY]))));
-  zero = fp_add(zero, fp_mul(a[34], c[EA_CM]));
-  first = fp_add(first, fp_add(fp_mul(a[35], fp_sub(c[EA_CPX], K.shift_x)), fp_mul(a[36], fp_sub(c[EA_CPY], K.shift_y))));
   // row 255: ec_add(zG, rQ) becomes lane C's point on the next row; ec_add(wB, -S).x == r      alpha 37 .. 44
   const Fp dab = fp_sub(c[EA_APX], c[EA_BPX]);
   Fp last = fp_add(fp_mul(a[37], fp_sub(fp_mul(c[EA_AI], dab), one)),
