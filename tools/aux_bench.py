@@ -184,8 +184,10 @@ def ecdsa_air(ctx, log_n=20, n_queries=30, verify=True):
     ri, si = limbs_to_ints(r), limbs_to_ints(s_)
     keys = list(zip(limbs_to_ints(kx), limbs_to_ints(ky)))
     m_, r_, w_, kx_, ky_ = air_inputs(msgs, ri, si, keys)
-    trace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx_, ky_)
-    trace_ms = ctx.last_kernel_ms
+    trace_ms = 1e30
+    for _ in range(2):                      # the first call also pays the kernels' lazy module load
+        trace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx_, ky_)
+        trace_ms = min(trace_ms, ctx.last_kernel_ms)
     d_trace = torch.from_numpy(trace.view(np.int64)).cuda()
     best, stages = 1e30, None
     for _ in range(4):
