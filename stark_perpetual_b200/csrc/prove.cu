@@ -65,8 +65,11 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
 
   // ---- public input, channel
   Fp h_last[SPG_AIR_LANES];
-  // upload chunks (columns): a small first chunk so that the LDE starts after 1/25 of the copy
-  const int n_chunks = 6, chunk_begin[7] = {0, 1, 5, 10, 15, 20, 25};
+  // upload chunks (columns).  A column takes ~0.6 ms to arrive over PCIe and ~1.07 ms to extend, and a chunk's transforms
+  // start when its last byte is there: growing chunks (1, 1, 2, 4, ...) keep the copy just ahead of the kernels, so only
+  // the first column's upload is exposed (the even 1, 4, 5, 5, 5, 5 split left the GPU idle for 1.4 ms after column 0)
+  const int n_chunks = 7, chunk_begin[8] = {0, 1, 2, 4, 8, 13, 19, 25};
+  static_assert(sizeof(ctx->copy_ev) / sizeof(ctx->copy_ev[0]) >= 7, "one event per chunk");
   static_assert(SPG_AIR_COLS == 25, "chunk table");
   if (h_trace) {
     for (int l = 0; l < SPG_AIR_LANES; l++) h_last[l] = h_trace[((size_t)(5 * l) << log_n) + (n - 1)];   // (unused by kind 2)

@@ -211,7 +211,14 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
 
   int rc;
   // ---- 1. interpolate (my columns) -> all-gather (rounds) -> evaluate on my cosets, pipelined in chunks
-  const int n_rounds = (C + world - 1) / world, rpc = world >= 8 ? 1 : 8 / world, n_chunks = (n_rounds + rpc - 1) / rpc;
+  // chunks of whole rounds.  Device-resident columns: ~8 columns per chunk (large launches).  Host columns: growing
+  // chunks (1, 1, 2, 4, ... rounds) so that the first interpolation starts after ONE column per rank has crossed PCIe and
+  // the copy stays just ahead of the kernels (a rank's column takes ~0.6 ms to arrive, ~0.13 ms to interpolate)
+  const int n_rounds = (C + world - 1) / world, rpc = world >= 8 ? 1 : 8 / world;
+  std::vector<int> cb = {0};
+  if (h_cols) { for (int sz = 1, first = 1; cb.back() < n_rounds; sz = first ? 1 : std::min(2 * sz, rpc), first = 0) cb.push_back(std::min(n_rounds, cb.back() + sz)); }
+  else { while (cb.back() < n_rounds) cb.push_back(std::min(n_rounds, cb.back() + rpc)); }
+  const int n_chunks = (int)cb.size() - 1;
   SPG_ARG(n_chunks <= 8, "chunk count");
   auto my_rounds = [&](int k0, int k1) { int c = 0; for (int k = k0; k < k1; k++) if (k * world + rank < C) c++; return c; };
   spg_stage_begin(ctx, ST_LDE);
@@ -228,7 +235,7 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     }
     SPG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->comm_ev[15], 0));
     for (int c = 0; c < n_chunks; c++) {
-      const int k0 = c * rpc, k1 = std::min(n_rounds, k0 + rpc), mine = my_rounds(k0, k1);
+      const int k0 = cb[c], k1 = cb[c + 1], mine = my_rounds(k0, k1);
       if (mine)
         SPG_CUDA(cudaMemcpyAsync(d_cols + (size_t)k0 * n, h_cols + (size_t)k0 * n, (size_t)mine * n * sizeof(Fp),
                                  cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -236,7 +243,7 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     }
   }
   for (int c = 0; c < n_chunks; c++) {
-    const int k0 = c * rpc, k1 = std::min(n_rounds, k0 + rpc), mine = my_rounds(k0, k1);
+    const int k0 = cb[c], k1 = cb[c + 1], mine = my_rounds(k0, k1);
     if (mine) {
       if (h_cols) SPG_CUDA(cudaStreamWaitEvent(S, ctx->copy_ev[c], 0));
       if ((rc = spg_lde_coeffs_device(ctx, d_cols + (size_t)k0 * n, log_n, (size_t)mine, nullptr,
@@ -257,14 +264,14 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     }
     SPG_CUDA(cudaEventRecord(ctx->comm_ev[8 + (c & 3)], CS));
     if (c >= 1) {   // evaluate the previous chunk while this one is in flight
-      const int pk0 = (c - 1) * rpc, pk1 = std::min(n_rounds, pk0 + rpc);
+      const int pk0 = cb[c - 1], pk1 = cb[c];
       const size_t col0 = (size_t)pk0 * world, ncols = std::min((size_t)C, (size_t)pk1 * world) - col0;
       SPG_CUDA(cudaStreamWaitEvent(S, ctx->comm_ev[8 + ((c - 1) & 3)], 0));
       if ((rc = spg_lde_cosets_device(ctx, t_coef + col0 * n, log_n, ncols, SPG_LOG_BLOWUP, first, cs, t_lde, C, col0))) return rc;
     }
   }
   {
-    const int pk0 = (n_chunks - 1) * rpc;
+    const int pk0 = cb[n_chunks - 1];
     const size_t col0 = (size_t)pk0 * world, ncols = (size_t)C - col0;
     SPG_CUDA(cudaStreamWaitEvent(S, ctx->comm_ev[8 + ((n_chunks - 1) & 3)], 0));
     if ((rc = spg_lde_cosets_device(ctx, t_coef + col0 * n, log_n, ncols, SPG_LOG_BLOWUP, first, cs, t_lde, C, col0))) return rc;

@@ -194,9 +194,13 @@ def ecdsa_air(ctx, log_n=20, n_queries=30, verify=True):
         proof = ctx.prove_ecdsa(None, log_n, m_, kx_, n_queries, device_ptr=d_trace.data_ptr())
         if ctx.last_kernel_ms < best:
             best, stages = ctx.last_kernel_ms, [round(ctx.stage_ms(k), 3) for k in range(9)]
-    t0 = time.perf_counter()
-    proof_h = ctx.prove_ecdsa(trace, log_n, m_, kx_, n_queries)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    pinned = torch.from_numpy(trace.view(np.int64)).pin_memory()          # the upload overlaps the LDE only from pinned memory
+    host_trace = pinned.numpy().view(np.uint64)
+    e2e_ms = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        proof_h = ctx.prove_ecdsa(host_trace, log_n, m_, kx_, n_queries)
+        e2e_ms = min(e2e_ms, (time.perf_counter() - t0) * 1e3)
     row = {"log_n": log_n, "signatures": count, "trace_ms": trace_ms, "proof_ms": best, "e2e_ms": e2e_ms,
            "signatures_per_s": count / (best * 1e-3), "proof_bytes": len(proof), "same_proof_from_host_trace": proof_h == proof,
            "stage_ms": dict(zip(["lde_trace", "merkle_trace", "air_composition", "lde_chunks", "merkle_chunks", "oods_eval",
