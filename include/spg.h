@@ -318,6 +318,10 @@ int spg_comm_unique_id(spg_ctx* ctx, uint8_t* id_out /*[128]*/);
 int spg_comm_init(spg_ctx* ctx, int rank, int world, const uint8_t* id /*[128], may be NULL when world == 1*/);
 int spg_prove_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsigned log_n, unsigned chain_log, const uint64_t* x0,
                       const uint64_t* outs, unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
+/* the same collective over the ECDSA-builtin AIR (cols_local: this rank's columns of the trace spg_ecdsa_air_trace writes;
+ * msgs, key_x: the whole public input on every rank, host).  Byte-identical to spg_prove_ecdsa. */
+int spg_prove_ecdsa_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsigned log_n, const uint64_t* msgs, const uint64_t* key_x,
+                            unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags);
 
 /* ---- stage-level entry points for the multi-GPU host driver (device pointers; DESIGN.md "Multi-GPU") ----------
  * A GPU owns n_cosets consecutive cosets starting at first_coset; its tables hold exactly those cosets,

@@ -79,6 +79,7 @@ def _load():
             "spg_comm_unique_id": (C.c_int, [vp, vp]),
             "spg_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
             "spg_prove_sharded": (C.c_int, [vp, vp, C.c_uint, C.c_uint, vp, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
+            "spg_prove_ecdsa_sharded": (C.c_int, [vp, vp, C.c_uint, vp, vp, C.c_uint, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]),
             "spg_stage_ms": (C.c_double, [vp, C.c_int]),
             "spg_lde": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, C.c_uint, vp, vp, C.c_int]),
             "spg_lde_coeffs": (C.c_int, [vp, vp, C.c_uint, C.c_size_t, vp, vp, C.c_int]),
@@ -571,6 +572,24 @@ class Context:
     def comm_init(self, rank, world, unique_id=None):
         idb = np.frombuffer(unique_id, dtype=np.uint8).copy() if unique_id is not None else None
         self._check(self._lib.spg_comm_init(self._h, rank, world, _ptr(idb) if idb is not None else None))
+
+    def prove_ecdsa_sharded(self, cols_local, log_n, msgs, key_x, n_queries=30, device_ptr=None):
+        """spg_prove_ecdsa over the communicator: cols_local = this rank's columns (cyclic deal) of an ECDSA-AIR trace; msgs,
+        key_x = the whole public input.  Collective; every rank gets the proof, byte-identical to prove_ecdsa's."""
+        ma = np.ascontiguousarray(msgs, dtype=np.uint64).reshape(-1, 4)
+        ka = np.ascontiguousarray(key_x, dtype=np.uint64).reshape(-1, 4)
+        assert ma.shape[0] == ka.shape[0] == (1 << log_n) >> 8
+        if device_ptr is None:
+            tr = np.ascontiguousarray(cols_local, dtype=np.uint64).reshape(-1, 4)
+            tp, flags = (_ptr(tr) if tr.shape[0] else None), 0
+        else:
+            tp, flags = C.c_void_p(device_ptr), SPG_DEVICE_PTRS
+        cap = 64 + 64 * 32 + 64 * 32 + 128 * 32 + n_queries * (8 * 29 + 8 * 8 + 10 * 24) * 32 + 65536 + 64 * ma.shape[0]
+        buf = np.empty(cap, dtype=np.uint8)
+        ln = C.c_size_t(0)
+        self._check(self._lib.spg_prove_ecdsa_sharded(self._h, tp, log_n, _ptr(ma), _ptr(ka), n_queries, _ptr(buf), cap,
+                                                      C.byref(ln), flags))
+        return buf[:ln.value].tobytes()
 
     def prove_sharded(self, cols_local, log_n, chain_log, x0, outs, n_queries=30, device_ptr=None):
         """cols_local: this rank's columns (cyclic deal) as a (my_cols * 2^log_n, 4) uint64 host array, or device_ptr = their

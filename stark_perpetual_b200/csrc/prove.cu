@@ -7,18 +7,6 @@
 #include <string.h>
 
 #include "prove_common.h"
-#include "ecdsa_air_point.cuh"
-
-// which AIR a proof is for: the protocol around it is the same (25 columns, mask {x, x w_N}, 4 composition chunks)
-struct AirSpec {
-  int kind = 1;                         // proof header VERSION: 1 = Pedersen hash chain, 2 = ECDSA builtin
-  unsigned chain_log = 0;               // kind 1
-  const uint64_t* x0_canon = nullptr;   // kind 1: the 5 lane seeds
-  const uint64_t* msgs_canon = nullptr; // kind 2: the public input, [N/256] message hashes ...
-  const uint64_t* keys_canon = nullptr; //         ... and [N/256] keys' x (canonical, host)
-};
-#define SPG_MAX_ALPHA (SPG_AIR_LANES * SPG_AIR_NCONSTR)
-static_assert(SPG_EAIR_NALPHA <= SPG_MAX_ALPHA && SPG_EAIR_COLS == SPG_AIR_COLS, "both AIRs share the protocol's shape");
 
 // d_trace: [25][N] canonical felts on the device.  Appends the proof to `proof`.
 // h_trace (optional): the same trace in HOST memory; it is then uploaded into d_trace in column chunks on a
@@ -108,13 +96,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
     for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.x0[l]);
     for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.outs[l]);
   } else {                                   // oracle/stark_ecdsa.py EcdsaAir.seed / .header
-    const char* tag = "ecdsa-builtin";
-    seed.insert(seed.end(), tag, tag + 13);
-    put_u32(seed, log_n); put_u32(seed, n_queries);
-    for (size_t b = 0; b < (n >> 8); b++) {
-      const Fp m = spg_host_from_u64(air.msgs_canon + 4 * b), k = spg_host_from_u64(air.keys_canon + 4 * b);
-      put_fp(seed, m); put_fp(seed, k); put_fp(proof, m); put_fp(proof, k);
-    }
+    put_ecdsa_statement(air, log_n, n_queries, seed, proof);
   }
   Channel ch(seed);
 

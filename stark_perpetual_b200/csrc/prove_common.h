@@ -7,6 +7,7 @@
 
 #include "blake2s.cuh"
 #include "stark_kernels.cuh"
+#include "ecdsa_air_point.cuh"
 
 // ------------------------------------------------------------------ host helpers
 static void ser_fp(const Fp& a /*canonical representative of the Montgomery form*/, uint8_t* out) {
@@ -58,6 +59,29 @@ struct Channel {
     return v % n;
   }
 };
+
+// which AIR a proof is for: the protocol around it is the same (25 columns, mask {x, x w_N}, 4 composition chunks)
+struct AirSpec {
+  int kind = 1;                         // proof header VERSION: 1 = Pedersen hash chain, 2 = ECDSA builtin
+  unsigned chain_log = 0;               // kind 1
+  const uint64_t* x0_canon = nullptr;   // kind 1: the 5 lane seeds
+  const uint64_t* msgs_canon = nullptr; // kind 2: the public input, [N/256] message hashes ...
+  const uint64_t* keys_canon = nullptr; //         ... and [N/256] keys' x (canonical, host)
+};
+#define SPG_MAX_ALPHA (SPG_AIR_LANES * SPG_AIR_NCONSTR)
+static_assert(SPG_EAIR_NALPHA <= SPG_MAX_ALPHA && SPG_EAIR_COLS == SPG_AIR_COLS, "both AIRs share the protocol's shape");
+
+// the statement of a kind-2 proof into the channel seed and the proof header (oracle/stark_ecdsa.py EcdsaAir.seed / .header)
+static void put_ecdsa_statement(const AirSpec& air, unsigned log_n, unsigned n_queries, std::vector<uint8_t>& seed,
+                                std::vector<uint8_t>& proof) {
+  const char* tag = "ecdsa-builtin";
+  seed.insert(seed.end(), tag, tag + 13);
+  put_u32(seed, log_n); put_u32(seed, n_queries);
+  for (size_t b = 0; b < (((size_t)1 << log_n) >> 8); b++) {
+    const Fp m = spg_host_from_u64(air.msgs_canon + 4 * b), k = spg_host_from_u64(air.keys_canon + 4 * b);
+    put_fp(seed, m); put_fp(seed, k); put_fp(proof, m); put_fp(proof, k);
+  }
+}
 
 // bump allocator over one cached device block
 struct Arena {

@@ -154,10 +154,14 @@ static void top_levels(const std::vector<uint8_t>& roots /*world x 32*/, std::ve
 
 // d_cols: this rank's columns (cyclic deal), [my_cols][N] canonical, on the device; h_cols: the same in host memory
 // (then uploaded chunk by chunk, overlapped with the pipeline).  Appends the proof to `proof` on every rank.
-static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsigned log_n, unsigned chain_log,
-                                const uint64_t* x0_canon, const uint64_t* outs_canon, unsigned n_queries, std::vector<uint8_t>& proof) {
+static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsigned log_n, const AirSpec& air,
+                                const uint64_t* outs_canon, unsigned n_queries, std::vector<uint8_t>& proof) {
+  const unsigned chain_log = air.chain_log;
+  const uint64_t* x0_canon = air.x0_canon;
+  const bool pedersen = air.kind == 1;
+  const int n_alpha = pedersen ? SPG_MAX_ALPHA : SPG_EAIR_NALPHA;
   SPG_ARG(log_n >= 9 && log_n + SPG_LOG_BLOWUP <= SPG_UNI_LOG, "spg_prove_sharded: log_n must be in [9, 23]");
-  SPG_ARG(9 + chain_log <= log_n, "spg_prove_sharded: chain_log");
+  SPG_ARG(!pedersen || 9 + chain_log <= log_n, "spg_prove_sharded: chain_log");
   SPG_ARG(n_queries >= 1 && n_queries <= 1024, "spg_prove_sharded: n_queries");
   SPG_ARG(ctx->comm_world >= 1 && ctx->comm_stream, "spg_prove_sharded: call spg_comm_init first");
   const int rank = ctx->comm_rank, world = ctx->comm_world, cs = SPG_BLOWUP / world, first = rank * cs;
@@ -198,16 +202,20 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
 
   // ---- public input, channel (identical to prove.cu)
   AirPublic pub;
-  for (int l = 0; l < SPG_AIR_LANES; l++) { pub.x0[l] = spg_host_from_u64(x0_canon + 4 * l); pub.outs[l] = spg_host_from_u64(outs_canon + 4 * l); }
   std::vector<uint8_t> seed;
-  put_u32(seed, log_n); put_u32(seed, chain_log); put_u32(seed, n_queries);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.x0[l]);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.outs[l]);
-  Channel ch(seed);
   proof.insert(proof.end(), {'S', 'P', 'G', 'P'});
-  put_u32(proof, 1); put_u32(proof, log_n); put_u32(proof, chain_log); put_u32(proof, n_queries); put_u32(proof, (uint32_t)n_folds);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.x0[l]);
-  for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.outs[l]);
+  put_u32(proof, (uint32_t)air.kind); put_u32(proof, log_n); put_u32(proof, chain_log); put_u32(proof, n_queries); put_u32(proof, (uint32_t)n_folds);
+  if (pedersen) {
+    for (int l = 0; l < SPG_AIR_LANES; l++) { pub.x0[l] = spg_host_from_u64(x0_canon + 4 * l); pub.outs[l] = spg_host_from_u64(outs_canon + 4 * l); }
+    put_u32(seed, log_n); put_u32(seed, chain_log); put_u32(seed, n_queries);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.x0[l]);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(seed, pub.outs[l]);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.x0[l]);
+    for (int l = 0; l < SPG_AIR_LANES; l++) put_fp(proof, pub.outs[l]);
+  } else {
+    put_ecdsa_statement(air, log_n, n_queries, seed, proof);
+  }
+  Channel ch(seed);
 
   int rc;
   // ---- 1. interpolate (my columns) -> all-gather (rounds) -> evaluate on my cosets, pipelined in chunks
@@ -301,15 +309,25 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
 
   // ---- 2. composition on the even cosets this rank owns; chunk split; exchange of the chunk values; chunk LDE; commitment
   const Fp alpha = ch.draw_felt();
-  Fp apows[SPG_AIR_LANES * SPG_AIR_NCONSTR];
+  Fp apows[SPG_MAX_ALPHA];
   apows[0] = fp_one();
-  for (int k = 1; k < SPG_AIR_LANES * SPG_AIR_NCONSTR; k++) apows[k] = fp_mul(apows[k - 1], alpha);
+  for (int k = 1; k < n_alpha; k++) apows[k] = fp_mul(apows[k - 1], alpha);
   int jj0 = -1, n_even = 0;
   for (int jj = 0; jj < 4; jj++)
     if (2 * jj >= first && 2 * jj < first + cs) { if (jj0 < 0) jj0 = jj; n_even++; }
   spg_stage_begin(ctx, ST_AIR);
+  DevBuf e_pub, e_coef, e_lde;       // kind 2: the public columns (values, coefficients on every rank; this rank's even cosets)
+  if (!pedersen) {
+    const size_t nb = n >> 8;
+    SPG_CUDA(e_pub.alloc(ctx, 2 * nb * 32)); SPG_CUDA(e_coef.alloc(ctx, 2 * nb * 32)); SPG_CUDA(e_lde.alloc(ctx, (size_t)std::max(n_even, 1) * 2 * n * 32));
+    SPG_CUDA(cudaMemcpyAsync(e_pub.p, air.msgs_canon, nb * 32, cudaMemcpyHostToDevice, S));
+    SPG_CUDA(cudaMemcpyAsync(e_pub.as<Fp>() + nb, air.keys_canon, nb * 32, cudaMemcpyHostToDevice, S));
+    if ((rc = spg_eair_public_device(ctx, log_n, e_pub.as<Fp>(), e_coef.as<Fp>(), e_lde.as<Fp>(), std::max(jj0, 0), n_even))) return rc;
+  }
   if (n_even) {
-    if ((rc = spg_air_eval_device(ctx, log_n, chain_log, t_lde, pub, apows, cp, first, jj0, n_even))) return rc;
+    if (pedersen) rc = spg_air_eval_device(ctx, log_n, chain_log, t_lde, pub, apows, cp, first, jj0, n_even);
+    else rc = spg_eair_eval_device(ctx, log_n, t_lde, e_lde.as<Fp>(), apows, cp, first, jj0, n_even);
+    if (rc) return rc;
     if ((rc = spg_cp_split_device(ctx, log_n, cp, hev, jj0, n_even))) return rc;
   }
   if (world > 1) {
@@ -384,7 +402,10 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     spg_stage_end(ctx, ST_OODS);
   }
   {
-    const Fp lhs = spg_air_composition_at_host(log_n, chain_log, pub, apows, z, oods, oods + C, ctx->h_const_points);
+    Fp pub_z[2];
+    if (!pedersen && (rc = spg_eair_public_at_host(ctx, log_n, e_coef.as<Fp>(), z, pub_z))) return rc;
+    const Fp lhs = pedersen ? spg_air_composition_at_host(log_n, chain_log, pub, apows, z, oods, oods + C, ctx->h_const_points)
+                            : spg_eair_composition_at_host(ctx, log_n, pub_z, apows, z, oods, oods + C);
     Fp rhs = fp_zero(), zp = fp_one();
     for (int m = 0; m < 4; m++) { rhs = fp_add(rhs, fp_mul(zp, oods[2 * C + m])); zp = fp_mul(zp, z); }
     if (!fp_eq(lhs, rhs)) { ctx->err = "trace does not satisfy the AIR (composition mismatch at the out-of-domain point)"; return SPG_E_PROOF; }
@@ -514,11 +535,8 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
   return SPG_OK;
 }
 
-extern "C" int spg_prove_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsigned log_n, unsigned chain_log, const uint64_t* x0,
-                                 const uint64_t* outs, unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
-                                 int flags) {
-  SPG_LOCK(ctx);
-  SPG_ARG(ctx && x0 && outs && proof_len, "spg_prove_sharded: null");
+static int prove_sharded_entry(spg_ctx* ctx, const uint64_t* cols_local, unsigned log_n, const AirSpec& air, const uint64_t* outs,
+                               unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len, int flags) {
   SPG_ARG(log_n >= 9 && log_n <= 23, "spg_prove_sharded: log_n must be in [9, 23]");
   SPG_ARG(ctx->comm_world >= 1, "spg_prove_sharded: call spg_comm_init first");
   SPG_CUDA(cudaSetDevice(ctx->device));
@@ -536,7 +554,7 @@ extern "C" int spg_prove_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsig
     h_cols = (const Fp*)cols_local;
   }
   std::vector<uint8_t> proof;
-  int rc = prove_sharded_device(ctx, d_cols, h_cols, log_n, chain_log, x0, outs, n_queries, proof);
+  int rc = prove_sharded_device(ctx, d_cols, h_cols, log_n, air, outs, n_queries, proof);
   if (rc) return rc;
   SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -547,4 +565,34 @@ extern "C" int spg_prove_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsig
     memcpy(proof_out, proof.data(), proof.size());
   }
   return SPG_OK;
+}
+
+extern "C" int spg_prove_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsigned log_n, unsigned chain_log, const uint64_t* x0,
+                                 const uint64_t* outs, unsigned n_queries, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
+                                 int flags) {
+  SPG_LOCK(ctx);
+  SPG_ARG(ctx && x0 && outs && proof_len, "spg_prove_sharded: null");
+  AirSpec air;
+  air.kind = 1; air.chain_log = chain_log; air.x0_canon = x0;
+  return prove_sharded_entry(ctx, cols_local, log_n, air, outs, n_queries, proof_out, proof_cap, proof_len, flags);
+}
+
+// the sharded prover over the ECDSA-builtin AIR: cols_local as for spg_prove_sharded (this rank's columns of the trace
+// spg_ecdsa_air_trace writes, dealt cyclically); msgs, key_x: the whole public input on every rank (host).  Byte-identical
+// to spg_prove_ecdsa.
+extern "C" int spg_prove_ecdsa_sharded(spg_ctx* ctx, const uint64_t* cols_local, unsigned log_n, const uint64_t* msgs,
+                                       const uint64_t* key_x, unsigned n_queries, uint8_t* proof_out, size_t proof_cap,
+                                       size_t* proof_len, int flags) {
+  SPG_LOCK(ctx);
+  SPG_ARG(ctx && msgs && key_x && proof_len, "spg_prove_ecdsa_sharded: null");
+  SPG_ARG(log_n >= 9 && log_n <= 23, "spg_prove_ecdsa_sharded: log_n must be in [9, 23]");
+  for (size_t b = 0; b < (((size_t)1 << log_n) >> 8); b++)
+    for (const uint64_t* v : {msgs + 4 * b, key_x + 4 * b}) {
+      uint32_t lim[8];
+      for (int q = 0; q < 4; q++) { lim[2 * q] = (uint32_t)v[q]; lim[2 * q + 1] = (uint32_t)(v[q] >> 32); }
+      SPG_ARG(!spg_canon_geq_p(lim), "spg_prove_ecdsa_sharded: public value >= p");
+    }
+  AirSpec air;
+  air.kind = 2; air.msgs_canon = msgs; air.keys_canon = key_x;
+  return prove_sharded_entry(ctx, cols_local, log_n, air, nullptr, n_queries, proof_out, proof_cap, proof_len, flags);
 }

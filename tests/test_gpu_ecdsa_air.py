@@ -192,3 +192,16 @@ def test_composition_at_sampled_points_headline_size(log_n, n_points):
         x = stark.lde_point(log_n, j, i)
         want = air.composition_per(t_vals[(j, i)], t_vals[(j, (i + 1) % n)], air.periodic_at(x), air.inv_zerofiers(x), apows)
         assert g == want, (j, i)
+
+
+def test_sharded_prover_world1_equals_monolithic():
+    """spg_prove_ecdsa_sharded with a one-rank communicator (no NCCL needed) == spg_prove_ecdsa; the 2 / 4 / 8-GPU form of the
+    same check is tools/multi_gpu_check.py (profiles/*multi_gpu_check*)"""
+    from stark_perpetual_b200._lib import Context
+    ctx = Context(0)
+    sigs = se.make_signatures(4, 41)
+    ins = _inputs(sigs)
+    trace = ctx.ecdsa_air_trace(10, *ins)
+    ctx.comm_init(0, 1)
+    assert ctx.prove_ecdsa_sharded(trace, 10, ins[0], ins[3], 30) == ctx.prove_ecdsa(trace, 10, ins[0], ins[3], 30)
+    ctx.close()

@@ -41,11 +41,31 @@ def main():
     assert outs2 == outs
     assert pv.prove_sharded_device(block, log_n, chain_log, x0, outs, 30) == proof, "Python stage driver differs"
     dist.barrier()
+    # the second AIR (ECDSA builtin) through the same sharded sequence: every rank builds the same trace from the same seed
+    import random
+    from stark_perpetual_b200._lib import ints_to_limbs
+    from stark_perpetual_b200.ecdsa_air import air_inputs
+    rng = random.Random(5)
+    count = n >> 8
+    privs = [rng.randrange(1, 1 << 250) for _ in range(count)]
+    msgs = [rng.randrange(1, 1 << 251) for _ in range(count)]
+    kx, ky, _st = ctx.private_to_stark_key(ints_to_limbs(privs), want_y=True)
+    r, s_, _st = ctx.sign(ints_to_limbs(msgs), ints_to_limbs(privs))
+    m_, r_, w_, kx_, ky_ = air_inputs(msgs, limbs_to_ints(r), limbs_to_ints(s_), list(zip(limbs_to_ints(kx), limbs_to_ints(ky))))
+    etrace = ctx.ecdsa_air_trace(log_n, m_, r_, w_, kx_, ky_)
+    emine = np.ascontiguousarray(etrace.reshape(25, n, 4)[pv.cyclic_columns()]).reshape(-1, 4)
+    eproof = ctx.prove_ecdsa_sharded(emine, log_n, m_, kx_, 30)
+    edev = torch.from_numpy(emine.view(np.int64)).cuda()
+    assert ctx.prove_ecdsa_sharded(None, log_n, m_, kx_, 30, device_ptr=edev.data_ptr()) == eproof
+    dist.barrier()
     if rank == 0:
         from oracle import stark
         want = ctx.prove(trace, log_n, chain_log, x0, 30)
         stark.verify(proof)
-        print("MULTI_GPU_CHECK world=%d log_n=%d bytes=%d %s" % (world, log_n, len(proof), "MATCH" if proof == want else "MISMATCH"))
+        ewant = ctx.prove_ecdsa(etrace, log_n, m_, kx_, 30)
+        assert stark.verify(eproof)["air"] == "ecdsa"
+        print("MULTI_GPU_CHECK world=%d log_n=%d bytes=%d %s   ecdsa-air bytes=%d %s" % (
+            world, log_n, len(proof), "MATCH" if proof == want else "MISMATCH", len(eproof), "MATCH" if eproof == ewant else "MISMATCH"))
     dist.destroy_process_group()
 
 
