@@ -1,5 +1,6 @@
 // Internal context shared by the translation units of libspg.
 #pragma once
+#include <string.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -21,6 +22,7 @@ struct spg_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host-trace upload pipelined against the LDE (spg_prove with host buffers): copy stream + per-chunk events
+  void* pin = nullptr;              // pinned host staging buffer for the small device->host reads the host waits on (spg_d2h_sync)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[8] = {nullptr};
   cudaEvent_t copy_gate = nullptr;
@@ -110,6 +112,23 @@ static inline cudaError_t spg_scratch(spg_ctx* ctx, int slot, size_t bytes, void
   }
   *out = ctx->scratch_p[slot];
   return cudaSuccess;
+}
+
+// Device -> host copy the caller waits for (Merkle roots, out-of-domain values, openings: every Fiat-Shamir round trip).
+// A copy into pageable memory is staged by the driver and costs tens of microseconds more than one into pinned memory;
+// a proof has ~15 of them on its critical path, so they go through one pinned buffer of the context.
+#define SPG_PIN_BYTES ((size_t)1 << 20)
+static inline cudaError_t spg_d2h_sync(spg_ctx* ctx, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (!ctx->pin && cudaHostAlloc(&ctx->pin, SPG_PIN_BYTES, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->pin = nullptr; }
+  cudaError_t e;
+  if (ctx->pin && bytes <= SPG_PIN_BYTES) {
+    if ((e = cudaMemcpyAsync(ctx->pin, src, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
+    memcpy(dst, ctx->pin, bytes);
+    return cudaSuccess;
+  }
+  if ((e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
 }
 
 #define SPG_LOCK(ctx)                                   \

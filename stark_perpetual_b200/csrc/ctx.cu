@@ -105,6 +105,7 @@ extern "C" void spg_destroy(spg_ctx* ctx) {
   for (void* p : ctx->scratch_p) cudaFree(p);
   for (auto& b : ctx->pool) cudaFree(b.p);
   spg_comm_destroy(ctx);
+  if (ctx->pin) cudaFreeHost(ctx->pin);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
   if (ctx->copy_gate) cudaEventDestroy(ctx->copy_gate);

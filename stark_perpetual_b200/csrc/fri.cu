@@ -296,8 +296,7 @@ int spg_poly_eval_device(spg_ctx* ctx, unsigned log_n, const Fp* const* h_cols, 
   SPG_LAUNCH_CHECK();
   k_poly_eval_final<<<n_items, 256, 0, ctx->stream>>>(dpart.as<Fp>(), nb, dout.as<Fp>());
   SPG_LAUNCH_CHECK();
-  SPG_CUDA(cudaMemcpyAsync(h_out, dout.p, n_items * sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  SPG_CUDA(spg_d2h_sync(ctx, h_out, dout.p, n_items * sizeof(Fp), ctx->stream));
   return SPG_OK;
 }
 

@@ -77,8 +77,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
     }
   } else if (pedersen) {
     for (int l = 0; l < SPG_AIR_LANES; l++)
-      SPG_CUDA(cudaMemcpyAsync(&h_last[l], d_trace + ((size_t)(5 * l) << log_n) + (n - 1), sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
-    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+      SPG_CUDA(spg_d2h_sync(ctx, &h_last[l], d_trace + ((size_t)(5 * l) << log_n) + (n - 1), sizeof(Fp), ctx->stream));
   }
   AirPublic pub;
   std::vector<uint8_t> seed;
@@ -118,8 +117,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
   spg_stage_begin(ctx, ST_MERKLE_T);
   if ((rc = spg_merkle_build_device(ctx, t_lde, C, n, tree_t))) return rc;
   spg_stage_end(ctx, ST_MERKLE_T);
-  SPG_CUDA(cudaMemcpyAsync(root, tree_t + 8 * (2 * n - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  SPG_CUDA(spg_d2h_sync(ctx, root, tree_t + 8 * (2 * n - 2), 32, ctx->stream));
   ch.absorb(root, 32);
   put_bytes(proof, root, 32);
   // ---- 2. composition polynomial on cosets 0, 2, 4, 6; chunk split; chunk LDE; commitment
@@ -153,8 +151,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
   spg_stage_begin(ctx, ST_MERKLE_H);
   if ((rc = spg_merkle_build_device(ctx, h_lde, 4, n, tree_h))) return rc;
   spg_stage_end(ctx, ST_MERKLE_H);
-  SPG_CUDA(cudaMemcpyAsync(root, tree_h + 8 * (2 * n - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  SPG_CUDA(spg_d2h_sync(ctx, root, tree_h + 8 * (2 * n - 2), 32, ctx->stream));
   ch.absorb(root, 32);
   put_bytes(proof, root, 32);
   // ---- 3. out-of-domain sampling
@@ -204,8 +201,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
       const Fp beta = ch.draw_felt();
       if ((rc = spg_fri_fold8_device(ctx, layers[l - 1], log_rows[l - 1], fp_mul(beta, fp_inv(g_l)), layers[l]))) return rc;
       if ((rc = spg_merkle_build_device(ctx, layers[l], 1, (size_t)1 << log_rows[l], trees[l]))) return rc;
-      SPG_CUDA(cudaMemcpyAsync(root, trees[l] + 8 * (((size_t)2 << log_rows[l]) - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
-      SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+      SPG_CUDA(spg_d2h_sync(ctx, root, trees[l] + 8 * (((size_t)2 << log_rows[l]) - 2), 32, ctx->stream));
       ch.absorb(root, 32);
       put_bytes(fri_roots, root, 32);
       for (int k = 0; k < 3; k++) g_l = fp_sqr(g_l);
@@ -216,8 +212,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
     const unsigned lr = log_rows[n_folds];
     const size_t n_last = (size_t)1 << lr;
     std::vector<Fp> vals(8 * n_last), coeffs;
-    SPG_CUDA(cudaMemcpyAsync(vals.data(), layers[n_folds], vals.size() * sizeof(Fp), cudaMemcpyDeviceToHost, ctx->stream));
-    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SPG_CUDA(spg_d2h_sync(ctx, vals.data(), layers[n_folds], vals.size() * sizeof(Fp), ctx->stream));
     if (!spg_fri_last_layer_host(vals, lr, n_folds, coeffs)) {
       ctx->err = "trace does not satisfy the AIR (FRI last layer is not of low degree)";
       return SPG_E_PROOF;
@@ -265,8 +260,7 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
                                        d_open + leaf_off[t], d_open + path_off[t]))) return rc;
     }
     std::vector<uint32_t> open(total_words);
-    SPG_CUDA(cudaMemcpyAsync(open.data(), d_open, total_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SPG_CUDA(spg_d2h_sync(ctx, open.data(), d_open, total_words * 4, ctx->stream));
     const uint8_t* ob = (const uint8_t*)open.data();
     for (unsigned q = 0; q < n_queries; q++)
       for (int t = 0; t < nt; t++) {

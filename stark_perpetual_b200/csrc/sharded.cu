@@ -293,8 +293,7 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     SPG_CUDA(cudaMemcpyAsync(d_roots + 8 * rank, tree + 8 * (2 * lt - 2), 32, cudaMemcpyDeviceToDevice, S));
     if ((r = ag_inplace(ctx, d_roots, 32, S))) return r;
     std::vector<uint8_t> roots(32 * world);
-    SPG_CUDA(cudaMemcpyAsync(roots.data(), d_roots, roots.size(), cudaMemcpyDeviceToHost, S));
-    SPG_CUDA(cudaStreamSynchronize(S));
+    SPG_CUDA(spg_d2h_sync(ctx, roots.data(), d_roots, roots.size(), S));
     top_levels(roots, top);
     memcpy(root, top.back().data(), 32);
     return SPG_OK;
@@ -394,8 +393,7 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
       std::vector<Fp> all((size_t)per_rank * world);
       SPG_CUDA(cudaMemcpyAsync(d_oods + (size_t)rank * per_rank, mine, per_rank * sizeof(Fp), cudaMemcpyHostToDevice, S));
       if ((rc = ag_inplace(ctx, d_oods, per_rank * sizeof(Fp), S))) return rc;
-      SPG_CUDA(cudaMemcpyAsync(all.data(), d_oods, all.size() * sizeof(Fp), cudaMemcpyDeviceToHost, S));
-      SPG_CUDA(cudaStreamSynchronize(S));
+      SPG_CUDA(spg_d2h_sync(ctx, all.data(), d_oods, all.size() * sizeof(Fp), S));
       for (int r = 0; r < world; r++)
         for (int i = 0, k = r; k < SPG_N_OODS; k += world, i++) oods[k] = all[(size_t)r * per_rank + i];
     }
@@ -437,8 +435,7 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
         if ((rc = spg_fri_fold8_device(ctx, layers[l - 1], log_rows[l - 1], fp_mul(beta, fp_inv(g_l)), layers[l]))) return rc;
       }
       if ((rc = spg_merkle_build_device(ctx, layers[l], 1, rows_l, trees[l]))) return rc;
-      SPG_CUDA(cudaMemcpyAsync(root, trees[l] + 8 * (2 * rows_l - 2), 32, cudaMemcpyDeviceToHost, S));
-      SPG_CUDA(cudaStreamSynchronize(S));
+      SPG_CUDA(spg_d2h_sync(ctx, root, trees[l] + 8 * (2 * rows_l - 2), 32, S));
       ch.absorb(root, 32);
       put_bytes(fri_roots, root, 32);
       for (int k = 0; k < 3; k++) g_l = fp_sqr(g_l);
@@ -448,8 +445,7 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     const unsigned lr = log_rows[n_folds];
     const size_t n_last = (size_t)1 << lr;
     std::vector<Fp> vals(8 * n_last), coeffs;
-    SPG_CUDA(cudaMemcpyAsync(vals.data(), layers[n_folds], vals.size() * sizeof(Fp), cudaMemcpyDeviceToHost, S));
-    SPG_CUDA(cudaStreamSynchronize(S));
+    SPG_CUDA(spg_d2h_sync(ctx, vals.data(), layers[n_folds], vals.size() * sizeof(Fp), S));
     if (!spg_fri_last_layer_host(vals, lr, n_folds, coeffs)) {
       ctx->err = "trace does not satisfy the AIR (FRI last layer is not of low degree)";
       return SPG_E_PROOF;
@@ -515,8 +511,7 @@ static int prove_sharded_device(spg_ctx* ctx, Fp* d_cols, const Fp* h_cols, unsi
     if (world > 1)
       SPG_NCCL(g_nccl.AllReduce(d_open, d_open, shared_words * 4, SPG_NCCL_UINT8, SPG_NCCL_SUM, (spg_nccl_comm)ctx->nccl_comm, S));
     std::vector<uint32_t> open(total_words);
-    SPG_CUDA(cudaMemcpyAsync(open.data(), d_open, total_words * 4, cudaMemcpyDeviceToHost, S));
-    SPG_CUDA(cudaStreamSynchronize(S));
+    SPG_CUDA(spg_d2h_sync(ctx, open.data(), d_open, total_words * 4, S));
     const uint8_t* ob = (const uint8_t*)open.data();
     for (unsigned q = 0; q < n_queries; q++)
       for (int t = 0; t < nt; t++) {
