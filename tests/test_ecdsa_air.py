@@ -95,3 +95,26 @@ def test_emulated_ecdsa_air_point_vs_oracle():
     assert len(out) == len(want)
     for k, (o, w) in enumerate(zip(out, want)):
         assert int(o, 16) == w, k
+
+
+def test_emulated_witness_generator_vs_oracle_trace(sigs2):
+    """csrc/ecdsa_air_witness.cuh (Jacobian walks + batched-inversion finish: the three witness kernels' per-thread code) run
+    thread by thread on the host == the oracle twin's trace, cell for cell; an invalid signature, an off-curve key and an
+    out-of-range scalar raise the status bits the C-ABI turns into errors"""
+    exe = _build("emul_ecdsa_air_witness")
+
+    def run(sigs):
+        inp = "".join("%x %x %x %x %x\n" % (z, r, w, key[0], key[1]) for z, r, w, key in sigs)
+        res = subprocess.run([exe, "9"], input=inp, capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr[-500:]
+        lines = res.stdout.split()
+        return int(lines[0]), [int(v, 16) for v in lines[1:]]
+    st, flat = run(sigs2)
+    want = se.gen_trace(9, sigs2)
+    assert st == 0 and len(flat) == 25 * 512
+    for c in range(25):
+        assert flat[512 * c:512 * (c + 1)] == want[c], "column %d" % c
+    z, r, w, key = sigs2[1]
+    assert run([sigs2[0], (z ^ 1, r, w, key)])[0] & 4                                 # verify() == False
+    assert run([sigs2[0], (z, r, w, (key[0], (key[1] + 1) % P))])[0] & 1              # key off the curve
+    assert run([sigs2[0], (z, r + (1 << 251), w, key)])[0] & 1                        # r outside [1, 2^251)
