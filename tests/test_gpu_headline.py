@@ -80,3 +80,33 @@ def test_cpp_sharded_prover_world1_equals_monolithic(ctx, log_n, chain_log):
     assert ctx.prove_sharded(trace, log_n, chain_log, x0, outs, 30) == want
     dev = torch.from_numpy(trace.view(np.int64)).cuda()
     assert ctx.prove_sharded(None, log_n, chain_log, x0, outs, 30, device_ptr=dev.data_ptr()) == want
+
+
+def test_maximum_trace_size_2_23():
+    """The largest trace the interface admits (log_n = 23: 8.4 M rows x 25 columns = 6.7 GB, 54 GB extended; three-pass
+    transforms): witness on the device, one proof, accepted by the oracle verifier.  Runs in its own process (its ~100 GB of
+    device memory are released afterwards); skipped where the device or the host cannot hold it."""
+    import torch
+    free, _total = torch.cuda.mem_get_info()
+    if free < 130e9:
+        pytest.skip("needs ~100 GB of free device memory")
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+from test_gpu_headline import bench_inputs
+from oracle import stark
+import stark_perpetual_b200 as spg
+ctx = spg.Context(0)
+x0, ys = bench_inputs(23)
+trace = ctx.pedersen_chain_trace(23, 2, x0, ys)
+proof = ctx.prove(trace, 23, 2, x0)
+print("PROOF_MS %.1f" % ctx.last_kernel_ms)
+st = stark.verify(proof)
+assert st["log_n"] == 23 and st["x0"] == x0
+print("VERIFIED", len(proof))
+'''
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    if out.returncode != 0 and ("out of memory" in out.stderr or "MemoryError" in out.stderr):
+        pytest.skip("not enough memory for the 2^23 trace: " + out.stderr[-200:])
+    assert out.returncode == 0 and "VERIFIED" in out.stdout, out.stdout[-500:] + out.stderr[-1500:]
+    print(out.stdout.strip())
