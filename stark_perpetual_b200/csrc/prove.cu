@@ -4,6 +4,7 @@
 // Protocol: DESIGN.md "Protocol"; CPU restatement and verifier: oracle/stark.py.  The reference repository has
 // no prover; its only description of the prover boundary is the cairo-run artefact
 // list of src/starkware/cairo/lang/cairo_cmake_rules.cmake:72-110 -- here the "runner output" is the trace.
+#include <stdlib.h>
 #include <string.h>
 
 #include "prove_common.h"
@@ -54,10 +55,15 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
   // ---- public input, channel
   Fp h_last[SPG_AIR_LANES];
   // upload chunks (columns).  A column takes ~0.6 ms to arrive over PCIe and ~1.07 ms to extend, and a chunk's transforms
-  // start when its last byte is there: growing chunks (1, 1, 2, 4, ...) keep the copy just ahead of the kernels, so only
+  // start when its last byte is there: growing chunks (1, 2, 3, 5, ...) keep the copy just ahead of the kernels, so only
   // the first column's upload is exposed (the even 1, 4, 5, 5, 5, 5 split left the GPU idle for 1.4 ms after column 0)
-  const int n_chunks = 7, chunk_begin[8] = {0, 1, 2, 4, 8, 13, 19, 25};
-  static_assert(sizeof(ctx->copy_ev) / sizeof(ctx->copy_ev[0]) >= 7, "one event per chunk");
+  int n_chunks = 6, chunk_begin[9] = {0, 1, 3, 6, 11, 18, 25, 25, 25};     // 1, 2, 3, 5, 7, 7 (measured: tools/gpu_r2_chunks.sh)
+  static_assert(sizeof(ctx->copy_ev) / sizeof(ctx->copy_ev[0]) >= 8, "one event per chunk");
+  if (const char* e = getenv("SPG_UPLOAD_CHUNKS")) {     // A/B knob: comma-separated chunk sizes summing to 25, at most 8
+    int sizes[8], k = 0, sum = 0;
+    for (const char* q = e; *q && k < 8;) { sizes[k] = atoi(q); sum += sizes[k++]; while (*q && *q != ',') q++; if (*q) q++; }
+    if (sum == SPG_AIR_COLS && k >= 1) { n_chunks = k; for (int i = 0; i < k; i++) chunk_begin[i + 1] = chunk_begin[i] + sizes[i]; }
+  }
   static_assert(SPG_AIR_COLS == 25, "chunk table");
   if (h_trace) {
     for (int l = 0; l < SPG_AIR_LANES; l++) h_last[l] = h_trace[((size_t)(5 * l) << log_n) + (n - 1)];   // (unused by kind 2)
