@@ -82,7 +82,7 @@ def _gpu_signatures(ctx, count, seed):
     return msgs, _ints(r), _ints(s), list(zip(_ints(kx), _ints(ky)))
 
 
-@pytest.mark.parametrize("log_n", [14, 17])
+@pytest.mark.parametrize("log_n", [14, 17, 20])
 def test_larger_batches_verify_under_the_oracle(log_n):
     from stark_perpetual_b200.ecdsa_air import prove_signatures
     ctx = _ctx()
