@@ -183,9 +183,13 @@ SPG_HD int ped_ctz(uint32_t w) {
   return __builtin_ctz(w);
 #endif
 }
-SPG_HD bool pedersen_absorb_stream(PedersenAcc& a, const uint32_t (&x)[8], const uint32_t (&y)[8], int n_elems, const APoint* tab) {
+// bits = steps per element (252 for the hash, 251 for mimic_ec_mult_air over the generator table); bits of an element
+// above that are ignored, as the step loops ignore them
+SPG_HD bool pedersen_absorb_stream(PedersenAcc& a, const uint32_t (&x)[8], const uint32_t (&y)[8], int n_elems, const APoint* tab,
+                                   int bits = SPG_HASH_BITS) {
   bool ok = true;
-  const int total = SPG_HASH_BITS * n_elems, last_word = 8 * n_elems - 1;
+  const int total = bits * n_elems, last_word = 8 * n_elems - 1;
+  const uint32_t top_mask = (1u << (bits - 224)) - 1u;
   int s = 0;                      // next step whose collision check is due
   int wi = 0, base = 0;           // current word of the stream and the step index of its bit 0
   uint32_t word = x[0];
@@ -195,7 +199,8 @@ SPG_HD bool pedersen_absorb_stream(PedersenAcc& a, const uint32_t (&x)[8], const
     while (word == 0 && wi < last_word) {
       wi++;
       word = ped_word(x, y, wi);
-      base = (wi >> 3) * SPG_HASH_BITS + (wi & 7) * 32;
+      if ((wi & 7) == 7) word &= top_mask;
+      base = (wi >> 3) * bits + (wi & 7) * 32;
     }
     if (word == 0) break;
     const int sb = base + ped_ctz(word);
