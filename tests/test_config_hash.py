@@ -73,3 +73,26 @@ def test_reference_config_hash_script_runs_unchanged(cases, tmp_path):
                          cwd=str(tmp_path), timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     assert out.stdout == c["output"] + "\n"
+
+
+def test_compat_field_lists_fold_to_the_reference_hashes(cases):
+    """CPU: the compat module's field builders (what the GPU chains are fed) folded with the ORACLE hash give the reference's
+    digests -- the builders are checked without a GPU; the device chain itself is pinned by the hash tests"""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, COMPAT]))
+    code = ("import json, sys\n"
+            "from services.perpetual.public import generate_perpetual_config_hash as g\n"
+            "from oracle.pedersen import pedersen_hash\n"
+            "def fold(vals):\n"
+            "    h = 0\n"
+            "    for v in vals:\n"
+            "        h = pedersen_hash(h, v)\n"
+            "    return h\n"
+            "for c in json.load(open(sys.argv[1]))['cases']:\n"
+            "    cfg = c['config']\n"
+            "    assert fold(g.general_config_fields(cfg)) == int(c['general'], 16)\n"
+            "    for a, h in c['assets'].items():\n"
+            "        assert fold(g.asset_fields(cfg, a)) == int(h, 16), a\n"
+            "print('OK')\n")
+    out = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "tests", "golden", "config_hash_golden.json")], env=env,
+                         capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
