@@ -53,6 +53,7 @@ struct spg_ctx {
   bool ntt_tma_in = true;           // contiguous passes fetch their tile with one cp.async.bulk (TMA); SPG_NTT_TMA=0: per-thread LDG
   bool ntt_tma_strided = true;      // strided whole-workspace passes gather their tile through a tensor map (TMA); SPG_NTT_TMA2D=0 off
   bool ntt_tma_store = true;        // the strided pass also stores through the tensor map; SPG_NTT_TMA2D_STORE=0 off
+  bool deep_pointwise = false;      // SPG_DEEP_POINTWISE=1: combine the 25 extended columns at every point (A/B of fri.cu's coefficient form)
   bool ntt_generic_only = false;    // SPG_NTT_GENERIC=1: route every pass through the generic tile kernel (A/B measurements)
   // growable scratch slots (device), kept until spg_destroy
   void* scratch_p[8] = {nullptr};

@@ -83,6 +83,7 @@ extern "C" int spg_create(int device_ordinal, spg_ctx** out) {
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
   { const char* e = getenv("SPG_NTT_GENERIC"); ctx->ntt_generic_only = e && e[0] == '1'; }
+  { const char* e = getenv("SPG_DEEP_POINTWISE"); ctx->deep_pointwise = e && e[0] == '1'; }
   { const char* e = getenv("SPG_NTT_TMA2D_STORE"); ctx->ntt_tma_store = !(e && e[0] == '0'); }   // default on
   { const char* e = getenv("SPG_NTT_TMA2D"); ctx->ntt_tma_strided = !(e && e[0] == '0'); }   // default on; SPG_NTT_TMA2D=0: per-thread loads
   { const char* e = getenv("SPG_NTT_TMA"); ctx->ntt_tma_in = !(e && e[0] == '0'); }     // default on; SPG_NTT_TMA=0: per-thread loads

@@ -135,10 +135,47 @@ __global__ void __launch_bounds__(256) k_deep(unsigned log_n, const Fp* __restri
   out[idx] = fp_reduce(q);
 }
 
+// A = sum_c gamma^c T_c is a polynomial of degree < N like its summands: when all 8 cosets are on this GPU it is cheaper to
+// combine the 25 COEFFICIENT columns once (25 N products) and extend the one combined column (16 single-column transform
+// launches) than to combine the 25 extended columns at every one of the 8 N points (200 N products, 6.7 GB of reads).
+__global__ void __launch_bounds__(256) k_combine_cols(unsigned log_n, const Fp* __restrict__ cols, const Fp* __restrict__ gamma,
+                                                      Fp* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ((size_t)1 << log_n)) return;
+  Fp a = fp_zero();
+#pragma unroll 5
+  for (int col = 0; col < SPG_AIR_COLS; col++) {
+    a = fp_add_raw(a, fp_mul_lazy(cols[((size_t)col << log_n) + i], gamma[col]));
+    if (col % 12 == 11) a = fp_partial(a);
+  }
+  out[i] = fp_reduce(fp_partial(a));
+}
+// the quotient with A already extended: a_lde[j][i]
+__global__ void __launch_bounds__(256) k_deep_combined(unsigned log_n, const Fp* __restrict__ a_lde, const Fp* __restrict__ h_lde,
+                                                       const Fp* __restrict__ inv2, const Fp* __restrict__ gamma,
+                                                       const Fp* __restrict__ K, Fp* __restrict__ out, int n_cosets) {
+  const size_t n = (size_t)1 << log_n;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_cosets * n) return;
+  const size_t j = idx >> log_n, i = idx & (n - 1);
+  Fp a = fp_reduce(a_lde[idx]), c = fp_zero();
+  Fp b = fp_mul(a, gamma[SPG_AIR_COLS]);             // gamma^25 / w
+  const Fp* hp = h_lde + (j * 4 << log_n) + i;
+#pragma unroll
+  for (int m = 0; m < 4; m++) c = fp_add_raw(c, fp_mul_lazy(hp[(size_t)m << log_n], gamma[2 * SPG_AIR_COLS + m]));
+  c = fp_partial(c);
+  a = fp_sub(a, K[0]); b = fp_sub(b, K[1]); c = fp_sub(c, K[2]);
+  const Fp i1 = inv2[idx], i2 = inv2[(j << log_n) + ((i + n - 1) & (n - 1))], i3 = inv2[idx + (size_t)n_cosets * n];
+  out[idx] = fp_reduce(fp_add(fp_add(fp_mul(a, i1), fp_mul(b, i2)), fp_mul(c, i3)));
+}
+
 // The whole DEEP stage on n_cosets consecutive cosets starting at first_coset: constants on the host, two batched
-// inverse tables, the quotient kernel.  z, gamma, oods[54]: Montgomery; inv_scratch: 2 n_cosets N felts; d_small: >= 64.
+// inverse tables, the quotient kernel.  z, gamma, oods[54]: Montgomery; inv_scratch: 2 n_cosets N felts (3 n_cosets N when
+// t_coef is given); d_small: >= 64.  t_coef (optional): the trace's scaled coefficient columns [25][N] as spg_lde_coeffs
+// leaves them, a_coef: N felts of scratch -- with both and all 8 cosets here, A is combined before the extension.
 int spg_deep_stage_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, int first_coset, int n_cosets,
-                          const Fp& z, const Fp& gamma, const Fp* oods, Fp* inv_scratch, Fp* d_small, Fp* out) {
+                          const Fp& z, const Fp& gamma, const Fp* oods, Fp* inv_scratch, Fp* d_small, Fp* out,
+                          const Fp* t_coef, Fp* a_coef) {
   const int C = SPG_AIR_COLS;
   const Fp wn = spg_host_root_of_unity((int)log_n), wn_inv = fp_inv(wn), z4 = fp_sqr(fp_sqr(z));
   Fp gp[SPG_N_OODS + 5];
@@ -155,8 +192,18 @@ int spg_deep_stage_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const F
   int rc = spg_inv_x_minus_device(ctx, log_n, first_coset, 1, n_cosets, d_small + SPG_N_OODS + 3, 2, inv_scratch);
   if (rc) return rc;
   const size_t total = (size_t)n_cosets << log_n;
-  k_deep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_lde, h_lde, inv_scratch, d_small, d_small + SPG_N_OODS, out,
-                                                                   n_cosets);
+  if (t_coef && a_coef && n_cosets == SPG_BLOWUP && !ctx->deep_pointwise) {
+    const size_t n = (size_t)1 << log_n;
+    Fp* a_lde = inv_scratch + 2 * total;
+    k_combine_cols<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_coef, d_small, a_coef);
+    SPG_LAUNCH_CHECK();
+    if ((rc = spg_lde_cosets_device(ctx, a_coef, log_n, 1, SPG_LOG_BLOWUP, (size_t)first_coset, (size_t)n_cosets, a_lde))) return rc;
+    k_deep_combined<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, a_lde, h_lde, inv_scratch, d_small,
+                                                                             d_small + SPG_N_OODS, out, n_cosets);
+  } else {
+    k_deep<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(log_n, t_lde, h_lde, inv_scratch, d_small, d_small + SPG_N_OODS, out,
+                                                                     n_cosets);
+  }
   SPG_LAUNCH_CHECK();
   return SPG_OK;
 }

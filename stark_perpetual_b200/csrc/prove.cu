@@ -195,7 +195,8 @@ static int prove_device(spg_ctx* ctx, const Fp* d_trace, unsigned log_n, const A
   // ---- 4. DEEP quotient
   const Fp gamma = ch.draw_felt();
   spg_stage_begin(ctx, ST_DEEP);
-  if ((rc = spg_deep_stage_device(ctx, log_n, t_lde, h_lde, 0, 8, z, gamma, oods, inv3, d_small, layer0))) return rc;
+  // cp (4N felts) is free after the chunk split: its first N felts hold the combined coefficient column
+  if ((rc = spg_deep_stage_device(ctx, log_n, t_lde, h_lde, 0, 8, z, gamma, oods, inv3, d_small, layer0, t_coef, cp))) return rc;
   spg_stage_end(ctx, ST_DEEP);
   // ---- 5. FRI
   std::vector<uint8_t> fri_roots;

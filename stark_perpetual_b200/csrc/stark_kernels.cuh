@@ -31,9 +31,11 @@ int spg_merkle_open_device(spg_ctx* ctx, const Fp* table, int ncols, size_t rows
 // out[a][jj][i] = 1 / (x - A[a]),  x = g * w_{8N}^(j0 + jstep*jj + 8 i),  a < n_a, jj < nj, i < N  (Montgomery)
 int spg_inv_x_minus_device(spg_ctx* ctx, unsigned log_n, int j0, int jstep, int nj, const Fp* d_A, int n_a, Fp* out);
 // DEEP quotient stage over n_cosets consecutive cosets of the LDE domain starting at first_coset (tables hold exactly those
-// cosets): out[j][i].  z, gamma, oods[54] Montgomery (host); inv_scratch: device, 2 * n_cosets * N felts; d_small: device, >= 64.
+// cosets): out[j][i].  z, gamma, oods[54] Montgomery (host); inv_scratch: device, 2 * n_cosets * N felts (3 * with t_coef);
+// d_small: device, >= 64.  t_coef / a_coef (optional): combine the coefficient columns before extending (fri.cu).
 int spg_deep_stage_device(spg_ctx* ctx, unsigned log_n, const Fp* t_lde, const Fp* h_lde, int first_coset, int n_cosets,
-                          const Fp& z, const Fp& gamma, const Fp* oods, Fp* inv_scratch, Fp* d_small, Fp* out);
+                          const Fp& z, const Fp& gamma, const Fp* oods, Fp* inv_scratch, Fp* d_small, Fp* out,
+                          const Fp* t_coef = nullptr, Fp* a_coef = nullptr);
 // one FRI fold by 8 of n_cosets consecutive cosets starting at first_coset: in [n_cosets][rows] -> out
 // [n_cosets][rows/8]; x = g_l * w_{8 rows}^(j + 8 i)
 int spg_fri_fold8_device(spg_ctx* ctx, const Fp* in, unsigned log_rows, const Fp& beta_over_g /*beta / g_l, Mont*/, Fp* out,
