@@ -220,12 +220,95 @@ SPG_HD bool pedersen_absorb_stream(PedersenAcc& a, const uint32_t (&x)[8], const
     if (fp_is_zero(fp_sub(fp_mul(tab[s].x, a.zz), a.p.X))) ok = false;
   return ok;
 }
+// ---- the stream with DEFERRED checks.  In pedersen_absorb_stream the check loop between two additions runs as long as the
+// longest gap among a warp's lanes (6.4 steps on average for random scalars, against a mean gap of 2), so two thirds of
+// its lane-slots idle.  Here the partial sums of the last SPG_PED_RING additions are kept (X and Z^2, thread-private), the
+// checks of skipped steps queue up behind a second cursor and every addition serves at most SPG_PED_BUDGET of them: the
+// per-round work is the same for every lane, and a check still compares its step's table point with the partial sum that
+// was current at that step (signature.py:313).  A lane whose queue would outlive the ring (a zero run longer than ~16
+// steps) drains it on the spot.
+// MEASURED (profiles/r2ab6_pedersen_deferred_ab.json): 2^20 random pairs 56.4 -> 54.8 ms, the order pipeline 46.9 -> 49.3 ms
+// -- the kernel is bound by the latency of the dependent addition chain (8 warps per SM), not by the idle lanes of the
+// check loop, so this form is NOT the default (PEDERSEN_STREAM=2 selects it); it stays as the tested record of the attempt.
+#define SPG_PED_RING 8
+#define SPG_PED_BUDGET 2
+struct PedCheckCursor {          // the next step to check: word index, bit position in it, remaining bits of that word
+  int wi, pos, round;            // round = number of set bits below the step = index of the partial sum it is checked against
+  uint32_t bits;
+};
+SPG_HD bool pedersen_absorb_deferred(PedersenAcc& a, const uint32_t (&x)[8], const uint32_t (&y)[8], int n_elems, const APoint* tab,
+                                     int bits = SPG_HASH_BITS) {
+  bool ok = true;
+  const int last_word = 8 * n_elems - 1, top_len = bits - 224;
+  const uint32_t top_mask = (1u << top_len) - 1u;
+  Fp rx[SPG_PED_RING], rz[SPG_PED_RING];
+  int k = 0;                                     // additions done so far = index of the current partial sum
+  rx[0] = a.p.X; rz[0] = a.zz;
+  int wi = 0, base = 0;
+  uint32_t word = x[0];
+  PedCheckCursor c = {0, 0, 0, x[0]};
+  // one queued step: a set-bit step was checked inside its addition (it only advances the round); an unset one is
+  // checked now against the partial sum of its round.  Returns true if a multiplication was spent.
+  auto serve = [&]() -> bool {
+    const int step = (c.wi >> 3) * bits + (c.wi & 7) * 32 + c.pos;
+    bool spent = false;
+    if (c.bits & 1u) c.round++;
+    else {
+      const int slot = c.round & (SPG_PED_RING - 1);
+      if (fp_is_zero(fp_sub(fp_mul(tab[step].x, rz[slot]), rx[slot]))) ok = false;
+      spent = true;
+    }
+    c.bits >>= 1;
+    if (++c.pos == (((c.wi & 7) == 7) ? top_len : 32)) {
+      c.pos = 0;
+      c.wi++;
+      c.bits = c.wi <= last_word ? ped_word(x, y, c.wi) : 0u;
+      if ((c.wi & 7) == 7) c.bits &= top_mask;
+    }
+    return spent;
+  };
+  auto cursor_step = [&]() { return (c.wi >> 3) * bits + (c.wi & 7) * 32 + c.pos; };
+#pragma unroll 1
+  for (;;) {
+#pragma unroll 1
+    while (word == 0 && wi < last_word) {
+      wi++;
+      word = ped_word(x, y, wi);
+      if ((wi & 7) == 7) word &= top_mask;
+      base = (wi >> 3) * bits + (wi & 7) * 32;
+    }
+    if (word == 0) break;
+    const int sb = base + ped_ctz(word);
+    word &= word - 1;
+    // slot (k + 1) mod RING is about to be overwritten: everything still queued against partial sum k + 1 - RING goes first
+#pragma unroll 1
+    while (c.round <= k + 1 - SPG_PED_RING) serve();
+    const APoint q = tab[sb];
+    const Fp u2 = fp_mul(q.x, a.zz);
+    if (fp_is_zero(fp_sub(u2, a.p.X))) ok = false;          // the set-bit step's own check
+    a.p = ec_madd_nocheck(a.p, q, a.zzz, u2);
+    a.zz = fp_sqr(a.p.Z);
+    a.zzz = fp_mul(a.zz, a.p.Z);
+    k++;
+    rx[k & (SPG_PED_RING - 1)] = a.p.X; rz[k & (SPG_PED_RING - 1)] = a.zz;
+    // serve the queue: steps up to sb have their partial sums in the ring
+    int budget = SPG_PED_BUDGET;
+#pragma unroll 1
+    while (budget > 0 && cursor_step() <= sb) if (serve()) budget--;
+  }
+  const int total = bits * n_elems;
+#pragma unroll 1
+  while (cursor_step() < total) serve();
+  return ok;
+}
 #ifndef PEDERSEN_STREAM
-#define PEDERSEN_STREAM 1         // 0: the step-by-step absorption (A/B measurements)
+#define PEDERSEN_STREAM 1         // 0: the step-by-step absorption, 1: set-bit stream, 2: stream with deferred checks
 #endif
 // both elements (n_elems = 2) or x alone (n_elems = 1) into the accumulator
 SPG_HD bool pedersen_absorb_elems(PedersenAcc& a, const uint32_t (&x)[8], const uint32_t (&y)[8], int n_elems, const APoint* tab) {
-#if PEDERSEN_STREAM
+#if PEDERSEN_STREAM == 2
+  return pedersen_absorb_deferred(a, x, y, n_elems, tab);
+#elif PEDERSEN_STREAM
   return pedersen_absorb_stream(a, x, y, n_elems, tab);
 #else
   bool ok = pedersen_absorb(a, x, tab);

@@ -24,6 +24,30 @@ int main() {
   pts.push_back(base(0)); pts.push_back(base(1));
   const int chain[4] = {248, 4, 248, 4};
   for (int k = 0; k < 4; k++) { APoint q = base(2 + k); for (int i = 0; i < chain[k]; i++) { pts.push_back(q); q = ec_affine_double(q); } }
+  // self-test of the "Unhashable input." detection (signature.py:313) in all three absorption forms: the table is doctored so
+  // that a step's point has the x of the partial sum current at that step -- an unset step right at the start, a set-bit
+  // step, an unset step behind a zero run longer than the deferred form's ring, and an unset step after one addition
+  {
+    const APoint s1 = ec_affine_add(pts[0], pts[2]);            // the partial sum after adding table point 0
+    struct Case { int step; uint32_t lo, hi; bool after_add; } cases[] = {
+      {5, 64u, 0u, false}, {5, 32u, 0u, false}, {30, 0u, 256u, false}, {3, 1u | 64u, 0u, true}, {200, 1u, 0u, true}};
+    for (const Case& cs : cases) {
+      std::vector<APoint> tab(pts.begin() + 2, pts.end());
+      tab[cs.step].x = cs.after_add ? s1.x : pts[0].x;
+      uint32_t x[8] = {cs.lo, cs.hi, 0, 0, 0, 0, 0, 0}, y[8] = {3, 0, 0, 0, 0, 0, 0, 0};
+      PedersenAcc a1, a2, a3;
+      a1.init(pts[0]); a2.init(pts[0]); a3.init(pts[0]);
+      bool r1 = pedersen_absorb(a1, x, tab.data());
+      r1 = pedersen_absorb(a1, y, tab.data() + SPG_HASH_BITS) && r1;
+      const bool r2 = pedersen_absorb_stream(a2, x, y, 2, tab.data()), r3 = pedersen_absorb_deferred(a3, x, y, 2, tab.data());
+      if (r1 || r2 || r3) { fprintf(stderr, "collision at step %d not detected: %d %d %d\n", cs.step, r1, r2, r3); return 5; }
+    }
+    // and the undoctored table accepts the same scalars
+    uint32_t x[8] = {1u | 64u, 256u, 0, 0, 0, 0, 0, 0}, y[8] = {3, 0, 0, 0, 0, 0, 0, 0};
+    PedersenAcc a2, a3;
+    a2.init(pts[0]); a3.init(pts[0]);
+    if (!pedersen_absorb_stream(a2, x, y, 2, pts.data() + 2) || !pedersen_absorb_deferred(a3, x, y, 2, pts.data() + 2)) return 6;
+  }
   char a[128], b[128];
   while (scanf("%100s %100s", a, b) == 2) {
     uint64_t xw[4], yw[4];
@@ -39,6 +63,12 @@ int main() {
       PedersenAcc acc2 = acc;
       bool ok2 = pedersen_absorb(acc2, x, pts.data() + 2);
       ok2 = pedersen_absorb(acc2, y, pts.data() + 2 + SPG_HASH_BITS) && ok2;
+      PedersenAcc acc3 = acc;
+      const bool ok3 = pedersen_absorb_deferred(acc3, x, y, 2, pts.data() + 2);
+      if (ok3 != ok2 || (ok3 && !(fp_eq(acc3.p.X, acc2.p.X) && fp_eq(acc3.p.Y, acc2.p.Y) && fp_eq(acc3.p.Z, acc2.p.Z)))) {
+        fprintf(stderr, "deferred / step absorption disagree\n");
+        return 4;
+      }
       bool ok = pedersen_absorb_stream(acc, x, y, 2, pts.data() + 2);
       if (ok != ok2 || (ok && !(fp_eq(acc.p.X, acc2.p.X) && fp_eq(acc.p.Y, acc2.p.Y) && fp_eq(acc.p.Z, acc2.p.Z)))) {
         fprintf(stderr, "stream / step absorption disagree\n");
