@@ -55,7 +55,9 @@ __device__ __forceinline__ void load_canon(const uint64_t* src, uint32_t (&x)[8]
 // chain_len elements per hash unit: h = H(e0, e1); h = H(h, e2); ... (chain_len >= 1; a single element
 // hashes alone like the reference's variadic pedersen_hash(x)).  elems: [n][chain_len] canonical felts.
 #ifndef PEDERSEN_MIN_CTAS
-#define PEDERSEN_MIN_CTAS 1
+#define PEDERSEN_MIN_CTAS 3       // 163 registers, no spills, 12 warps per SM instead of 8 (183 registers): the set-bit walk is bound by
+                                  // the latency of its dependent addition chain -- 2^20 pairs 56.3 -> 52.5 ms; 4 (128 registers, 96 bytes of
+                                  // spills) is as fast at 2^20 but 10 % slower for 1024 pairs (profiles/r2ab6_pedersen_occupancy_ab.json)
 #endif
 #ifndef PEDERSEN_THREADS
 #define PEDERSEN_THREADS 128

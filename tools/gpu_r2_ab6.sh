@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the deferred-check Pedersen absorption (libspg_v2.so, -DPEDERSEN_STREAM=2) against the set-bit stream (libspg.so)
 mkdir -p gpurun_out
-for v in "" _v2; do
+for v in "" ${VARIANT:-_v2}; do
   echo "=== libspg$v.so"
   SPG_LIB=$PWD/stark_perpetual_b200/libspg$v.so timeout 300 python -m pytest tests/test_gpu_pedersen.py -m gpu -x -q 2>&1 | tail -1
   SPG_LIB=$PWD/stark_perpetual_b200/libspg$v.so timeout 600 python - <<'PY' 2>&1 | tail -6
