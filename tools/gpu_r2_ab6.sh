@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for v in "" ${VARIANT:-_v2}; do
   echo "=== libspg$v.so"
-  SPG_LIB=$PWD/stark_perpetual_b200/libspg$v.so timeout 300 python -m pytest tests/test_gpu_pedersen.py -m gpu -x -q 2>&1 | tail -1
+  SPG_LIB=$PWD/stark_perpetual_b200/libspg$v.so timeout 300 python -m pytest tests/test_gpu_pedersen.py tests/test_gpu_ecdsa.py -m gpu -x -q 2>&1 | tail -1
   SPG_LIB=$PWD/stark_perpetual_b200/libspg$v.so timeout 600 python - <<'PY' 2>&1 | tail -6
 import json, os, sys
 sys.path.insert(0, 'tools'); sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
